@@ -1,0 +1,217 @@
+/*
+ * vokselis_rt.h — C ABI of the B200-native volume raycaster (libvokselis_rt.so).
+ *
+ * This is the drop-in boundary for ONE path of pudnax/vokselis: the compute raycast that
+ * `Xor::render` records every frame (reference: examples/xor/main.rs:210-262) and that executes
+ * shaders/raycast_compute.wgsl (entry points `single` :133-137 and `tile` :139-144).
+ *
+ * The reference binds five bind groups and dispatches (examples/xor/raycast.rs:64-81,
+ * shaders/raycast_compute.wgsl:22-33):
+ *   group 0  Uniform   48-B UBO   (src/context/global_ubo.rs:52-65)       -> VkrtUniform
+ *   group 1  Camera   144-B UBO   (src/camera.rs:5-11)                    -> VkrtCameraUniform
+ *   group 2  volume + volume_normal, rgba16float 3-D storage textures
+ *            (examples/xor/xor_compute.rs:93-118)                         -> vkrt_upload_rgba16f
+ *   group 3  out_tex, rgba16float 2-D storage texture
+ *            (src/context/hdr_backbuffer.rs:10-11,48-59)                  -> the context's frame
+ *   group 4  Offset, 8-B read-only storage with dynamic offset
+ *            (examples/xor/main.rs:20-25,77-118)                          -> VkrtOffset
+ * Every entry point below names the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * VkrtStatus; nothing throws or aborts across this boundary; vkrt_last_error() returns a
+ * human-readable message for the last failing call on the calling thread. Host pointers are
+ * borrowed for the duration of the call. A context is bound to one CUDA device and one stream and
+ * must be driven from one host thread at a time. There is NO CPU fallback: if no CUDA device is
+ * usable, vkrt_create fails with VKRT_ERR_CUDA.
+ */
+#ifndef VOKSELIS_RT_H
+#define VOKSELIS_RT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define VKRT_API __declspec(dllexport)
+#else
+#define VKRT_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* Structs with frozen layouts (byte-compatible with the reference's #[repr(C)] Pod structs).   */
+
+/* src/camera.rs:5-11 `CameraUniform` — matrices are column-major (glam `to_cols_array_2d`).
+ * NOTE `inv_proj` is inverse(proj * view), not inverse(proj) (src/camera.rs:164-170). */
+typedef struct VkrtCameraUniform {
+    float view_position[4];
+    float proj_view[16];
+    float inv_proj[16];
+} VkrtCameraUniform; /* 144 bytes */
+
+/* src/context/global_ubo.rs:52-65 `Uniform`. The raycast reads `time` and discards it
+ * (shaders/raycast_compute.wgsl:100); the generator reads `time` (shaders/xor.wgsl:56). */
+typedef struct VkrtUniform {
+    float pos[3];
+    uint32_t frame;
+    float resolution[2];
+    float mouse[2];
+    uint32_t mouse_pressed;
+    float time;
+    float time_delta;
+    float _padding;
+} VkrtUniform; /* 48 bytes */
+
+/* examples/xor/main.rs:20-25 `Offset` — tile origin in pixels, as two f32. */
+typedef struct VkrtOffset {
+    float x;
+    float y;
+} VkrtOffset; /* 8 bytes */
+
+/* ------------------------------------------------------------------------------------------ */
+
+typedef enum VkrtStatus {
+    VKRT_OK = 0,
+    VKRT_ERR_INVALID = -1,   /* bad argument / bad state (the reference would hit a wgpu validation error) */
+    VKRT_ERR_CUDA = -2,      /* CUDA runtime failure (device lost, OOM, no device) */
+    VKRT_ERR_NO_VOLUME = -3, /* render before any upload/generate */
+    VKRT_ERR_UNSUPPORTED = -4
+} VkrtStatus;
+
+/* Which march body runs.
+ *  M0: shaders/raycast_compute.wgsl:62-97 literally — two rgba16f volumes, nearest texel fetch,
+ *      inline shading, initial alpha 0.1.
+ *  M1: scalar volume + transfer function, trilinear; march body and `vertigo` transfer function
+ *      of shaders/raycast_naive.wgsl:96-119 driven by M0's ray generation and box. */
+typedef enum VkrtMode { VKRT_MODE_M0 = 0, VKRT_MODE_M1 = 1 } VkrtMode;
+
+typedef enum VkrtDtype { VKRT_U8 = 0, VKRT_F16 = 1, VKRT_F32 = 2 } VkrtDtype;
+
+/* How the volume is staged in HBM (a B200 design choice; results are identical for LINEAR and
+ * BRICKED; TEXTURE uses hardware filtering: exact for M0 point fetches, 8-bit weights for M1). */
+typedef enum VkrtLayout {
+    VKRT_LAYOUT_LINEAR = 0,  /* as uploaded: x fastest, then y, then z */
+    VKRT_LAYOUT_BRICKED = 1, /* cache-line bricks, see DESIGN.md */
+    VKRT_LAYOUT_TEXTURE = 2  /* cudaArray + tex3D */
+} VkrtLayout;
+
+/* Everything the reference hard-codes as a WGSL literal or Rust const on this path. Defaults
+ * (vkrt_default_params) reproduce the reference exactly. */
+typedef struct VkrtParams {
+    uint32_t struct_size;     /* = sizeof(VkrtParams); for ABI growth */
+    int32_t mode;             /* VkrtMode */
+    float dt_scale;           /* raycast_compute.wgsl:67 `dt_scale` = 1.0 */
+    float dt_floor;           /* raycast_compute.wgsl:68 literal 0.01; M1 default 0 (raycast_naive.wgsl:99) */
+    float alpha_threshold;    /* raycast_compute.wgsl:92 literal 0.95 */
+    float initial_alpha;      /* raycast_compute.wgsl:63 literal 0.1; M1 default 0 (raycast_naive.wgsl:96) */
+    float clear_color[4];     /* raycast_compute.wgsl:118 (0.023, 0.02, 0.02, 0.0) */
+    int32_t tile_size;        /* examples/xor/main.rs:12 TILE_SIZE = 256 */
+    int32_t layout;           /* VkrtLayout */
+    int32_t skip_empty;       /* 1: occupancy-grid empty-space skipping (exact) */
+    int32_t count_samples;    /* 1: accumulate VkrtStats counters (adds one atomic per block) */
+    int32_t m1_srgb;          /* M1 only: apply raycast_naive.wgsl:63-68,121-123 in-shader sRGB */
+    int32_t reserved[7];
+} VkrtParams;
+
+typedef struct VkrtStats {
+    uint64_t rays_hit;          /* pixels whose ray entered the box (t0 < t1) */
+    uint64_t samples_reference; /* loop iterations the reference shader executes (incl. early termination) */
+    uint64_t samples_fetched;   /* iterations that actually fetched texels (after empty-space skipping) */
+    float last_render_ms;       /* CUDA-event time of the last render call's kernels */
+    float _pad;
+} VkrtStats;
+
+typedef struct VkrtContext VkrtContext; /* opaque */
+
+/* ------------------------------------------------------------------------------------------ */
+/* Context — replaces `Context::new` (src/context.rs:71-181) + `HdrBackBuffer::new`
+ * (src/context/hdr_backbuffer.rs:41-87) for this path: picks the device, creates the stream and
+ * the W x H rgba16f frame. The reference hard-wires 1280x720 (hdr_backbuffer.rs:11). */
+VKRT_API int vkrt_create(int device, int width, int height, VkrtContext** out_ctx);
+VKRT_API int vkrt_destroy(VkrtContext* ctx);
+/* Replaces `Context::resize` (src/context.rs:238-249); unlike the reference it recreates the frame. */
+VKRT_API int vkrt_resize(VkrtContext* ctx, int width, int height);
+
+VKRT_API const char* vkrt_last_error(void);
+VKRT_API void vkrt_default_params(int mode, VkrtParams* out);
+VKRT_API int vkrt_set_params(VkrtContext* ctx, const VkrtParams* params);
+VKRT_API int vkrt_get_params(VkrtContext* ctx, VkrtParams* out);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Volume resources.
+ * vkrt_upload_rgba16f replaces the two `Rgba16Float` 3-D textures of
+ * `XorCompute::new_with_module` (examples/xor/xor_compute.rs:93-118): `color` = (r,g,b,alpha),
+ * `normal` = (n.xyz, |n|), each nx*ny*nz texels of 4 halfs, x fastest then y then z. */
+VKRT_API int vkrt_upload_rgba16f(VkrtContext* ctx, const uint16_t* color, const uint16_t* normal,
+                                 int nx, int ny, int nz);
+/* vkrt_upload_scalar replaces `VolumeTexture::new` (src/context/volume_texture.rs:32-59): a
+ * tightly packed scalar grid, bytes_per_row = nx*sizeof(T), rows_per_image = ny. u8 is read as
+ * unorm (R8Unorm); f16/f32 are read as-is. Sampling is linear, clamp-to-edge (:61-66). */
+VKRT_API int vkrt_upload_scalar(VkrtContext* ctx, const void* data, int dtype, int nx, int ny, int nz);
+/* vkrt_generate_xor replaces `XorCompute::record` (examples/xor/xor_compute.rs:188-200), i.e.
+ * shaders/xor.wgsl `cs_main`, writing both rgba16f volumes on the device. `which`: 0 = live
+ * `noise_volume` (:55-61), 1 = the dead bit-pattern `volume` (:46-53). Only `un->time` is read. */
+VKRT_API int vkrt_generate_xor(VkrtContext* ctx, const VkrtUniform* un, int n, int which);
+/* Read the device-resident rgba16f volumes back in the upload layout (tests, screenshots). */
+VKRT_API int vkrt_download_rgba16f(VkrtContext* ctx, uint16_t* color, uint16_t* normal);
+
+/* ------------------------------------------------------------------------------------------ */
+/* The hot path. vkrt_render replaces the compute pass of `Xor::render`
+ * (examples/xor/main.rs:223-254): offset == NULL records `single` over the whole frame
+ * (:226-233); offset != NULL records `tile` for the tile_size^2 tile at that origin (:235-253).
+ * Asynchronous on the context's stream, like a wgpu queue submit. */
+VKRT_API int vkrt_render(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un,
+                         const VkrtOffset* offset);
+/* All `n` tiles of an offset table in ONE launch (the reference loops 18 dispatches,
+ * examples/xor/main.rs:242-253). This is also the sort-first seam: a rank passes its share. */
+VKRT_API int vkrt_render_tiles(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un,
+                               const VkrtOffset* offsets, int n);
+/* The reference's tile table (examples/xor/main.rs:80-95): (w/ts+1)*(h/ts+1) origins, row-major.
+ * Returns the count; writes at most `cap` entries. */
+VKRT_API int vkrt_tile_table(int width, int height, int tile_size, VkrtOffset* out, int cap);
+
+/* Present — replaces the present pass (shaders/present.wgsl:23-35,111-119;
+ * src/context/present_pipeline.rs:123-136): ACES + sRGB of the frame into a W x H RGBA8 buffer. */
+VKRT_API int vkrt_present(VkrtContext* ctx);
+
+/* Result consumers — replace `ScreenshotCtx::capture_frame` (src/context/screenshot.rs:37-77).
+ * Both block until the stream is idle. Rows are top-first, tightly packed. */
+VKRT_API int vkrt_readback(VkrtContext* ctx, uint16_t* rgba16f /* W*H*4 halfs */);
+VKRT_API int vkrt_readback_rgba8(VkrtContext* ctx, uint8_t* rgba8 /* W*H*4 bytes */);
+VKRT_API int vkrt_sync(VkrtContext* ctx);
+
+/* One frame end to end from HOST buffers: camera+uniform H2D, raycast, present, RGBA8 D2H into
+ * the caller's `rgba8` (W*H*4 bytes); blocks until this frame's pixels are there. The _async/_wait
+ * pair does the same through one of two pinned staging slots so that the D2H of frame i overlaps
+ * the raycast of frame i+1 (the reference's Fifo presentation is similarly one frame deep). */
+VKRT_API int vkrt_frame_host(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un,
+                             uint8_t* rgba8);
+VKRT_API int vkrt_frame_host_async(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un,
+                                   int slot /* 0 or 1 */);
+VKRT_API int vkrt_frame_host_wait(VkrtContext* ctx, int slot, uint8_t* rgba8);
+
+/* Device pointers (for zero-copy consumers, P2P and torch.distributed wrapping). */
+VKRT_API void* vkrt_frame_device_ptr(VkrtContext* ctx);       /* W*H rgba16f */
+VKRT_API void* vkrt_frame_rgba8_device_ptr(VkrtContext* ctx); /* W*H rgba8 */
+VKRT_API void* vkrt_stream(VkrtContext* ctx);                 /* cudaStream_t */
+VKRT_API int vkrt_stats(VkrtContext* ctx, VkrtStats* out);    /* synchronises */
+VKRT_API int vkrt_reset_stats(VkrtContext* ctx);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Host-side camera — replaces `Camera::new` + `Camera::get_proj_view_matrix`
+ * (src/camera.rs:93-113,148-171; glam 0.20.5 look_at_rh / perspective_rh / inverse). */
+VKRT_API int vkrt_camera_uniform(float zoom, float pitch, float yaw, const float target[3], float aspect,
+                                 VkrtCameraUniform* out);
+/* src/utils/mod.rs:15-18 */
+VKRT_API uint32_t vkrt_dispatch_optimal(uint32_t len, uint32_t subgroup_size);
+
+#ifdef __cplusplus
+} /* extern "C" */
+static_assert(sizeof(VkrtCameraUniform) == 144, "CameraUniform ABI (src/camera.rs:5-11)");
+static_assert(sizeof(VkrtUniform) == 48, "Uniform ABI (src/context/global_ubo.rs:52-65)");
+static_assert(sizeof(VkrtOffset) == 8, "Offset ABI (examples/xor/main.rs:20-25)");
+#endif
+
+#endif /* VOKSELIS_RT_H */
