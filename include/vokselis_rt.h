@@ -181,6 +181,10 @@ VKRT_API int vkrt_present(VkrtContext* ctx);
 VKRT_API int vkrt_readback(VkrtContext* ctx, uint16_t* rgba16f /* W*H*4 halfs */);
 VKRT_API int vkrt_readback_rgba8(VkrtContext* ctx, uint8_t* rgba8 /* W*H*4 bytes */);
 VKRT_API int vkrt_sync(VkrtContext* ctx);
+/* Validation output (no reference counterpart; the reference cannot report it): after a render with
+ * params.count_samples = 1, one u32 per pixel: bit 31 = the ray entered the box (t0 < t1,
+ * raycast_compute.wgsl:123), bits 0..30 = loop iterations the reference shader executes for it. */
+VKRT_API int vkrt_readback_aux(VkrtContext* ctx, uint32_t* aux /* W*H */);
 
 /* One frame end to end from HOST buffers: camera+uniform H2D, raycast, present, RGBA8 D2H into
  * the caller's `rgba8` (W*H*4 bytes); blocks until this frame's pixels are there. The _async/_wait
@@ -190,7 +194,8 @@ VKRT_API int vkrt_frame_host(VkrtContext* ctx, const VkrtCameraUniform* cam, con
                              uint8_t* rgba8);
 VKRT_API int vkrt_frame_host_async(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un,
                                    int slot /* 0 or 1 */);
-VKRT_API int vkrt_frame_host_wait(VkrtContext* ctx, int slot, uint8_t* rgba8);
+VKRT_API int vkrt_frame_host_wait(VkrtContext* ctx, int slot, uint8_t* rgba8 /* may be NULL */);
+VKRT_API const uint8_t* vkrt_frame_host_slot_ptr(VkrtContext* ctx, int slot); /* pinned staging, valid after _wait */
 
 /* Device pointers (for zero-copy consumers, P2P and torch.distributed wrapping). */
 VKRT_API void* vkrt_frame_device_ptr(VkrtContext* ctx);       /* W*H rgba16f */
@@ -198,6 +203,9 @@ VKRT_API void* vkrt_frame_rgba8_device_ptr(VkrtContext* ctx); /* W*H rgba8 */
 VKRT_API void* vkrt_stream(VkrtContext* ctx);                 /* cudaStream_t */
 VKRT_API int vkrt_stats(VkrtContext* ctx, VkrtStats* out);    /* synchronises */
 VKRT_API int vkrt_reset_stats(VkrtContext* ctx);
+/* kind: 0 none, 1 rgba16f pair, 2 scalar. bricks = 8^3-voxel cells of the occupancy grid. */
+VKRT_API int vkrt_volume_info(VkrtContext* ctx, int* kind, int* dtype, int dims[3], uint64_t* bricks_total,
+                              uint64_t* bricks_occupied);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Host-side camera — replaces `Camera::new` + `Camera::get_proj_view_matrix`

@@ -59,6 +59,8 @@ def lib() -> C.CDLL:
                                          C.POINTER(CameraUniform)]
         L.vko_rays.restype = C.c_int
         L.vko_rays.argtypes = [C.POINTER(CameraUniform), C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]
+        L.vko_naive_fs.restype = C.c_int
+        L.vko_naive_fs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.vko_f32_to_f16.restype = C.c_uint16
         L.vko_f32_to_f16.argtypes = [C.c_float]
         L.vko_f16_to_f32.restype = C.c_float
@@ -158,6 +160,17 @@ def present(frame: np.ndarray) -> np.ndarray:
 def rays(cam: CameraUniform, W: int, H: int, offx: float = 0.0, offy: float = 0.0) -> np.ndarray:
     out = np.empty((H, W, 8), np.float32)
     rc = lib().vko_rays(C.byref(cam), W, H, offx, offy, _ptr(out))
+    assert rc == 0
+    return out
+
+
+def naive_fs(vol_u8, eyes, dirs, nthreads: int = 0) -> np.ndarray:
+    vol_u8 = np.ascontiguousarray(vol_u8, np.uint8)
+    nz, ny, nx = vol_u8.shape
+    eyes = np.ascontiguousarray(eyes, np.float32).reshape(-1, 3)
+    dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+    out = np.zeros((eyes.shape[0], 4), np.float32)
+    rc = lib().vko_naive_fs(_ptr(vol_u8), nx, ny, nz, eyes.shape[0], _ptr(eyes), _ptr(dirs), _ptr(out), nthreads)
     assert rc == 0
     return out
 

@@ -477,6 +477,58 @@ int vko_rays(const VkrtCameraUniform* cam, int W, int H, float offx, float offy,
     return VKRT_OK;
 }
 
+// shaders/raycast_naive.wgsl:83-125 — `fs_main`, literal (box [0,1]^3, p accumulated by += dir*dt,
+// dt from the literal 256, in-shader sRGB). Input per fragment: what vs_main hands over (:40-48),
+// transformed_eye and ray_dir. This is M1's semantic source; M1 itself (march_m1) runs on the
+// compute boundary's rays. out4 = fragment colour.
+int vko_naive_fs(const uint8_t* vol, int nx, int ny, int nz, int count, const float* eye3, const float* dir3, float* out4,
+                 int nthreads) {
+    if (!vol || !eye3 || !dir3 || !out4) return VKRT_ERR_INVALID;
+    VkoVolume V{};
+    V.nx = nx; V.ny = ny; V.nz = nz; V.dtype = VKRT_U8; V.scalar = vol;
+    const int nt = resolve_threads(nthreads);
+    (void)nt;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nt)
+    for (int i = 0; i < count; ++i) {
+        v3 eye = {eye3[i * 3], eye3[i * 3 + 1], eye3[i * 3 + 2]};
+        v3 ray_dir = normalize3(v3{dir3[i * 3], dir3[i * 3 + 1], dir3[i * 3 + 2]});
+        float* o = out4 + i * 4;
+        // intersect_box (:50-61) against [0,1]^3
+        v3 inv = {1.0f / ray_dir.x, 1.0f / ray_dir.y, 1.0f / ray_dir.z};
+        v3 a = (v3{0.0f, 0.0f, 0.0f} - eye) * inv, b = (v3{1.0f, 1.0f, 1.0f} - eye) * inv;
+        float t0 = wmax(wmin(a.x, b.x), wmax(wmin(a.y, b.y), wmin(a.z, b.z)));
+        float t1 = wmin(wmax(a.x, b.x), wmin(wmax(a.y, b.y), wmax(a.z, b.z)));
+        if (t0 > t1) { o[0] = o[1] = o[2] = 0.0f; o[3] = 1.0f; continue; }
+        t0 = wmax(t0, 0.0f);
+        float r = 0.0f, g = 0.0f, bl = 0.0f, al = 0.0f;
+        const float dx = 1.0f / (256.0f * std::fabs(ray_dir.x)), dy = 1.0f / (256.0f * std::fabs(ray_dir.y)),
+                    dz = 1.0f / (256.0f * std::fabs(ray_dir.z));
+        const float dt = 1.0f * wmin(dx, wmin(dy, dz));
+        v3 p = eye + t0 * ray_dir;
+        for (float t = t0; t < t1; t = t + dt) {
+            float s = trilinear(&V, p.x * (float)nx - 0.5f, p.y * (float)ny - 0.5f, p.z * (float)nz - 0.5f);
+            // tex_content = (s, 0, 0, 1): val = .rgb, val_alpha = pow(.a, 2)
+            float val_alpha = std::pow(1.0f, 2.0f);
+            float val = wmin(wmax(0.4f, 0.9f), s);
+            val = wsmoothstep(0.10f, 1.2f, val);
+            const float TAU = 6.28318f;
+            float pr = 0.5f + 0.5f * std::cos(TAU * (1.0f * val + 0.0f));
+            float pg = 0.5f + 0.5f * std::cos(TAU * (1.7f * val + 0.15f));
+            float pb = 0.5f + 0.5f * std::cos(TAU * (0.4f * val + 0.20f));
+            float w = (1.0f - al) * val;
+            float k = 1.0f - val_alpha;
+            r = r + w * pr + 0.1f * 0.01f * k;
+            g = g + w * pg + 0.2f * 0.01f * k;
+            bl = bl + w * pb + 0.3f * 0.01f * k;
+            al = al + (1.0f - al) * val;
+            if (al >= 0.95f) break;
+            p = p + ray_dir * dt;
+        }
+        o[0] = linear_to_srgb_naive(r); o[1] = linear_to_srgb_naive(g); o[2] = linear_to_srgb_naive(bl); o[3] = 1.0f;
+    }
+    return VKRT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // shaders/xor.wgsl — the volume generator.
 namespace {

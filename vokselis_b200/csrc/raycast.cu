@@ -1,0 +1,221 @@
+// raycast.cu — the hot path: one thread per pixel, warp-coherent 8x4 pixel tiles (sm_100a).
+//
+// Replaces shaders/raycast_compute.wgsl entry points `single` (:133-137) and `tile` (:139-144):
+// ray generation + slab test (`render` :99-131, `intersect_box` :42-53), fixed-step march with
+// shading, front-to-back compositing and early ray termination (`get_col2` :62-97). Mode M1 swaps
+// the march body for the scalar/trilinear/transfer-function body of shaders/raycast_naive.wgsl:96-119.
+//
+// B200 mapping: a block is 8x8 pixels = two warps of 8x4 pixels, so the 32 rays of a
+// warp walk through neighbouring voxels and their texel requests coalesce into a handful of 32-B
+// sectors. All tiles of a frame go out in ONE launch (grid.z = tile). Not a contraction: no tensor
+// cores; the limiter is the texel path (TEX/L1 -> L2 -> HBM) and the dependent ALU chain per sample.
+#include "raycast.cuh"
+#include "vkrt_device.cuh"
+
+namespace vkrt {
+
+namespace {
+
+// Value below which the M1 transfer function is exactly transparent (smoothstep(0.1,1.2,min(.9,s)) == 0
+// <=> s <= 0.1f). A brick is marked empty only if every voxel a sample inside it can touch is <= this
+// slightly smaller bound, so fp32 rounding inside any trilinear formula cannot cross 0.1f.
+template <int DTYPE> struct Scalar;
+template <> struct Scalar<VKRT_U8> {
+    using T = uint8_t;
+    static __device__ __forceinline__ float load(const void* p, size_t i) { return (float)__ldg((const uint8_t*)p + i) / 255.0f; }
+};
+template <> struct Scalar<VKRT_F16> {
+    using T = __half;
+    static __device__ __forceinline__ float load(const void* p, size_t i) {
+        return __half2float(__ushort_as_half(__ldg((const unsigned short*)p + i)));
+    }
+};
+template <> struct Scalar<VKRT_F32> {
+    using T = float;
+    static __device__ __forceinline__ float load(const void* p, size_t i) { return __ldg((const float*)p + i); }
+};
+
+__device__ __forceinline__ bool occupied(const RenderArgs& A, int ix, int iy, int iz) {
+    const uint32_t cell = ((uint32_t)(iz >> 3) * (uint32_t)A.nby + (uint32_t)(iy >> 3)) * (uint32_t)A.nbx + (uint32_t)(ix >> 3);
+    return (__ldg(A.occ + (cell >> 5)) >> (cell & 31u)) & 1u;
+}
+
+// ---- texel fetch, M0 (nearest, two rgba16f texels at one integer coordinate) -----------------
+template <int LAYOUT>
+__device__ __forceinline__ void m0_fetch(const RenderArgs& A, int ix, int iy, int iz, bool inb, float4& c, float4& n) {
+    if (LAYOUT == VKRT_LAYOUT_TEXTURE) {
+        // border addressing returns 0 outside: the out-of-range textureLoad definition
+        c = tex3D<float4>(A.tex_a, (float)ix + 0.5f, (float)iy + 0.5f, (float)iz + 0.5f);
+        n = tex3D<float4>(A.tex_b, (float)ix + 0.5f, (float)iy + 0.5f, (float)iz + 0.5f);
+        return;
+    }
+    if (!inb) {
+        c = make_float4(0.f, 0.f, 0.f, 0.f);
+        n = c;
+        return;
+    }
+    if (LAYOUT == VKRT_LAYOUT_BRICKED) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(A.vol_a) + bricked_index(ix, iy, iz, A.nbx, A.nby));
+        c = unpack_rgba16f(make_uint2(v.x, v.y));
+        n = unpack_rgba16f(make_uint2(v.z, v.w));
+    } else {
+        const size_t i = ((size_t)iz * A.ny + iy) * A.nx + ix;
+        c = unpack_rgba16f(__ldg(reinterpret_cast<const uint2*>(A.vol_a) + i));
+        n = unpack_rgba16f(__ldg(reinterpret_cast<const uint2*>(A.vol_b) + i));
+    }
+}
+
+// ---- scalar sample, M1 (linear filter, clamp-to-edge) ----------------------------------------
+template <int LAYOUT, int DTYPE>
+__device__ __forceinline__ float m1_sample(const RenderArgs& A, float qx, float qy, float qz) {
+    if (LAYOUT == VKRT_LAYOUT_TEXTURE) {
+        return tex3D<float>(A.tex_a, qx, qy, qz);  // hardware trilinear, 8-bit weights
+    }
+    const float ux = qx - 0.5f, uy = qy - 0.5f, uz = qz - 0.5f;
+    const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
+    const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+    const int x0 = (int)flx, y0 = (int)fly, z0 = (int)flz;
+    // clamp-to-edge on both taps, like the oracle's scalar_at()
+    const int xa2 = min(max(x0, 0), A.nx - 1), xb2 = min(max(x0 + 1, 0), A.nx - 1);
+    const int ya2 = min(max(y0, 0), A.ny - 1), yb2 = min(max(y0 + 1, 0), A.ny - 1);
+    const int za2 = min(max(z0, 0), A.nz - 1), zb2 = min(max(z0 + 1, 0), A.nz - 1);
+    const size_t sy = (size_t)A.nx, sz = (size_t)A.nx * A.ny;
+    const size_t r00 = za2 * sz + ya2 * sy, r10 = za2 * sz + yb2 * sy, r01 = zb2 * sz + ya2 * sy, r11 = zb2 * sz + yb2 * sy;
+    using S = Scalar<DTYPE>;
+    const float c000 = S::load(A.vol_a, r00 + xa2), c100 = S::load(A.vol_a, r00 + xb2);
+    const float c010 = S::load(A.vol_a, r10 + xa2), c110 = S::load(A.vol_a, r10 + xb2);
+    const float c001 = S::load(A.vol_a, r01 + xa2), c101 = S::load(A.vol_a, r01 + xb2);
+    const float c011 = S::load(A.vol_a, r11 + xa2), c111 = S::load(A.vol_a, r11 + xb2);
+    const float c00 = c000 + fx * (c100 - c000), c10 = c010 + fx * (c110 - c010);
+    const float c01 = c001 + fx * (c101 - c001), c11 = c011 + fx * (c111 - c011);
+    const float c0 = c00 + fy * (c10 - c00), c1 = c01 + fy * (c11 - c01);
+    return c0 + fz * (c1 - c0);
+}
+
+template <int MODE, int LAYOUT, int DTYPE, bool SKIP, bool DBG>
+__global__ void __launch_bounds__(64) raycast_kernel(const __grid_constant__ RenderArgs A) {
+    // ---- which pixel -------------------------------------------------------------------------
+    const uint32_t gx = blockIdx.x * 8u + threadIdx.x, gy = blockIdx.y * 8u + threadIdx.y;
+    float offx = 0.0f, offy = 0.0f;
+    uint32_t px = gx, py = gy;
+    bool valid = true;
+    if (A.n_tiles > 0) {  // `tile` entry: coord = gid + offset; store at gid + u32(offset)
+        const VkrtOffset o = A.offsets[blockIdx.z];
+        offx = o.x;
+        offy = o.y;
+        px = gx + (uint32_t)__float2int_rz(offx);
+        py = gy + (uint32_t)__float2int_rz(offy);
+        valid = gx < (uint32_t)A.tile_size && gy < (uint32_t)A.tile_size;
+    }
+    valid = valid && px < (uint32_t)A.W && py < (uint32_t)A.H;  // out-of-range textureStore is dropped
+
+    // ---- ray ---------------------------------------------------------------------------------
+    f3 eye, dir;
+    gen_ray(A.inv, (float)gx, (float)gy, offx, offy, (float)A.W, (float)A.H, eye, dir);
+    float t0, t1;
+    intersect_box(eye, dir, t0, t1);
+    const bool hit = valid && (t0 < t1);
+    t0 = fmaxf(t0, 0.0f);
+
+    Rgba col;
+    col.r = MODE == VKRT_MODE_M0 ? A.clear[0] : 0.0f;
+    col.g = MODE == VKRT_MODE_M0 ? A.clear[1] : 0.0f;
+    col.b = MODE == VKRT_MODE_M0 ? A.clear[2] : 0.0f;
+    col.a = A.initial_alpha;
+    uint32_t iters = 0, fetched = 0;
+
+    if (hit) {
+        const float dt = step_dt(dir, A.fx, A.fy, A.fz, A.dt_scale, A.dt_floor);
+        for (float t = t0; t < t1; t = xadd(t, dt)) {
+            if (DBG) ++iters;
+            // p = eye + t*dir ; q = (p + 1) * (N/2) — exact, decides the texel
+            f3 p = {xadd(eye.x, xmul(t, dir.x)), xadd(eye.y, xmul(t, dir.y)), xadd(eye.z, xmul(t, dir.z))};
+            const float qx = xmul(xadd(p.x, 1.0f), A.hx), qy = xmul(xadd(p.y, 1.0f), A.hy), qz = xmul(xadd(p.z, 1.0f), A.hz);
+            const int ix = __float2int_rz(qx), iy = __float2int_rz(qy), iz = __float2int_rz(qz);
+            const bool inb = (unsigned)ix < (unsigned)A.nx && (unsigned)iy < (unsigned)A.ny && (unsigned)iz < (unsigned)A.nz;
+            if (SKIP) {
+                // Exact empty-space skipping: a sample in an empty brick (or outside the grid, M0) leaves
+                // colour and alpha bit-identical, so only the t sequence is advanced.
+                if (MODE == VKRT_MODE_M0 ? (!inb || !occupied(A, ix, iy, iz)) : (inb && !occupied(A, ix, iy, iz))) continue;
+            }
+            if (DBG) ++fetched;
+            if (MODE == VKRT_MODE_M0) {
+                float4 c, n;
+                m0_fetch<LAYOUT>(A, ix, iy, iz, inb, c, n);
+                m0_shade(col, c, n, p, A.clear);
+            } else {
+                m1_shade(col, m1_sample<LAYOUT, DTYPE>(A, qx, qy, qz));
+            }
+            if (col.a >= A.alpha_threshold) break;
+        }
+        if (MODE == VKRT_MODE_M1 && A.m1_srgb) {
+            col.r = linear_to_srgb_naive(col.r);
+            col.g = linear_to_srgb_naive(col.g);
+            col.b = linear_to_srgb_naive(col.b);
+        }
+    } else {
+        col.r = A.clear[0];
+        col.g = A.clear[1];
+        col.b = A.clear[2];
+    }
+
+    if (valid) {
+        const size_t o = (size_t)py * A.W + px;
+        A.frame[o] = pack_rgba16f(col.r, col.g, col.b, 1.0f);
+        if (DBG && A.aux) A.aux[o] = hit ? (0x80000000u | iters) : 0u;
+    }
+    if (DBG && A.counters) {
+        const unsigned h = __reduce_add_sync(0xffffffffu, hit ? 1u : 0u);
+        const unsigned it = __reduce_add_sync(0xffffffffu, hit ? iters : 0u);
+        const unsigned fe = __reduce_add_sync(0xffffffffu, hit ? fetched : 0u);
+        if (((threadIdx.y * 8 + threadIdx.x) & 31) == 0) {
+            atomicAdd(A.counters + 0, (unsigned long long)h);
+            atomicAdd(A.counters + 1, (unsigned long long)it);
+            atomicAdd(A.counters + 2, (unsigned long long)fe);
+        }
+    }
+}
+
+template <int MODE, int LAYOUT, int DTYPE>
+cudaError_t launch3(const RenderArgs& A, dim3 grid, cudaStream_t s, bool skip, bool dbg) {
+    const dim3 block(8, 8, 1);
+    if (skip) {
+        if (dbg) raycast_kernel<MODE, LAYOUT, DTYPE, true, true><<<grid, block, 0, s>>>(A);
+        else raycast_kernel<MODE, LAYOUT, DTYPE, true, false><<<grid, block, 0, s>>>(A);
+    } else {
+        if (dbg) raycast_kernel<MODE, LAYOUT, DTYPE, false, true><<<grid, block, 0, s>>>(A);
+        else raycast_kernel<MODE, LAYOUT, DTYPE, false, false><<<grid, block, 0, s>>>(A);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_raycast(const RenderArgs& A, int mode, int layout, int dtype, bool skip, bool dbg, cudaStream_t s) {
+    dim3 grid;
+    if (A.n_tiles > 0) {
+        const unsigned g = (unsigned)((A.tile_size + 7) / 8);
+        grid = dim3(g, g, (unsigned)A.n_tiles);
+    } else {
+        grid = dim3((unsigned)((A.W + 7) / 8), (unsigned)((A.H + 7) / 8), 1);
+    }
+    if (mode == VKRT_MODE_M0) {
+        switch (layout) {
+            case VKRT_LAYOUT_LINEAR: return launch3<VKRT_MODE_M0, VKRT_LAYOUT_LINEAR, 0>(A, grid, s, skip, dbg);
+            case VKRT_LAYOUT_BRICKED: return launch3<VKRT_MODE_M0, VKRT_LAYOUT_BRICKED, 0>(A, grid, s, skip, dbg);
+            case VKRT_LAYOUT_TEXTURE: return launch3<VKRT_MODE_M0, VKRT_LAYOUT_TEXTURE, 0>(A, grid, s, skip, dbg);
+        }
+    } else {
+        if (layout == VKRT_LAYOUT_TEXTURE) return launch3<VKRT_MODE_M1, VKRT_LAYOUT_TEXTURE, 0>(A, grid, s, skip, dbg);
+        if (layout == VKRT_LAYOUT_LINEAR) {
+            switch (dtype) {
+                case VKRT_U8: return launch3<VKRT_MODE_M1, VKRT_LAYOUT_LINEAR, VKRT_U8>(A, grid, s, skip, dbg);
+                case VKRT_F16: return launch3<VKRT_MODE_M1, VKRT_LAYOUT_LINEAR, VKRT_F16>(A, grid, s, skip, dbg);
+                case VKRT_F32: return launch3<VKRT_MODE_M1, VKRT_LAYOUT_LINEAR, VKRT_F32>(A, grid, s, skip, dbg);
+            }
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace vkrt

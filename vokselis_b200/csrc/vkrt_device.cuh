@@ -1,0 +1,154 @@
+// vkrt_device.cuh — device-side building blocks shared by the raycast kernels (sm_100a).
+//
+// Arithmetic policy. Everything that decides WHICH texel a sample reads or WHETHER a
+// ray hits — ray generation, the slab test, the t sequence, the sample position and the voxel
+// index — is written with explicitly rounded intrinsics (__fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn),
+// which nvcc never contracts into FMAs, in exactly the operation order the oracle fixes. Hit masks
+// and voxel indices are therefore bit-identical to the oracle's. Shading and compositing use
+// ordinary fp32 (FMA contraction allowed) and are checked against the stated tolerance.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vokselis_rt.h"
+
+namespace vkrt {
+
+struct f3 {
+    float x, y, z;
+};
+
+// ---- exact helpers ------------------------------------------------------------------------
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float xdot3(f3 a, f3 b) { return xadd(xadd(xmul(a.x, b.x), xmul(a.y, b.y)), xmul(a.z, b.z)); }
+
+// column-major mat4 * (x, y, z, w) with the oracle's summation order ((c0*x + c1*y) + c2*z) + c3*w
+__device__ __forceinline__ float xrow(const float* m, int r, float x, float y, float z, float w) {
+    return xadd(xadd(xadd(xmul(m[r], x), xmul(m[4 + r], y)), xmul(m[8 + r], z)), xmul(m[12 + r], w));
+}
+
+// shaders/raycast_compute.wgsl:102-116 — ray generation (`render`). gx, gy = global_invocation_id.
+__device__ __forceinline__ void gen_ray(const float* inv, float gx, float gy, float offx, float offy, float W, float H,
+                                        f3& eye, f3& dir) {
+    const float cx = xadd(gx, offx), cy = xadd(gy, offy);
+    const float aspect_ratio = xdiv(H, W);
+    const float sx = xsub(xdiv(xmul(2.0f, cx), W), 1.0f);
+    float sy = xsub(xdiv(xmul(2.0f, cy), H), 1.0f);
+    sy = xmul(sy, -aspect_ratio);
+    // screen_point = (sx, sy, 0, 1); screen_tangent = screen_point + (0,0,1,0) = (sx, sy, 1, 1)
+    f3 vp, vt;
+    vp.x = xrow(inv, 0, sx, sy, 0.0f, 1.0f); vp.y = xrow(inv, 1, sx, sy, 0.0f, 1.0f); vp.z = xrow(inv, 2, sx, sy, 0.0f, 1.0f);
+    const float vpw = xrow(inv, 3, sx, sy, 0.0f, 1.0f);
+    vt.x = xrow(inv, 0, sx, sy, 1.0f, 1.0f); vt.y = xrow(inv, 1, sx, sy, 1.0f, 1.0f); vt.z = xrow(inv, 2, sx, sy, 1.0f, 1.0f);
+    const float vtw = xrow(inv, 3, sx, sy, 1.0f, 1.0f);
+    eye.x = xdiv(vp.x, vpw); eye.y = xdiv(vp.y, vpw); eye.z = xdiv(vp.z, vpw);
+    f3 d = {xsub(xdiv(vt.x, vtw), eye.x), xsub(xdiv(vt.y, vtw), eye.y), xsub(xdiv(vt.z, vtw), eye.z)};
+    const float len = __fsqrt_rn(xdot3(d, d));
+    dir.x = xdiv(d.x, len); dir.y = xdiv(d.y, len); dir.z = xdiv(d.z, len);
+}
+
+// shaders/raycast_compute.wgsl:42-53 — slab test against [-1,1]^3 (fminf/fmaxf = WGSL min/max on NVIDIA).
+__device__ __forceinline__ void intersect_box(f3 o, f3 d, float& t0, float& t1) {
+    const float ix = xdiv(1.0f, d.x), iy = xdiv(1.0f, d.y), iz = xdiv(1.0f, d.z);
+    const float ax = xmul(xsub(-1.0f, o.x), ix), ay = xmul(xsub(-1.0f, o.y), iy), az = xmul(xsub(-1.0f, o.z), iz);
+    const float bx = xmul(xsub(1.0f, o.x), ix), by = xmul(xsub(1.0f, o.y), iy), bz = xmul(xsub(1.0f, o.z), iz);
+    t0 = fmaxf(fminf(ax, bx), fmaxf(fminf(ay, by), fminf(az, bz)));
+    t1 = fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz)));
+}
+
+// shaders/raycast_compute.wgsl:65-68 — step length.
+__device__ __forceinline__ float step_dt(f3 dir, float nx, float ny, float nz, float dt_scale, float dt_floor) {
+    const float dx = xdiv(1.0f, xmul(nx, fabsf(dir.x)));
+    const float dy = xdiv(1.0f, xmul(ny, fabsf(dir.y)));
+    const float dz = xdiv(1.0f, xmul(nz, fabsf(dir.z)));
+    return xmul(dt_scale, fmaxf(fminf(dx, fminf(dy, dz)), dt_floor));
+}
+
+// ---- shading (tolerance-checked, FMA allowed) ----------------------------------------------
+__device__ __forceinline__ float smoothstep_f(float e0, float e1, float x) {
+    float t = __saturatef((x - e0) / (e1 - e0));  // saturate maps NaN -> 0 like fmin(fmax(NaN,0),1)
+    return t * t * (3.0f - 2.0f * t);
+}
+
+struct Rgba {
+    float r, g, b, a;
+};
+
+// shaders/raycast_compute.wgsl:74-91 — one sample of `get_col2`. c = volume texel, n = normal texel
+// (n.w unused), p = sample position. clear_color.a == 0 is assumed by the fast path (asserted on the
+// host: with a non-zero clear alpha the generic path below is used).
+__device__ __forceinline__ float m0_alpha(float ca) {
+    // pow(a, 3.0) then smoothstep(0, 0.7, .): x*x*x is within 1 ulp of the exact cube (CUDA powf: 4 ulp).
+    const float a3 = ca * ca * ca;
+    return smoothstep_f(0.0f, 0.7f, a3);
+}
+
+__device__ __forceinline__ void m0_shade(Rgba& col, float4 c, float4 n, f3 p, const float* clear) {
+    const float kL = 0.33333334f;  // normalize(-2,-2,-1) = (-2/3, -2/3, -1/3)
+    const float kP = 0.57735026f;  // normalize(1,1,-1) = (1,1,-1)/sqrt(3)
+    const float shade_s = fmaxf(0.0f, -n.y);  // dot((0,-1,0), n); fmaxf drops NaN
+    const float vol_alpha = m0_alpha(c.w);
+    const float ndl = fmaxf((-2.0f * kL) * n.x + (-2.0f * kL) * n.y + (-kL) * n.z, 0.0f);
+    const float pd = smoothstep_f(0.3f, 1.5f, kP * p.x + kP * p.y - kP * p.z);
+    const float dsc = ndl * pd;
+    const float vr = c.x + 3.0f * dsc, vg = c.y + 0.3f * dsc, vb = c.z + 0.39f * dsc;
+    const float bottom = 0.9f * __saturatef(0.5f - 0.5f * n.y);
+    const float sh_rg = shade_s * 0.8f;                         // mix(shade, 0, 0.2)
+    const float sh_b = shade_s * 0.8f + (bottom * 0.6f) * 0.2f;  // mix(shade, bottom*0.6, 0.2)
+    const float w = (1.0f - col.a) * vol_alpha;
+    const float k = clear[3] * (1.0f - vol_alpha);
+    col.r = col.r + w * vr * sh_rg + clear[0] * k;
+    col.g = col.g + w * vg * sh_rg + clear[1] * k;
+    col.b = col.b + w * vb * sh_b + clear[2] * k;
+    col.a = col.a + w * (1.0f - clear[3]);
+}
+
+// shaders/raycast_naive.wgsl:70-81,106-117 — transfer function + composite of one scalar sample.
+__device__ __forceinline__ float m1_alpha(float s) { return smoothstep_f(0.10f, 1.2f, fminf(0.9f, s)); }
+
+__device__ __forceinline__ void m1_shade(Rgba& col, float s) {
+    const float TAU = 6.28318f;
+    const float v = m1_alpha(s);
+    const float pr = 0.5f + 0.5f * __cosf(TAU * v);
+    const float pg = 0.5f + 0.5f * __cosf(TAU * (1.7f * v + 0.15f));
+    const float pb = 0.5f + 0.5f * __cosf(TAU * (0.4f * v + 0.20f));
+    const float w = (1.0f - col.a) * v;
+    col.r += w * pr;
+    col.g += w * pg;
+    col.b += w * pb;
+    col.a += w;
+}
+
+// shaders/raycast_naive.wgsl:63-68
+__device__ __forceinline__ float linear_to_srgb_naive(float x) {
+    return x <= 0.0031308f ? 12.92f * x : 1.055f * powf(x, 1.0f / 2.4f) - 0.055f;
+}
+
+__device__ __forceinline__ uint2 pack_rgba16f(float r, float g, float b, float a) {
+    __half2 lo = __floats2half2_rn(r, g), hi = __floats2half2_rn(b, a);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    return o;
+}
+__device__ __forceinline__ float4 unpack_rgba16f(uint2 v) {
+    const __half2 lo = *reinterpret_cast<const __half2*>(&v.x), hi = *reinterpret_cast<const __half2*>(&v.y);
+    const float2 a = __half22float2(lo), b = __half22float2(hi);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// ---- bricked layout address --------------------------------------------------
+// M0 interleaved texel = 16 B (colour rgba16f + normal rgba16f). 2x2x2 texels fill one 128-B line;
+// 4x4x4 lines (8^3 voxels, 8 KB) form a brick; bricks are x-fastest. nbx, nby = bricks per axis.
+__device__ __host__ __forceinline__ uint32_t bricked_index(int ix, int iy, int iz, int nbx, int nby) {
+    const uint32_t brick = ((uint32_t)(iz >> 3) * (uint32_t)nby + (uint32_t)(iy >> 3)) * (uint32_t)nbx + (uint32_t)(ix >> 3);
+    const uint32_t line = (((uint32_t)iz >> 1) & 3u) << 4 | (((uint32_t)iy >> 1) & 3u) << 2 | (((uint32_t)ix >> 1) & 3u);
+    const uint32_t in_line = ((uint32_t)iz & 1u) << 2 | ((uint32_t)iy & 1u) << 1 | ((uint32_t)ix & 1u);
+    return (brick << 9) | (line << 3) | in_line;
+}
+
+}  // namespace vkrt

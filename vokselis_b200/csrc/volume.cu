@@ -1,0 +1,189 @@
+// volume.cu — volume staging kernels: bricked re-layout, occupancy grids, and the procedural generator.
+//
+//  * interleave_bricked: builds the B200 layout of DESIGN.md §5 from the upload layout of
+//    examples/xor/xor_compute.rs:93-118 (two rgba16f textures, x fastest).
+//  * occupancy_m0 / occupancy_m1: one bit per 8^3-voxel brick, set when some sample falling in the
+//    brick can change the running colour (exactness argument: DESIGN.md §4.4).
+//  * generate_xor: shaders/xor.wgsl `cs_main` (:69-78) with `noise_volume` (:55-61) or the dead
+//    bit-pattern `volume` (:46-53), writing both rgba16f volumes on the device ("next" row N1).
+#include "raycast.cuh"
+#include "vkrt_device.cuh"
+
+namespace vkrt {
+
+namespace {
+
+__global__ void __launch_bounds__(256) interleave_bricked_kernel(const uint2* __restrict__ color, const uint2* __restrict__ normal,
+                                                                 uint4* __restrict__ out, int nx, int ny, int nz, int nbx, int nby,
+                                                                 size_t total) {
+    const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= total) return;
+    // invert bricked_index(): o = brick<<9 | line<<3 | in_line
+    const uint32_t in_line = (uint32_t)o & 7u, line = ((uint32_t)o >> 3) & 63u;
+    const size_t brick = o >> 9;
+    const int bx = (int)(brick % (size_t)nbx), by = (int)((brick / (size_t)nbx) % (size_t)nby), bz = (int)(brick / ((size_t)nbx * nby));
+    const int ix = bx * 8 + (int)((line & 3u) << 1 | (in_line & 1u));
+    const int iy = by * 8 + (int)(((line >> 2) & 3u) << 1 | ((in_line >> 1) & 1u));
+    const int iz = bz * 8 + (int)(((line >> 4) & 3u) << 1 | ((in_line >> 2) & 1u));
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (ix < nx && iy < ny && iz < nz) {
+        const size_t i = ((size_t)iz * ny + iy) * nx + ix;
+        const uint2 c = __ldg(color + i), n = __ldg(normal + i);
+        v = make_uint4(c.x, c.y, n.x, n.y);
+    }
+    out[o] = v;
+}
+
+// one warp per brick
+__global__ void __launch_bounds__(256) occupancy_m0_kernel(const uint2* __restrict__ color, int nx, int ny, int nz, int nbx, int nby,
+                                                           int nbz, uint32_t* __restrict__ occ) {
+    const uint32_t cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31u;
+    if (cell >= (uint32_t)nbx * nby * nbz) return;
+    const int bx = (int)(cell % (uint32_t)nbx), by = (int)((cell / (uint32_t)nbx) % (uint32_t)nby), bz = (int)(cell / ((uint32_t)nbx * nby));
+    bool any = false;
+    for (int k = (int)lane; k < 512; k += 32) {
+        const int ix = bx * 8 + (k & 7), iy = by * 8 + ((k >> 3) & 7), iz = bz * 8 + (k >> 6);
+        if (ix < nx && iy < ny && iz < nz) {
+            const uint2 c = __ldg(color + ((size_t)iz * ny + iy) * nx + ix);
+            const float a = unpack_rgba16f(c).w;
+            any = any || (m0_alpha(a) != 0.0f);  // the very function the march uses
+        }
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0 && any) atomicOr(occ + (cell >> 5), 1u << (cell & 31u));
+}
+
+template <int DTYPE> __device__ __forceinline__ float load_scalar(const void* p, size_t i);
+template <> __device__ __forceinline__ float load_scalar<VKRT_U8>(const void* p, size_t i) { return (float)__ldg((const uint8_t*)p + i) / 255.0f; }
+template <> __device__ __forceinline__ float load_scalar<VKRT_F16>(const void* p, size_t i) {
+    return __half2float(__ushort_as_half(__ldg((const unsigned short*)p + i)));
+}
+template <> __device__ __forceinline__ float load_scalar<VKRT_F32>(const void* p, size_t i) { return __ldg((const float*)p + i); }
+
+// A sample whose index floor((p+1)*N/2) lies in brick b touches voxels [8b-1, 8b+8] per axis
+// (clamped to the grid). The brick is empty iff all of them are <= M1_EMPTY_MAX.
+#define M1_EMPTY_MAX 0.0999999f
+template <int DTYPE>
+__global__ void __launch_bounds__(256) occupancy_m1_kernel(const void* __restrict__ vol, int nx, int ny, int nz, int nbx, int nby, int nbz,
+                                                           uint32_t* __restrict__ occ) {
+    const uint32_t cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31u;
+    if (cell >= (uint32_t)nbx * nby * nbz) return;
+    const int bx = (int)(cell % (uint32_t)nbx), by = (int)((cell / (uint32_t)nbx) % (uint32_t)nby), bz = (int)(cell / ((uint32_t)nbx * nby));
+    const int x0 = max(bx * 8 - 1, 0), x1 = min(bx * 8 + 8, nx - 1);
+    const int y0 = max(by * 8 - 1, 0), y1 = min(by * 8 + 8, ny - 1);
+    const int z0 = max(bz * 8 - 1, 0), z1 = min(bz * 8 + 8, nz - 1);
+    const int wy = y1 - y0 + 1, wz = z1 - z0 + 1;
+    bool any = false;
+    for (int r = (int)lane; r < wy * wz; r += 32) {
+        const int iy = y0 + r % wy, iz = z0 + r / wy;
+        const size_t row = ((size_t)iz * ny + iy) * nx;
+        for (int ix = x0; ix <= x1; ++ix) {
+            const float v = load_scalar<DTYPE>(vol, row + ix);
+            any = any || !(v <= M1_EMPTY_MAX);  // NaN counts as occupied
+        }
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0 && any) atomicOr(occ + (cell >> 5), 1u << (cell & 31u));
+}
+
+// ---- shaders/xor.wgsl -------------------------------------------------------------------------
+__device__ __forceinline__ float fractf(float x) { return x - floorf(x); }
+__device__ __forceinline__ float hash1(float h) { return fractf(sinf(h) * 43758.5453123f); }  // :18-20
+__device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+__device__ float noise3(float x, float y, float z) {  // :22-33
+    const float px = floorf(x), py = floorf(y), pz = floorf(z);
+    float fx = fractf(x), fy = fractf(y), fz = fractf(z);
+    fx = fx * fx * (3.0f - 2.0f * fx);
+    fy = fy * fy * (3.0f - 2.0f * fy);
+    fz = fz * fz * (3.0f - 2.0f * fz);
+    const float n = px + py * 157.0f + 113.0f * pz;
+    return mixf(mixf(mixf(hash1(n + 0.0f), hash1(n + 1.0f), fx), mixf(hash1(n + 157.0f), hash1(n + 158.0f), fx), fy),
+                mixf(mixf(hash1(n + 113.0f), hash1(n + 114.0f), fx), mixf(hash1(n + 270.0f), hash1(n + 271.0f), fx), fy), fz);
+}
+__device__ float fbm(float x, float y, float z) {  // :35-44
+    float f = 0.5f * noise3(x, y, z);
+    x *= 2.01f; y *= 2.01f; z *= 2.01f;
+    f += 0.25f * noise3(x, y, z);
+    x *= 2.02f; y *= 2.02f; z *= 2.02f;
+    f += 0.125f * noise3(x, y, z);
+    return f;
+}
+__device__ __forceinline__ float smoothstep_gen(float e0, float e1, float x) {
+    float t = fminf(fmaxf((x - e0) / (e1 - e0), 0.0f), 1.0f);
+    return t * t * (3.0f - 2.0f * t);
+}
+// returns (val, alpha): :55-61 noise_volume (which = 0), :46-53 volume (which = 1)
+__device__ float2 gen_volume(float cx, float cy, float cz, float time, int which) {
+    const float posx = (cx + 1.0f) * 32.0f, posy = (cy + sinf(time * 1.0f) * 0.1f) * 32.0f, posz = (cz + 21.0f) * 32.0f;
+    const float len = sqrtf(cx * cx + cy * cy + cz * cz);
+    if (which == 0) {
+        const float val = fbm(posx, posy, posz);
+        return make_float2(val, val * smoothstep_gen(0.5f, 0.25f, len));
+    }
+    const float res = 25.0f;
+    const float val = (float)(__float2int_rz(posx * res) & __float2int_rz(posy * res) & __float2int_rz(posz * res)) / res;
+    return make_float2(val, val * smoothstep_gen(0.7f, 0.0f, len));
+}
+
+__global__ void __launch_bounds__(256) generate_xor_kernel(uint2* __restrict__ color, uint2* __restrict__ normal, int n, float time, int which) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * n * n) return;
+    const int x = (int)(i % (size_t)n), y = (int)((i / (size_t)n) % (size_t)n), z = (int)(i / ((size_t)n * n));
+    const float dims = (float)n;
+    const float cx = ((float)x - dims / 2.0f) / dims, cy = ((float)y - dims / 2.0f) / dims, cz = ((float)z - dims / 2.0f) / dims;
+    const float2 vol = gen_volume(cx, cy, cz, time, which);
+    // gradient (:63-67), eps = 0.0001
+    const float eps = 0.0001f;
+    const float a = vol.y;
+    const float dx = a - gen_volume(cx - eps, cy, cz, time, which).y;
+    const float dy = a - gen_volume(cx, cy - eps, cz, time, which).y;
+    const float dz = a - gen_volume(cx, cy, cz - eps, time, which).y;
+    const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float nx_ = dx / len, ny_ = dy / len, nz_ = dz / len;  // 0/0 = NaN in empty space, like the reference
+    const float nl = sqrtf(nx_ * nx_ + ny_ * ny_ + nz_ * nz_);
+    color[i] = pack_rgba16f(vol.x / 2.0f, vol.x / 2.0f, vol.x / 2.0f, vol.y);
+    normal[i] = pack_rgba16f(nx_, ny_, nz_, nl);
+}
+
+}  // namespace
+
+cudaError_t launch_interleave_bricked(const uint2* color, const uint2* normal, uint4* out, int nx, int ny, int nz, int nbx, int nby,
+                                      int nbz, cudaStream_t s) {
+    const size_t total = (size_t)nbx * nby * nbz * 512;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    interleave_bricked_kernel<<<blocks, 256, 0, s>>>(color, normal, out, nx, ny, nz, nbx, nby, total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_occupancy_m0(const uint2* color, int nx, int ny, int nz, int nbx, int nby, int nbz, uint32_t* occ, cudaStream_t s) {
+    const size_t cells = (size_t)nbx * nby * nbz;
+    cudaError_t e = cudaMemsetAsync(occ, 0, ((cells + 31) / 32) * 4, s);
+    if (e != cudaSuccess) return e;
+    occupancy_m0_kernel<<<(unsigned)((cells + 7) / 8), 256, 0, s>>>(color, nx, ny, nz, nbx, nby, nbz, occ);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_occupancy_m1(const void* scalar, int dtype, int nx, int ny, int nz, int nbx, int nby, int nbz, uint32_t* occ,
+                                cudaStream_t s) {
+    const size_t cells = (size_t)nbx * nby * nbz;
+    cudaError_t e = cudaMemsetAsync(occ, 0, ((cells + 31) / 32) * 4, s);
+    if (e != cudaSuccess) return e;
+    const unsigned blocks = (unsigned)((cells + 7) / 8);
+    switch (dtype) {
+        case VKRT_U8: occupancy_m1_kernel<VKRT_U8><<<blocks, 256, 0, s>>>(scalar, nx, ny, nz, nbx, nby, nbz, occ); break;
+        case VKRT_F16: occupancy_m1_kernel<VKRT_F16><<<blocks, 256, 0, s>>>(scalar, nx, ny, nz, nbx, nby, nbz, occ); break;
+        case VKRT_F32: occupancy_m1_kernel<VKRT_F32><<<blocks, 256, 0, s>>>(scalar, nx, ny, nz, nbx, nby, nbz, occ); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_generate_xor(uint2* color, uint2* normal, int n, float time, int which, cudaStream_t s) {
+    const size_t total = (size_t)n * n * n;
+    generate_xor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(color, normal, n, time, which);
+    return cudaGetLastError();
+}
+
+}  // namespace vkrt

@@ -1,0 +1,47 @@
+// headless.cpp — offscreen harness next to the reference's windowed presenter (src/lib.rs:45-208).
+// Runs the xor example's Demo (examples/xor/main.rs) without a window: generate the volume once,
+// then render `frames` frames of an orbit, print the mean frame time, optionally dump the last frame.
+//   usage: headless [frames=360] [W=1280] [H=720] [single|tile] [out.rgba8]
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "vokselis.hpp"
+
+using namespace vokselis;
+
+struct Xor : Demo {  // examples/xor/main.rs:34-48,50-162,210-262
+    XorCompute xor_texture{256, 0};
+    RaycastPipeline raycast_single{"single"}, raycast_tile{"tile"};
+    bool tile_mode = false;
+    void init(Context& ctx) override { xor_texture.record(ctx); }
+    void render(Context& ctx) override { (tile_mode ? raycast_tile : raycast_single).record(ctx); }
+};
+
+int main(int argc, char** argv) {
+    const unsigned frames = argc > 1 ? (unsigned)atoi(argv[1]) : 360u;
+    const unsigned W = argc > 2 ? (unsigned)atoi(argv[2]) : HdrBackBuffer::DEFAULT_WIDTH;
+    const unsigned H = argc > 3 ? (unsigned)atoi(argv[3]) : HdrBackBuffer::DEFAULT_HEIGHT;
+    try {
+        Context ctx(0, W, H);
+        Xor demo;
+        demo.tile_mode = argc > 4 && strcmp(argv[4], "tile") == 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        run_headless(demo, ctx, frames, [&](Context& c, unsigned i) {
+            c.camera.set_yaw(1.0f + 6.2831853f * (float)i / (float)(frames ? frames : 1));
+        });
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        printf("%u frames %ux%u (%s) in %.3f s -> %.1f frames/s (includes volume generation)\n", frames, W, H,
+               demo.tile_mode ? "tile" : "single", s, frames / s);
+        if (argc > 5) {
+            const auto px = ctx.capture_frame();
+            FILE* f = fopen(argv[5], "wb");
+            if (f) { fwrite(px.data(), 1, px.size(), f); fclose(f); }
+        }
+    } catch (const Error& e) {
+        fprintf(stderr, "vokselis error %d: %s\n", e.code, e.what());
+        return 1;
+    }
+    return 0;
+}

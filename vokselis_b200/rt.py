@@ -1,0 +1,319 @@
+"""ctypes binding of libvokselis_rt.so — the product's C ABI (include/vokselis_rt.h).
+
+There is no fallback: if the shared library is missing, importing a symbol from here raises, and if
+no CUDA device is usable `Context(...)` raises `VokselisError` (VKRT_ERR_CUDA). Names follow the
+reference's host interface (src/lib.rs:13-18): Camera, Context, RaycastPipeline ("single"/"tile"),
+XorCompute, VolumeTexture, dispatch_optimal.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from pathlib import Path
+
+import numpy as np
+
+from . import abi
+from .abi import CameraUniform, Offset, Params, Stats, Uniform
+
+_SO = Path(__file__).resolve().parent / "libvokselis_rt.so"
+
+# Every symbol include/vokselis_rt.h declares (tests check the .so exports all of them).
+EXPORTS = [
+    "vkrt_create", "vkrt_destroy", "vkrt_resize", "vkrt_last_error", "vkrt_default_params", "vkrt_set_params",
+    "vkrt_get_params", "vkrt_upload_rgba16f", "vkrt_upload_scalar", "vkrt_generate_xor", "vkrt_download_rgba16f",
+    "vkrt_render", "vkrt_render_tiles", "vkrt_tile_table", "vkrt_present", "vkrt_readback", "vkrt_readback_rgba8",
+    "vkrt_readback_aux", "vkrt_sync", "vkrt_frame_host", "vkrt_frame_host_async", "vkrt_frame_host_wait",
+    "vkrt_frame_host_slot_ptr", "vkrt_frame_device_ptr", "vkrt_frame_rgba8_device_ptr", "vkrt_stream", "vkrt_stats",
+    "vkrt_reset_stats", "vkrt_volume_info", "vkrt_camera_uniform", "vkrt_dispatch_optimal",
+]
+
+
+class VokselisError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library; raises loudly when it has not been built (no CPU fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _SO.exists():
+        raise ImportError(f"{_SO} is missing: build it with `make` (or __graft_entry__.build()). "
+                          "vokselis_b200 has no CPU fallback.")
+    L = C.CDLL(str(_SO))
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    sig = {
+        "vkrt_create": (ci, [ci, ci, ci, C.POINTER(vp)]),
+        "vkrt_destroy": (ci, [vp]),
+        "vkrt_resize": (ci, [vp, ci, ci]),
+        "vkrt_last_error": (C.c_char_p, []),
+        "vkrt_default_params": (None, [ci, C.POINTER(Params)]),
+        "vkrt_set_params": (ci, [vp, C.POINTER(Params)]),
+        "vkrt_get_params": (ci, [vp, C.POINTER(Params)]),
+        "vkrt_upload_rgba16f": (ci, [vp, vp, vp, ci, ci, ci]),
+        "vkrt_upload_scalar": (ci, [vp, vp, ci, ci, ci, ci]),
+        "vkrt_generate_xor": (ci, [vp, C.POINTER(Uniform), ci, ci]),
+        "vkrt_download_rgba16f": (ci, [vp, vp, vp]),
+        "vkrt_render": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), C.POINTER(Offset)]),
+        "vkrt_render_tiles": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp, ci]),
+        "vkrt_tile_table": (ci, [ci, ci, ci, vp, ci]),
+        "vkrt_present": (ci, [vp]),
+        "vkrt_readback": (ci, [vp, vp]),
+        "vkrt_readback_rgba8": (ci, [vp, vp]),
+        "vkrt_readback_aux": (ci, [vp, vp]),
+        "vkrt_sync": (ci, [vp]),
+        "vkrt_frame_host": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp]),
+        "vkrt_frame_host_async": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), ci]),
+        "vkrt_frame_host_wait": (ci, [vp, ci, vp]),
+        "vkrt_frame_host_slot_ptr": (vp, [vp, ci]),
+        "vkrt_frame_device_ptr": (vp, [vp]),
+        "vkrt_frame_rgba8_device_ptr": (vp, [vp]),
+        "vkrt_stream": (vp, [vp]),
+        "vkrt_stats": (ci, [vp, C.POINTER(Stats)]),
+        "vkrt_reset_stats": (ci, [vp]),
+        "vkrt_volume_info": (ci, [vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci * 3), C.POINTER(C.c_uint64),
+                                  C.POINTER(C.c_uint64)]),
+        "vkrt_camera_uniform": (ci, [cf, cf, cf, C.POINTER(cf * 3), cf, C.POINTER(CameraUniform)]),
+        "vkrt_dispatch_optimal": (C.c_uint32, [C.c_uint32, C.c_uint32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise VokselisError(rc, (lib().vkrt_last_error() or b"").decode(errors="replace"))
+
+
+def _vp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def dispatch_optimal(length: int, subgroup_size: int) -> int:
+    """src/utils/mod.rs:15-18"""
+    return int(lib().vkrt_dispatch_optimal(length, subgroup_size))
+
+
+def default_params(mode: int = abi.MODE_M0) -> Params:
+    p = Params()
+    lib().vkrt_default_params(mode, C.byref(p))
+    return p
+
+
+def tile_table(width: int, height: int, tile_size: int = 256) -> np.ndarray:
+    """The reference's offset table (examples/xor/main.rs:80-95) as float32 [n, 2]."""
+    n = lib().vkrt_tile_table(width, height, tile_size, None, 0)
+    if n < 0:
+        _check(n)
+    out = np.zeros((n, 2), np.float32)
+    lib().vkrt_tile_table(width, height, tile_size, _vp(out), n)
+    return out
+
+
+class Camera:
+    """Orbit camera, src/camera.rs:75-171 (math runs in the library's C++ host layer)."""
+
+    ZFAR, ZNEAR, FOVY = 100.0, 0.1, math.pi / 2.0
+
+    def __init__(self, zoom: float, pitch: float, yaw: float, target=(0.0, 0.0, 0.0), aspect: float = 16 / 9):
+        self.zoom, self.pitch, self.yaw, self.target, self.aspect = zoom, pitch, yaw, tuple(target), aspect
+        self.updated = False
+
+    def set_zoom(self, zoom: float):
+        self.zoom = min(max(zoom, 0.3), self.ZFAR / 2.0)
+        self.updated = True
+
+    def add_zoom(self, delta: float):
+        self.set_zoom(self.zoom + delta)
+
+    def set_pitch(self, pitch: float):
+        eps = float(np.finfo(np.float32).eps)
+        self.pitch = min(max(pitch, -math.pi / 2.0 + eps), math.pi / 2.0 - eps)
+        self.updated = True
+
+    def add_pitch(self, delta: float):
+        self.set_pitch(self.pitch + delta)
+
+    def set_yaw(self, yaw: float):
+        self.yaw = yaw
+        self.updated = True
+
+    def add_yaw(self, delta: float):
+        self.set_yaw(self.yaw + delta)
+
+    def set_aspect(self, width: int, height: int):
+        self.aspect = width / height
+        self.updated = True
+
+    def get_proj_view_matrix(self) -> CameraUniform:
+        out = CameraUniform()
+        t = (C.c_float * 3)(*self.target)
+        _check(lib().vkrt_camera_uniform(self.zoom, self.pitch, self.yaw, C.byref(t), self.aspect, C.byref(out)))
+        return out
+
+
+class Context:
+    """Device + stream + rgba16f frame: the part of src/context.rs the raycast path needs."""
+
+    def __init__(self, device: int = 0, width: int = 1280, height: int = 720):
+        self._h = C.c_void_p()
+        _check(lib().vkrt_create(device, width, height, C.byref(self._h)))
+        self.width, self.height, self.device = width, height, device
+        self.global_uniform = Uniform.default()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().vkrt_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- params ---------------------------------------------------------------------------
+    def set_params(self, p: Params):
+        _check(lib().vkrt_set_params(self._h, C.byref(p)))
+
+    def get_params(self) -> Params:
+        p = Params()
+        _check(lib().vkrt_get_params(self._h, C.byref(p)))
+        return p
+
+    def resize(self, width: int, height: int):
+        _check(lib().vkrt_resize(self._h, width, height))
+        self.width, self.height = width, height
+
+    # -- volumes --------------------------------------------------------------------------
+    def upload_rgba16f(self, color: np.ndarray, normal: np.ndarray):
+        color = np.ascontiguousarray(color).view(np.uint16)
+        normal = np.ascontiguousarray(normal).view(np.uint16)
+        if color.shape != normal.shape or color.ndim != 4 or color.shape[3] != 4:
+            raise ValueError("color/normal must be [nz, ny, nx, 4] half arrays")
+        nz, ny, nx = color.shape[:3]
+        _check(lib().vkrt_upload_rgba16f(self._h, _vp(color), _vp(normal), nx, ny, nz))
+
+    def upload_scalar(self, vol: np.ndarray):
+        vol = np.ascontiguousarray(vol)
+        dt = {np.dtype(np.uint8): abi.DTYPE_U8, np.dtype(np.float16): abi.DTYPE_F16,
+              np.dtype(np.float32): abi.DTYPE_F32}.get(vol.dtype)
+        if dt is None or vol.ndim != 3:
+            raise ValueError("scalar volume must be [nz, ny, nx] uint8/float16/float32")
+        nz, ny, nx = vol.shape
+        _check(lib().vkrt_upload_scalar(self._h, _vp(vol), dt, nx, ny, nz))
+
+    def generate_xor(self, n: int = 256, which: int = 0, uniform: Uniform | None = None):
+        un = uniform if uniform is not None else self.global_uniform
+        _check(lib().vkrt_generate_xor(self._h, C.byref(un), n, which))
+
+    def download_rgba16f(self):
+        kind, dims = C.c_int(), (C.c_int * 3)()
+        _check(lib().vkrt_volume_info(self._h, C.byref(kind), None, C.byref(dims), None, None))
+        nx, ny, nz = dims[0], dims[1], dims[2]
+        color = np.empty((nz, ny, nx, 4), np.uint16)
+        normal = np.empty((nz, ny, nx, 4), np.uint16)
+        _check(lib().vkrt_download_rgba16f(self._h, _vp(color), _vp(normal)))
+        return color, normal
+
+    def volume_info(self) -> dict:
+        kind, dtype, dims = C.c_int(), C.c_int(), (C.c_int * 3)()
+        tot, occ = C.c_uint64(), C.c_uint64()
+        _check(lib().vkrt_volume_info(self._h, C.byref(kind), C.byref(dtype), C.byref(dims), C.byref(tot), C.byref(occ)))
+        return {"kind": kind.value, "dtype": dtype.value, "dims": tuple(dims), "bricks_total": tot.value,
+                "bricks_occupied": occ.value}
+
+    # -- the hot path ---------------------------------------------------------------------
+    def render(self, cam: CameraUniform, offset=None, uniform: Uniform | None = None):
+        un = uniform if uniform is not None else self.global_uniform
+        off = None
+        if offset is not None:
+            off = Offset(float(offset[0]), float(offset[1]))
+        _check(lib().vkrt_render(self._h, C.byref(cam), C.byref(un), C.byref(off) if off is not None else None))
+
+    def render_tiles(self, cam: CameraUniform, offsets, uniform: Uniform | None = None):
+        un = uniform if uniform is not None else self.global_uniform
+        offs = np.ascontiguousarray(np.asarray(offsets, np.float32).reshape(-1, 2))
+        _check(lib().vkrt_render_tiles(self._h, C.byref(cam), C.byref(un), _vp(offs), offs.shape[0]))
+
+    def present(self):
+        _check(lib().vkrt_present(self._h))
+
+    def sync(self):
+        _check(lib().vkrt_sync(self._h))
+
+    def readback(self) -> np.ndarray:
+        out = np.empty((self.height, self.width, 4), np.uint16)
+        _check(lib().vkrt_readback(self._h, _vp(out)))
+        return out
+
+    def readback_rgba8(self) -> np.ndarray:
+        out = np.empty((self.height, self.width, 4), np.uint8)
+        _check(lib().vkrt_readback_rgba8(self._h, _vp(out)))
+        return out
+
+    def readback_aux(self) -> np.ndarray:
+        out = np.empty((self.height, self.width), np.uint32)
+        _check(lib().vkrt_readback_aux(self._h, _vp(out)))
+        return out
+
+    def frame_host(self, cam: CameraUniform, out: np.ndarray | None = None, uniform: Uniform | None = None) -> np.ndarray:
+        un = uniform if uniform is not None else self.global_uniform
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.uint8)
+        _check(lib().vkrt_frame_host(self._h, C.byref(cam), C.byref(un), _vp(out)))
+        return out
+
+    def frame_host_async(self, cam: CameraUniform, slot: int, uniform: Uniform | None = None):
+        un = uniform if uniform is not None else self.global_uniform
+        _check(lib().vkrt_frame_host_async(self._h, C.byref(cam), C.byref(un), slot))
+
+    def frame_host_wait(self, slot: int, out: np.ndarray | None = None):
+        _check(lib().vkrt_frame_host_wait(self._h, slot, _vp(out) if out is not None else None))
+
+    def stats(self) -> Stats:
+        st = Stats()
+        _check(lib().vkrt_stats(self._h, C.byref(st)))
+        return st
+
+    def reset_stats(self):
+        _check(lib().vkrt_reset_stats(self._h))
+
+    @property
+    def frame_device_ptr(self) -> int:
+        return int(lib().vkrt_frame_device_ptr(self._h) or 0)
+
+    @property
+    def stream(self) -> int:
+        return int(lib().vkrt_stream(self._h) or 0)
+
+
+class RaycastPipeline:
+    """examples/xor/raycast.rs `RaycastPipeline` with its entry point ("single" | "tile")."""
+
+    def __init__(self, entry_point: str):
+        if entry_point not in ("single", "tile"):
+            raise VokselisError(abi.ERR_INVALID, f"unknown entry point: {entry_point}")
+        self.entry_point = entry_point
+
+    def record(self, ctx: Context, cam: CameraUniform):
+        """What `Xor::render` records for this pipeline (examples/xor/main.rs:223-254)."""
+        if self.entry_point == "single":
+            ctx.render(cam)
+        else:
+            ctx.render_tiles(cam, tile_table(ctx.width, ctx.height, ctx.get_params().tile_size))
