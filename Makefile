@@ -11,7 +11,7 @@ CU := $(SRC)/raycast.cu $(SRC)/volume.cu $(SRC)/present.cu $(SRC)/api.cu
 CUO := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(CU))
 HDR := $(SRC)/raycast.cuh $(SRC)/vkrt_device.cuh include/vokselis_rt.h vokselis_b200/host/vokselis.hpp
 
-all: $(LIB) build/headless
+all: $(LIB) build/headless build/microbench
 
 $(OBJ)/%.o: $(SRC)/%.cu $(HDR)
 	@mkdir -p $(OBJ)
@@ -27,6 +27,10 @@ $(LIB): $(CUO) $(OBJ)/camera.o
 build/headless: vokselis_b200/host/headless.cpp $(LIB) $(HDR)
 	@mkdir -p build
 	$(HOSTCXX) -O2 -std=c++17 -Wall -Wextra $< -o $@ -Lvokselis_b200 -lvokselis_rt -Wl,-rpath,'$$ORIGIN/../vokselis_b200'
+
+build/microbench: bench/microbench.cu
+	@mkdir -p build
+	$(NVCC) -O3 -std=c++17 $(ARCH) -ccbin $(HOSTCXX) -o $@ $<
 
 oracle:
 	$(MAKE) -C oracle all

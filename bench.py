@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""bench.py — the judged benchmark of the raycast hot path (contract: see the task brief).
+
+Workload (BASELINE.json configs[1]): the `xor` procedural volume, 256^3 uint8, rendered at 1920x1080
+over an orbit camera sweep of 360 frames (yaw_i = 1 + 2*pi*i/360, pitch -0.5, zoom 3, the xor
+example's camera, examples/xor/main.rs:273-279) in mode M1 (scalar volume, trilinear, `vertigo`
+transfer function, early ray termination, exact empty-space skipping). One STEP = one frame of the
+orbit. `value` = frames/s with the volume resident in HBM, timed per frame with CUDA events on the
+context's own stream, L2 flushed (a 256 MiB write) between timed frames. `e2e` = the same metric
+through the C ABI with HOST buffers (camera in, presented RGBA8 frame out into pinned host memory).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+--impl reference times the CPU restatement of the reference (the oracle port; the reference itself
+needs Rust + wgpu + Vulkan, none of which exist here) on all host cores, on the same workload.
+N > 1 (torchrun): image tiles are sharded sort-first across ranks and written into rank 0's frame.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+W, H = 1920, 1080
+NVOL = 256
+ORBIT = 360
+METRIC = "frames/s (xor 256^3 u8 @1920x1080, orbit sweep)"
+WORKLOAD = "configs[1]: xor procedural volume 256^3 uint8 at 1920x1080, orbit camera sweep of 360 frames, mode M1 (trilinear + vertigo TF + ERT + exact empty-space skipping)"
+
+
+def orbit_camera(rt_or_oracle, i: int):
+    yaw = 1.0 + 2.0 * math.pi * (i % ORBIT) / ORBIT
+    return (3.0, -0.5, yaw, (0.0, 0.0, 0.0), W / H)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (profiling guide's clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks() -> dict:
+    peaks = {"hbm_gbs": 6650.0, "hbm_source": "fallback (B200_PROFILING.md)"}
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            peaks["hbm_gbs"] = float(json.loads(p.read_text())["hbm_gbs"])
+            peaks["hbm_source"] = "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    m = ROOT / "profiles" / "microbench_r01.json"
+    if m.exists():
+        try:
+            peaks["micro"] = json.loads(m.read_text())
+        except Exception:
+            pass
+    return peaks
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, tiles_per_step: int = 4) -> dict:
+    """The reference's CPU arm: oracle port of the M1 march on all host cores. Each step renders a
+    stratified 1/36 sample of one orbit frame (4 of 144 tiles of 160x120 px... see `sample`)."""
+    from oracle import binding as ob
+    from vokselis_b200 import abi, volumes
+
+    vol = volumes.xor_u8(NVOL)
+    p = abi.default_params(abi.MODE_M1)
+    ts = 120
+    p.tile_size = ts
+    cols, rows = W // ts, H // ts  # 16 x 9 = 144 tiles cover 1920x1080 exactly
+    ntiles = cols * rows
+    stride = ntiles // tiles_per_step
+    frame = np.zeros((H, W, 4), np.uint16)
+    cores = ob.num_threads()
+
+    def step(i):
+        cam = ob.camera_uniform(*orbit_camera(None, i))
+        ids = [(i * 7 + k * stride) % ntiles for k in range(tiles_per_step)]
+        offs = np.array([[(t % cols) * ts, (t // cols) * ts] for t in ids], np.float32)
+        _, _, st = ob.render(p, cam, W, H, scalar=vol, offsets=offs, frame=frame, want_aux=False)
+        return st.samples_reference
+
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    samples = 0
+    for i in range(steps):
+        samples += step(warmup + i)
+    dt = time.perf_counter() - t0
+    frames_equiv = steps * tiles_per_step / ntiles
+    return {"fps": frames_equiv / dt, "seconds": dt, "samples_per_s": samples / dt, "cores": cores,
+            "sample": f"{steps} steps x {tiles_per_step} of {ntiles} tiles ({ts}x{ts} px, stratified, rotating with the orbit) of the 1920x1080 frame "
+                      f"= {frames_equiv:.2f} frame-equivalents in {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = cpu_reference_run(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "arm": "CPU restatement of the reference shader (oracle port, OpenMP) — the Rust/wgpu reference "
+                   "cannot be built in this image; substitute for wgpu-on-lavapipe", "step": "bounded sample of one frame, see cpu_baseline.sample"},
+        "ray_samples_per_s": r["samples_per_s"],
+        "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from vokselis_b200 import abi, rt, volumes
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rt.lib()  # fail loudly if the CUDA library is missing
+    K, Wm = args.steps, args.warmup
+    peaks = load_peaks()
+
+    vol = volumes.xor_u8(NVOL)
+    cams = [rt.Camera(*orbit_camera(rt, i)).get_proj_view_matrix() for i in range(ORBIT)]
+    ctx = rt.Context(local, W, H)
+    ctx.upload_scalar(vol)
+    p = rt.default_params(abi.MODE_M1)
+    p.skip_empty = 1
+    p.layout = abi.LAYOUT_LINEAR
+    ctx.set_params(p)
+
+    if world > 1:
+        from vokselis_b200 import sortfirst
+
+        group = sortfirst.SortFirstGroup(ctx, rank, world, tile=120)
+        render = group.render
+    else:
+        group = None
+        render = ctx.render
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- sample statistics of the workload (untimed, DBG kernel) -------------------------------
+    samples_ref = samples_fetched = 0
+    if rank == 0:
+        q = rt.default_params(abi.MODE_M1)
+        q.skip_empty, q.count_samples = 1, 1
+        ctx.set_params(q)
+        probe = list(range(0, ORBIT, 30))
+        ctx.reset_stats()
+        for i in probe:
+            ctx.render(cams[i])
+        st = ctx.stats()
+        samples_ref = st.samples_reference / len(probe)
+        samples_fetched = st.samples_fetched / len(probe)
+        ctx.set_params(p)
+
+    # ---- timed: device time per frame, L2 flushed between frames -------------------------------
+    ctx.timing_enable(max(K, 1))
+    for i in range(Wm):
+        ctx.flush_l2()
+        render(cams[i % ORBIT])
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    t_wall = time.perf_counter()
+    for i in range(K):
+        ctx.flush_l2()
+        render(cams[(Wm + i) % ORBIT])
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    frame_ms = ctx.timing_read(K).astype(np.float64) if group is None else group.frame_ms(K)
+    total_ms = float(frame_ms.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    fps = K / (total_ms * 1e-3)
+
+    # warm-L2 variant (steady-state orbit, no flush), device-timed the same way
+    for i in range(K):
+        render(cams[(Wm + i) % ORBIT])
+    barrier()
+    warm_ms = ctx.timing_read(K).astype(np.float64) if group is None else group.frame_ms(K)
+    clock_info = clocks.stop() if rank == 0 else None
+
+    # ---- e2e through the C ABI with host buffers -----------------------------------------------
+    e2e = None
+    if world == 1:
+        out = np.empty((H, W, 4), np.uint8)
+        for i in range(min(Wm, 5)):
+            ctx.frame_host(cams[i], out)
+        tot = 0.0
+        for i in range(K):
+            ctx.flush_l2()
+            ctx.sync()
+            t0 = time.perf_counter()
+            ctx.frame_host(cams[(Wm + i) % ORBIT], out)  # camera H2D (kernel args) -> raycast -> present -> RGBA8 D2H, blocking
+            tot += time.perf_counter() - t0
+        e2e_fps = K / tot
+        # pipelined (two slots), warm L2: D2H of frame i overlaps the raycast of frame i+1
+        ctx.sync()
+        t0 = time.perf_counter()
+        for i in range(K):
+            s = i & 1
+            if i >= 2:
+                ctx.frame_host_wait(s, out)
+            ctx.frame_host_async(cams[(Wm + i) % ORBIT], s)
+        for i in range(max(K - 2, 0), K):
+            ctx.frame_host_wait(i & 1, out)
+        pipe_fps = K / (time.perf_counter() - t0)
+        e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 144 + 48, "d2h_bytes_per_step": W * H * 4,
+               "how": "vkrt_frame_host per frame, blocking, L2 flushed before each frame (flush untimed), wall clock",
+               "pipelined_warm_l2": pipe_fps}
+    else:
+        e2e = group.e2e(cams, K, Wm)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_reference_run(steps=36, warmup=2, tiles_per_step=8)
+        cpu = {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "ray_samples_per_s": r["samples_per_s"],
+               "note": "CPU restatement of the reference shader (oracle port) — substitute for wgpu/lavapipe, which cannot be installed here"}
+
+    if rank == 0:
+        ms = total_ms / K
+        # roofline of the dominant kernel (raycast_kernel<M1,...>): algorithmic bytes = fetched samples x 8 taps x 1 B
+        alg_bytes = samples_fetched * 8.0 + W * H * 8.0
+        achieved = alg_bytes / (ms * 1e-3) / 1e9
+        micro = peaks.get("micro", {})
+        l1_peak = micro.get("ldg8_gather_F16_gload_s")
+        roofline = {
+            "kernel": "raycast_kernel<M1, LINEAR, U8, SKIP>",
+            "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "traffic": None, "peak_source": peaks["hbm_source"],
+            "algorithmic_bytes_per_launch": alg_bytes,
+            "note": "the 16 MiB volume is L2/L1-resident: HBM is not the binding resource; the binding one is the L1/LSU gather rate below",
+        }
+        if l1_peak:
+            loads = samples_fetched * 8.0 / (ms * 1e-3) / 1e9
+            roofline["binding"] = {"bound": "l1tex-gather", "achieved": loads, "peak": l1_peak, "unit": "Gload/s", "frac": loads / l1_peak,
+                                   "peak_source": "profiles/microbench_r01.json ldg8_gather_F16"}
+        line = {
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "volume": "xor bit pattern (shaders/xor.wgsl:46-53) quantised to u8, 16 MiB", "resolution": [W, H],
+                       "l2": "flushed between timed frames (write of a 256 MiB buffer, untimed)", "layout": "LINEAR (manual fp32 trilinear, parity path)",
+                       "parallelism": "single GPU" if world == 1 else f"sort-first image tiles over {world} GPUs, peer writes into rank 0's frame"},
+            "ray_samples_per_s": samples_ref * fps, "fetched_samples_per_s": samples_fetched * fps,
+            "samples_per_frame": {"reference": samples_ref, "fetched": samples_fetched},
+            "ms_per_step_warm_l2": float(warm_ms.mean()), "fps_warm_l2": 1e3 / float(warm_ms.mean()),
+            "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
+            "frame_ms_p10_p50_p90": [float(np.percentile(frame_ms, q)) for q in (10, 50, 90)],
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K, "clocks": clock_info,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=360)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

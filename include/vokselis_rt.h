@@ -203,6 +203,14 @@ VKRT_API void* vkrt_frame_rgba8_device_ptr(VkrtContext* ctx); /* W*H rgba8 */
 VKRT_API void* vkrt_stream(VkrtContext* ctx);                 /* cudaStream_t */
 VKRT_API int vkrt_stats(VkrtContext* ctx, VkrtStats* out);    /* synchronises */
 VKRT_API int vkrt_reset_stats(VkrtContext* ctx);
+/* Measurement — replaces the timestamp queries bracketing the raycast pass
+ * (examples/xor/main.rs:120-131,217,258-259): vkrt_timing_enable allocates `capacity` CUDA-event
+ * pairs; every vkrt_render* call then brackets its kernel with the next pair, and vkrt_timing_read
+ * returns the device times (ms) of the last n renders, oldest first. vkrt_flush_l2 writes a buffer
+ * larger than L2 on the context's stream (cold-cache timing hygiene; not part of the path). */
+VKRT_API int vkrt_timing_enable(VkrtContext* ctx, int capacity);
+VKRT_API int vkrt_timing_read(VkrtContext* ctx, float* ms, int n);
+VKRT_API int vkrt_flush_l2(VkrtContext* ctx);
 /* kind: 0 none, 1 rgba16f pair, 2 scalar. bricks = 8^3-voxel cells of the occupancy grid. */
 VKRT_API int vkrt_volume_info(VkrtContext* ctx, int* kind, int* dtype, int dims[3], uint64_t* bricks_total,
                               uint64_t* bricks_occupied);

@@ -37,6 +37,9 @@ int cuda_fail(cudaError_t e, const char* what) {
     } while (0)
 
 enum VolKind { VOL_NONE = 0, VOL_RGBA16F = 1, VOL_SCALAR = 2 };
+// Leaps are capped at this many bricks (8 voxels each): bounds the drift of the repeated addition that a
+// leap replays and the number of relaxation passes at upload.
+constexpr int kMaxLeapBricks = 16;
 
 }  // namespace
 
@@ -55,6 +58,10 @@ struct VkrtContext {
     uint32_t* aux = nullptr;
     unsigned long long* counters = nullptr;
     bool timed = false;
+    std::vector<cudaEvent_t> ring_begin, ring_end;  // per-render event pairs (vkrt_timing_enable)
+    size_t ring_next = 0, ring_count = 0;
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
     // volume resources
     int kind = VOL_NONE, dtype = 0;
     int nx = 0, ny = 0, nz = 0, nbx = 0, nby = 0, nbz = 0;
@@ -63,7 +70,7 @@ struct VkrtContext {
     uint4* bricked = nullptr;
     cudaArray_t arr_a = nullptr, arr_b = nullptr;
     cudaTextureObject_t tex_a = 0, tex_b = 0;
-    uint32_t* occ = nullptr;
+    uint8_t* dist = nullptr;  // brick distance field (0 = occupied)
     // tile offsets
     VkrtOffset* d_offsets = nullptr;
     int offsets_cap = 0;
@@ -86,9 +93,9 @@ void free_volume(VkrtContext* c) {
     free_layouts(c);
     if (c->lin_a) cudaFree(c->lin_a);
     if (c->lin_b) cudaFree(c->lin_b);
-    if (c->occ) cudaFree(c->occ);
+    if (c->dist) cudaFree(c->dist);
     c->lin_a = c->lin_b = nullptr;
-    c->occ = nullptr;
+    c->dist = nullptr;
     c->kind = VOL_NONE;
 }
 void free_frame(VkrtContext* c) {
@@ -197,9 +204,17 @@ int set_dims(VkrtContext* c, int nx, int ny, int nz) {
 
 int build_occupancy(VkrtContext* c) {
     const size_t cells = (size_t)c->nbx * c->nby * c->nbz;
-    CK(cudaMalloc(&c->occ, ((cells + 31) / 32) * 4));
-    if (c->kind == VOL_RGBA16F) CK(launch_occupancy_m0((const uint2*)c->lin_a, c->nx, c->ny, c->nz, c->nbx, c->nby, c->nbz, c->occ, c->stream));
-    else CK(launch_occupancy_m1(c->lin_a, c->dtype, c->nx, c->ny, c->nz, c->nbx, c->nby, c->nbz, c->occ, c->stream));
+    uint8_t* scratch = nullptr;
+    CK(cudaMalloc(&c->dist, cells));
+    CK(cudaMalloc(&scratch, cells));
+    cudaError_t e;
+    if (c->kind == VOL_RGBA16F) e = launch_occupancy_m0((const uint2*)c->lin_a, c->nx, c->ny, c->nz, c->nbx, c->nby, c->nbz, c->dist, c->stream);
+    else e = launch_occupancy_m1(c->lin_a, c->dtype, c->nx, c->ny, c->nz, c->nbx, c->nby, c->nbz, c->dist, c->stream);
+    // bricks outside the grid: empty for M0 (out-of-range texels read 0), occupied for M1 (clamp-to-edge)
+    if (e == cudaSuccess) e = launch_distance_transform(c->dist, scratch, c->nbx, c->nby, c->nbz, c->kind == VOL_RGBA16F ? 255 : 0, kMaxLeapBricks, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(scratch);
+    if (e != cudaSuccess) return cuda_fail(e, "build_occupancy");
     return VKRT_OK;
 }
 
@@ -259,7 +274,9 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     A.fx = (float)c->nx; A.fy = (float)c->ny; A.fz = (float)c->nz;
     A.hx = A.fx / 2.0f; A.hy = A.fy / 2.0f; A.hz = A.fz / 2.0f;
     A.nbx = c->nbx; A.nby = c->nby; A.nbz = c->nbz;
-    A.occ = c->occ;
+    A.dist = c->dist;
+    // shrink leap regions by ~16 ulp of the largest voxel coordinate (rounding of p and q)
+    A.leap_eps = 16.0f * 1.1920929e-07f * (float)(c->nx > c->ny ? (c->nx > c->nz ? c->nx : c->nz) : (c->ny > c->nz ? c->ny : c->nz));
     A.dt_scale = P.dt_scale; A.dt_floor = P.dt_floor; A.alpha_threshold = P.alpha_threshold; A.initial_alpha = P.initial_alpha;
     memcpy(A.clear, P.clear_color, sizeof A.clear);
     A.m1_srgb = P.m1_srgb;
@@ -271,10 +288,17 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     }
     A.aux = dbg ? c->aux : nullptr;
     A.counters = dbg ? c->counters : nullptr;
-    CK(cudaEventRecord(c->ev_begin, c->stream));
+    cudaEvent_t eb = c->ev_begin, ee = c->ev_end;
+    if (!c->ring_begin.empty()) {
+        eb = c->ring_begin[c->ring_next];
+        ee = c->ring_end[c->ring_next];
+        c->ring_next = (c->ring_next + 1) % c->ring_begin.size();
+        if (c->ring_count < c->ring_begin.size()) ++c->ring_count;
+    }
+    CK(cudaEventRecord(eb, c->stream));
     CK(launch_raycast(A, P.mode, layout, c->dtype, skip, dbg, c->stream));
-    CK(cudaEventRecord(c->ev_end, c->stream));
-    c->timed = true;
+    CK(cudaEventRecord(ee, c->stream));
+    if (c->ring_begin.empty()) c->timed = true;
     return VKRT_OK;
 }
 
@@ -348,6 +372,9 @@ int vkrt_destroy(VkrtContext* c) {
     free_frame(c);
     if (c->counters) cudaFree(c->counters);
     if (c->d_offsets) cudaFree(c->d_offsets);
+    if (c->flush_buf) cudaFree(c->flush_buf);
+    for (cudaEvent_t e : c->ring_begin) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ring_end) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_slot_ready[i]) cudaEventDestroy(c->ev_slot_ready[i]);
         if (c->ev_slot_copied[i]) cudaEventDestroy(c->ev_slot_copied[i]);
@@ -580,6 +607,51 @@ int vkrt_reset_stats(VkrtContext* c) {
     return VKRT_OK;
 }
 
+int vkrt_timing_enable(VkrtContext* c, int capacity) {
+    if (!c || capacity < 0 || capacity > (1 << 20)) return fail(VKRT_ERR_INVALID, "bad timing capacity");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (cudaEvent_t e : c->ring_begin) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ring_end) cudaEventDestroy(e);
+    c->ring_begin.clear();
+    c->ring_end.clear();
+    c->ring_next = c->ring_count = 0;
+    for (int i = 0; i < capacity; ++i) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        c->ring_begin.push_back(a);
+        c->ring_end.push_back(b);
+    }
+    return VKRT_OK;
+}
+
+int vkrt_timing_read(VkrtContext* c, float* ms, int n) {
+    if (!c || !ms || n < 0) return fail(VKRT_ERR_INVALID, "bad argument");
+    if ((size_t)n > c->ring_count) return fail(VKRT_ERR_INVALID, "fewer renders recorded than requested");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t cap = c->ring_begin.size();
+    for (int i = 0; i < n; ++i) {  // oldest of the last n first
+        const size_t k = (c->ring_next + cap - (size_t)n + (size_t)i) % cap;
+        CK(cudaEventElapsedTime(ms + i, c->ring_begin[k], c->ring_end[k]));
+    }
+    return VKRT_OK;
+}
+
+int vkrt_flush_l2(VkrtContext* c) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    if (!c->flush_buf) {
+        int l2 = 0;
+        CK(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, c->device));
+        c->flush_bytes = (size_t)l2 * 2 > ((size_t)256 << 20) ? (size_t)l2 * 2 : ((size_t)256 << 20);
+        CK(cudaMalloc(&c->flush_buf, c->flush_bytes));
+    }
+    CK(launch_flush_l2((uint4*)c->flush_buf, c->flush_bytes / 16, c->stream));
+    return VKRT_OK;
+}
+
 int vkrt_volume_info(VkrtContext* c, int* kind, int* dtype, int dims[3], uint64_t* bricks_total, uint64_t* bricks_occupied) {
     if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
     if (kind) *kind = c->kind;
@@ -589,13 +661,13 @@ int vkrt_volume_info(VkrtContext* c, int* kind, int* dtype, int dims[3], uint64_
     if (bricks_total) *bricks_total = cells;
     if (bricks_occupied) {
         *bricks_occupied = 0;
-        if (c->occ) {
+        if (c->dist) {
             CK(cudaSetDevice(c->device));
             CK(cudaStreamSynchronize(c->stream));
-            std::vector<uint32_t> h((cells + 31) / 32);
-            CK(cudaMemcpy(h.data(), c->occ, h.size() * 4, cudaMemcpyDeviceToHost));
+            std::vector<uint8_t> h(cells);
+            CK(cudaMemcpy(h.data(), c->dist, cells, cudaMemcpyDeviceToHost));
             uint64_t n = 0;
-            for (uint32_t w : h) n += (uint64_t)__builtin_popcount(w);
+            for (uint8_t d : h) n += d == 0;
             *bricks_occupied = n;
         }
     }

@@ -21,23 +21,30 @@ namespace {
 // slightly smaller bound, so fp32 rounding inside any trilinear formula cannot cross 0.1f.
 template <int DTYPE> struct Scalar;
 template <> struct Scalar<VKRT_U8> {
-    using T = uint8_t;
-    static __device__ __forceinline__ float load(const void* p, size_t i) { return (float)__ldg((const uint8_t*)p + i) / 255.0f; }
+    // R8Unorm: value = b / 255. The byte is turned into a float on the FMA pipe (0x4B000000 | b is
+    // 2^23 + b; no I2F on the XU pipe, no per-tap IEEE division); the 1/255 is applied once, after
+    // the interpolation (differs from the oracle's per-tap b/255 only in the last ulp).
+    static constexpr float kScale = 1.0f / 255.0f;
+    static __device__ __forceinline__ float load(const void* p, size_t i) {
+        return __uint_as_float(0x4B000000u | (uint32_t)__ldg((const uint8_t*)p + i)) - 8388608.0f;
+    }
 };
 template <> struct Scalar<VKRT_F16> {
-    using T = __half;
+    static constexpr float kScale = 1.0f;
     static __device__ __forceinline__ float load(const void* p, size_t i) {
         return __half2float(__ushort_as_half(__ldg((const unsigned short*)p + i)));
     }
 };
 template <> struct Scalar<VKRT_F32> {
-    using T = float;
+    static constexpr float kScale = 1.0f;
     static __device__ __forceinline__ float load(const void* p, size_t i) { return __ldg((const float*)p + i); }
 };
 
-__device__ __forceinline__ bool occupied(const RenderArgs& A, int ix, int iy, int iz) {
+// Distance field over the 8^3-voxel bricks: 0 = some sample in the brick can be non-transparent;
+// d >= 1 = every brick within Chebyshev radius d-1 (this one included) is empty.
+__device__ __forceinline__ uint32_t brick_distance(const RenderArgs& A, int ix, int iy, int iz) {
     const uint32_t cell = ((uint32_t)(iz >> 3) * (uint32_t)A.nby + (uint32_t)(iy >> 3)) * (uint32_t)A.nbx + (uint32_t)(ix >> 3);
-    return (__ldg(A.occ + (cell >> 5)) >> (cell & 31u)) & 1u;
+    return __ldg(A.dist + cell);
 }
 
 // ---- texel fetch, M0 (nearest, two rgba16f texels at one integer coordinate) -----------------
@@ -89,7 +96,7 @@ __device__ __forceinline__ float m1_sample(const RenderArgs& A, float qx, float 
     const float c00 = c000 + fx * (c100 - c000), c10 = c010 + fx * (c110 - c010);
     const float c01 = c001 + fx * (c101 - c001), c11 = c011 + fx * (c111 - c011);
     const float c0 = c00 + fy * (c10 - c00), c1 = c01 + fy * (c11 - c01);
-    return c0 + fz * (c1 - c0);
+    return (c0 + fz * (c1 - c0)) * S::kScale;
 }
 
 template <int MODE, int LAYOUT, int DTYPE, bool SKIP, bool DBG>
@@ -126,19 +133,68 @@ __global__ void __launch_bounds__(64) raycast_kernel(const __grid_constant__ Ren
 
     if (hit) {
         const float dt = step_dt(dir, A.fx, A.fy, A.fz, A.dt_scale, A.dt_floor);
-        for (float t = t0; t < t1; t = xadd(t, dt)) {
-            if (DBG) ++iters;
+        // Leap geometry (SKIP only; approximate on purpose, see the margins below): voxel-space advance
+        // per step and its reciprocal, per axis.
+        float dqx = 0.f, dqy = 0.f, dqz = 0.f, rqx = 0.f, rqy = 0.f, rqz = 0.f;
+        if (SKIP) {
+            dqx = dir.x * A.hx * dt; dqy = dir.y * A.hy * dt; dqz = dir.z * A.hz * dt;
+            rqx = fabsf(dqx) > 1e-12f ? 1.0f / dqx : 1e30f;
+            rqy = fabsf(dqy) > 1e-12f ? 1.0f / dqy : 1e30f;
+            rqz = fabsf(dqz) > 1e-12f ? 1.0f / dqz : 1e30f;
+        }
+        float t = t0;
+        while (t < t1) {
             // p = eye + t*dir ; q = (p + 1) * (N/2) — exact, decides the texel
             f3 p = {xadd(eye.x, xmul(t, dir.x)), xadd(eye.y, xmul(t, dir.y)), xadd(eye.z, xmul(t, dir.z))};
             const float qx = xmul(xadd(p.x, 1.0f), A.hx), qy = xmul(xadd(p.y, 1.0f), A.hy), qz = xmul(xadd(p.z, 1.0f), A.hz);
             const int ix = __float2int_rz(qx), iy = __float2int_rz(qy), iz = __float2int_rz(qz);
             const bool inb = (unsigned)ix < (unsigned)A.nx && (unsigned)iy < (unsigned)A.ny && (unsigned)iz < (unsigned)A.nz;
             if (SKIP) {
-                // Exact empty-space skipping: a sample in an empty brick (or outside the grid, M0) leaves
-                // colour and alpha bit-identical, so only the t sequence is advanced.
-                if (MODE == VKRT_MODE_M0 ? (!inb || !occupied(A, ix, iy, iz)) : (inb && !occupied(A, ix, iy, iz))) continue;
+                // Exact empty-space skipping. A sample in an empty brick (or, in M0,
+                // outside the grid) leaves colour and alpha bit-identical, so only the t sequence
+                // advances — by repeated addition, exactly like the reference loop. n = how many
+                // consecutive samples (this one included) provably stay inside the empty region.
+                int n = 0;
+                if (!inb) {
+                    n = MODE == VKRT_MODE_M0 ? 1 : 0;
+                } else {
+                    const uint32_t d = brick_distance(A, ix, iy, iz);
+                    if (d != 0u) {
+                        n = 1;
+                        // Region = bricks [c-(d-1), c+d) per axis, shrunk by A.leap_eps voxels (covers the
+                        // rounding of p and q); the -1 step covers the drift of the repeated addition.
+                        const int r = (int)d - 1;
+                        const float lox = (float)(((ix >> 3) - r) * 8) + A.leap_eps, loy = (float)(((iy >> 3) - r) * 8) + A.leap_eps,
+                                    loz = (float)(((iz >> 3) - r) * 8) + A.leap_eps;
+                        float hix = (float)(((ix >> 3) + r + 1) * 8), hiy = (float)(((iy >> 3) + r + 1) * 8), hiz = (float)(((iz >> 3) + r + 1) * 8);
+                        if (MODE == VKRT_MODE_M1) {  // clamp-to-edge sampling: outside the grid is NOT empty
+                            hix = fminf(hix, A.fx); hiy = fminf(hiy, A.fy); hiz = fminf(hiz, A.fz);
+                        }
+                        hix -= A.leap_eps; hiy -= A.leap_eps; hiz -= A.leap_eps;
+                        const float sx = ((dqx > 0.f ? hix : lox) - qx) * rqx;
+                        const float sy = ((dqy > 0.f ? hiy : loy) - qy) * rqy;
+                        const float sz = ((dqz > 0.f ? hiz : loz) - qz) * rqz;
+                        const float sm = fminf(fminf(sx, sy), fminf(sz, 4096.0f));
+                        n = max(__float2int_rz(sm) - 1, 1);
+                    }
+                }
+                if (n > 0) {
+                    if (DBG) {
+                        for (int j = 0; j < n && t < t1; ++j) {
+                            ++iters;
+                            t = xadd(t, dt);
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int j = 0; j < n; ++j) t = xadd(t, dt);
+                    }
+                    continue;
+                }
             }
-            if (DBG) ++fetched;
+            if (DBG) {
+                ++iters;
+                ++fetched;
+            }
             if (MODE == VKRT_MODE_M0) {
                 float4 c, n;
                 m0_fetch<LAYOUT>(A, ix, iy, iz, inb, c, n);
@@ -147,6 +203,7 @@ __global__ void __launch_bounds__(64) raycast_kernel(const __grid_constant__ Ren
                 m1_shade(col, m1_sample<LAYOUT, DTYPE>(A, qx, qy, qz));
             }
             if (col.a >= A.alpha_threshold) break;
+            t = xadd(t, dt);
         }
         if (MODE == VKRT_MODE_M1 && A.m1_srgb) {
             col.r = linear_to_srgb_naive(col.r);

@@ -23,7 +23,8 @@ struct RenderArgs {
     float fx, fy, fz;  // dims as f32   (textureDimensions -> vec3<f32>)
     float hx, hy, hz;  // dims / 2
     int nbx, nby, nbz;  // 8^3-voxel bricks per axis (occupancy grid and bricked layout)
-    const uint32_t* occ;  // 1 bit per brick: some sample in it can be non-transparent
+    const uint8_t* dist;  // per brick: 0 = occupied, d = bricks within Chebyshev radius d-1 are all empty
+    float leap_eps;       // safety shrink of leap regions, in voxels
     // parameters (VkrtParams)
     float dt_scale, dt_floor, alpha_threshold, initial_alpha;
     float clear[4];
@@ -39,11 +40,15 @@ cudaError_t launch_raycast(const RenderArgs& A, int mode, int layout, int dtype,
 // volume.cu
 cudaError_t launch_interleave_bricked(const uint2* color, const uint2* normal, uint4* out, int nx, int ny, int nz,
                                       int nbx, int nby, int nbz, cudaStream_t s);
-cudaError_t launch_occupancy_m0(const uint2* color, int nx, int ny, int nz, int nbx, int nby, int nbz, uint32_t* occ,
+// dist: one byte per brick, built in two steps: occupancy (0 / 255) then the Chebyshev distance transform
+cudaError_t launch_occupancy_m0(const uint2* color, int nx, int ny, int nz, int nbx, int nby, int nbz, uint8_t* dist,
                                 cudaStream_t s);
 cudaError_t launch_occupancy_m1(const void* scalar, int dtype, int nx, int ny, int nz, int nbx, int nby, int nbz,
-                                uint32_t* occ, cudaStream_t s);
+                                uint8_t* dist, cudaStream_t s);
+cudaError_t launch_distance_transform(uint8_t* dist, uint8_t* scratch, int nbx, int nby, int nbz, int border, int max_d, cudaStream_t s);
 cudaError_t launch_generate_xor(uint2* color, uint2* normal, int n, float time, int which, cudaStream_t s);
+
+cudaError_t launch_flush_l2(uint4* buf, size_t n16, cudaStream_t s);
 
 // present.cu
 cudaError_t launch_present(const uint2* frame, uint32_t* rgba8, int W, int H, cudaStream_t s);

@@ -69,8 +69,12 @@ __device__ __forceinline__ float step_dt(f3 dir, float nx, float ny, float nz, f
 }
 
 // ---- shading (tolerance-checked, FMA allowed) ----------------------------------------------
-__device__ __forceinline__ float smoothstep_f(float e0, float e1, float x) {
-    float t = __saturatef((x - e0) / (e1 - e0));  // saturate maps NaN -> 0 like fmin(fmax(NaN,0),1)
+// smoothstep with compile-time edges: the division by (e1 - e0) becomes a multiplication by its
+// reciprocal (an IEEE fdiv is ~10 instructions plus a slow path for zero numerators; profiles/).
+// __saturatef maps NaN -> 0 like fmin(fmax(NaN, 0), 1).
+#define VKRT_SMOOTHSTEP(e0, e1, x) vkrt::smoothstep_r((e0), 1.0f / ((e1) - (e0)), (x))
+__device__ __forceinline__ float smoothstep_r(float e0, float inv_range, float x) {
+    const float t = __saturatef((x - e0) * inv_range);
     return t * t * (3.0f - 2.0f * t);
 }
 
@@ -84,7 +88,7 @@ struct Rgba {
 __device__ __forceinline__ float m0_alpha(float ca) {
     // pow(a, 3.0) then smoothstep(0, 0.7, .): x*x*x is within 1 ulp of the exact cube (CUDA powf: 4 ulp).
     const float a3 = ca * ca * ca;
-    return smoothstep_f(0.0f, 0.7f, a3);
+    return VKRT_SMOOTHSTEP(0.0f, 0.7f, a3);
 }
 
 __device__ __forceinline__ void m0_shade(Rgba& col, float4 c, float4 n, f3 p, const float* clear) {
@@ -93,7 +97,7 @@ __device__ __forceinline__ void m0_shade(Rgba& col, float4 c, float4 n, f3 p, co
     const float shade_s = fmaxf(0.0f, -n.y);  // dot((0,-1,0), n); fmaxf drops NaN
     const float vol_alpha = m0_alpha(c.w);
     const float ndl = fmaxf((-2.0f * kL) * n.x + (-2.0f * kL) * n.y + (-kL) * n.z, 0.0f);
-    const float pd = smoothstep_f(0.3f, 1.5f, kP * p.x + kP * p.y - kP * p.z);
+    const float pd = VKRT_SMOOTHSTEP(0.3f, 1.5f, kP * p.x + kP * p.y - kP * p.z);
     const float dsc = ndl * pd;
     const float vr = c.x + 3.0f * dsc, vg = c.y + 0.3f * dsc, vb = c.z + 0.39f * dsc;
     const float bottom = 0.9f * __saturatef(0.5f - 0.5f * n.y);
@@ -108,7 +112,7 @@ __device__ __forceinline__ void m0_shade(Rgba& col, float4 c, float4 n, f3 p, co
 }
 
 // shaders/raycast_naive.wgsl:70-81,106-117 — transfer function + composite of one scalar sample.
-__device__ __forceinline__ float m1_alpha(float s) { return smoothstep_f(0.10f, 1.2f, fminf(0.9f, s)); }
+__device__ __forceinline__ float m1_alpha(float s) { return VKRT_SMOOTHSTEP(0.10f, 1.2f, fminf(0.9f, s)); }
 
 __device__ __forceinline__ void m1_shade(Rgba& col, float s) {
     const float TAU = 6.28318f;

@@ -25,7 +25,7 @@ EXPORTS = [
     "vkrt_render", "vkrt_render_tiles", "vkrt_tile_table", "vkrt_present", "vkrt_readback", "vkrt_readback_rgba8",
     "vkrt_readback_aux", "vkrt_sync", "vkrt_frame_host", "vkrt_frame_host_async", "vkrt_frame_host_wait",
     "vkrt_frame_host_slot_ptr", "vkrt_frame_device_ptr", "vkrt_frame_rgba8_device_ptr", "vkrt_stream", "vkrt_stats",
-    "vkrt_reset_stats", "vkrt_volume_info", "vkrt_camera_uniform", "vkrt_dispatch_optimal",
+    "vkrt_reset_stats", "vkrt_timing_enable", "vkrt_timing_read", "vkrt_flush_l2", "vkrt_volume_info", "vkrt_camera_uniform", "vkrt_dispatch_optimal",
 ]
 
 
@@ -77,6 +77,9 @@ def lib() -> C.CDLL:
         "vkrt_stream": (vp, [vp]),
         "vkrt_stats": (ci, [vp, C.POINTER(Stats)]),
         "vkrt_reset_stats": (ci, [vp]),
+        "vkrt_timing_enable": (ci, [vp, ci]),
+        "vkrt_timing_read": (ci, [vp, vp, ci]),
+        "vkrt_flush_l2": (ci, [vp]),
         "vkrt_volume_info": (ci, [vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci * 3), C.POINTER(C.c_uint64),
                                   C.POINTER(C.c_uint64)]),
         "vkrt_camera_uniform": (ci, [cf, cf, cf, C.POINTER(cf * 3), cf, C.POINTER(CameraUniform)]),
@@ -290,6 +293,17 @@ class Context:
         st = Stats()
         _check(lib().vkrt_stats(self._h, C.byref(st)))
         return st
+
+    def timing_enable(self, capacity: int):
+        _check(lib().vkrt_timing_enable(self._h, capacity))
+
+    def timing_read(self, n: int) -> np.ndarray:
+        out = np.empty(n, np.float32)
+        _check(lib().vkrt_timing_read(self._h, _vp(out), n))
+        return out
+
+    def flush_l2(self):
+        _check(lib().vkrt_flush_l2(self._h))
 
     def reset_stats(self):
         _check(lib().vkrt_reset_stats(self._h))
