@@ -191,14 +191,6 @@ def run_gpu(args):
     p.layout = abi.LAYOUT_LINEAR
     ctx.set_params(p)
 
-    if world > 1:
-        from vokselis_b200 import sortfirst
-
-        group = sortfirst.SortFirstGroup(ctx, rank, world, tile=120)
-        render = group.render
-    else:
-        group = None
-        render = ctx.render
 
     def barrier():
         ctx.sync()
@@ -221,40 +213,72 @@ def run_gpu(args):
         samples_fetched = st.samples_fetched / len(probe)
         ctx.set_params(p)
 
+    if world > 1:
+        from vokselis_b200 import sortfirst
+
+        # 1080p frames take a fraction of a millisecond on one GPU: deal whole frames round-robin
+        # ("frames" granularity); every frame still lands in rank 0's ring by peer stores.
+        group = sortfirst.SortFirstGroup(ctx, rank, world, granularity=args.granularity, tile=120)
+
+        def render(cam):
+            f = group.frame
+            if group.granularity == "tiles" or sortfirst.frame_owner(f, world) == rank:
+                if flushing[0]:
+                    ctx.flush_l2()
+            group.render(cam)
+    else:
+        group = None
+
+        def render(cam):
+            if flushing[0]:
+                ctx.flush_l2()
+            ctx.render(cam)
+    flushing = [True]
+
     # ---- timed: device time per frame, L2 flushed between frames -------------------------------
     ctx.timing_enable(max(K, 1))
     for i in range(Wm):
-        ctx.flush_l2()
         render(cams[i % ORBIT])
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    t_wall = time.perf_counter()
-    for i in range(K):
-        ctx.flush_l2()
-        render(cams[(Wm + i) % ORBIT])
-    barrier()
-    t_wall = time.perf_counter() - t_wall
-    frame_ms = ctx.timing_read(K).astype(np.float64) if group is None else group.frame_ms(K)
-    total_ms = float(frame_ms.sum())
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    fps = K / (total_ms * 1e-3)
 
+    def timed_pass():
+        """K steps between barriers; returns (per-frame device ms of the frames THIS rank rendered, wall s)."""
+        first = group.frame if group is not None else 0
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            render(cams[(Wm + i) % ORBIT])
+        barrier()
+        wall = time.perf_counter() - t0
+        mine = K if group is None else group.my_frames(first, K)
+        return (ctx.timing_read(mine).astype(np.float64) if mine > 0 else np.zeros(0)), wall
+
+    def whole_job_ms(ms):
+        total = float(ms.sum())  # this rank's busy device time (its frames: kernel + peer stores + arrival signal)
+        if world > 1:
+            t = torch.tensor([total], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t.item())
+        return total
+
+    frame_ms, t_wall = timed_pass()
+    total_ms = whole_job_ms(frame_ms)
+    fps = K / (total_ms * 1e-3)
     # warm-L2 variant (steady-state orbit, no flush), device-timed the same way
-    for i in range(K):
-        render(cams[(Wm + i) % ORBIT])
-    barrier()
-    warm_ms = ctx.timing_read(K).astype(np.float64) if group is None else group.frame_ms(K)
+    flushing[0] = False
+    warm_ms, t_wall_warm = timed_pass()
+    warm_total_ms = whole_job_ms(warm_ms)
+    flushing[0] = True
     clock_info = clocks.stop() if rank == 0 else None
 
     # ---- e2e through the C ABI with host buffers -----------------------------------------------
     e2e = None
     if world == 1:
-        out = np.empty((H, W, 4), np.uint8)
+        pinned = rt.PinnedArray((H, W, 4), np.uint8)  # result buffer in page-locked host memory
+        out = pinned.array
         for i in range(min(Wm, 5)):
             ctx.frame_host(cams[i], out)
         tot = 0.0
@@ -277,8 +301,10 @@ def run_gpu(args):
             ctx.frame_host_wait(i & 1, out)
         pipe_fps = K / (time.perf_counter() - t0)
         e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 144 + 48, "d2h_bytes_per_step": W * H * 4,
-               "how": "vkrt_frame_host per frame, blocking, L2 flushed before each frame (flush untimed), wall clock",
+               "how": "vkrt_frame_host per frame into a pinned host buffer, blocking, L2 flushed before each frame (flush untimed), wall clock",
                "pipelined_warm_l2": pipe_fps}
+        out = None
+        pinned.close()
     else:
         e2e = group.e2e(cams, K, Wm)
 
@@ -290,36 +316,54 @@ def run_gpu(args):
                "ray_samples_per_s": r["samples_per_s"],
                "note": "CPU restatement of the reference shader (oracle port) — substitute for wgpu/lavapipe, which cannot be installed here"}
 
+    if group is not None:
+        timeouts = ctx.sortfirst_timeouts() if rank == 0 else 0
+        group.close()
     if rank == 0:
         ms = total_ms / K
-        # roofline of the dominant kernel (raycast_kernel<M1,...>): algorithmic bytes = fetched samples x 8 taps x 1 B
-        alg_bytes = samples_fetched * 8.0 + W * H * 8.0
-        achieved = alg_bytes / (ms * 1e-3) / 1e9
+        # Roofline of the dominant kernel, raycast_kernel<M1, LINEAR, U8, SKIP>.
+        # Algorithmic bytes per ray-sample: 8 taps x 1 B; units per launch = the samples the
+        # kernel actually fetches for one frame. The 16 MiB volume is L1/L2-resident, so the texel path
+        # (LSU gathers out of L1) is the binding resource, not HBM; both are reported.
+        kernel_ms = float(frame_ms.mean())
         micro = peaks.get("micro", {})
-        l1_peak = micro.get("ldg8_gather_F16_gload_s")
+        alg_bytes = samples_fetched * 8.0
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        l1_peak = micro.get("ldg8_gather_F16_gload_s")  # Gload/s of 1-B gathers = GB/s of texel bytes
+        traffic = None
+        tfile = ROOT / "profiles" / "traffic_r01.json"
+        if tfile.exists():
+            try:
+                traffic = json.loads(tfile.read_text()).get("raycast_m1_linear_u8_skip_dram_bytes_per_launch")
+            except Exception:
+                pass
+        hbm_bytes = min(NVOL ** 3, alg_bytes) + W * H * 8.0
         roofline = {
-            "kernel": "raycast_kernel<M1, LINEAR, U8, SKIP>",
-            "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "traffic": None, "peak_source": peaks["hbm_source"],
-            "algorithmic_bytes_per_launch": alg_bytes,
-            "note": "the 16 MiB volume is L2/L1-resident: HBM is not the binding resource; the binding one is the L1/LSU gather rate below",
+            "kernel": "raycast_kernel<M1, LINEAR, U8, SKIP>", "bound": "l1tex",
+            "achieved": achieved, "peak": l1_peak, "unit": "GB/s", "frac": (achieved / l1_peak) if l1_peak else None, "traffic": traffic,
+            "peak_source": "profiles/microbench_r01.json ldg8_gather_F16 (measured on this pool's B200 by bench/microbench.cu: coherent 8x4 "
+                           "1-byte gathers out of L1); tex3D trilinear peak for comparison: %s Gfetch/s" % micro.get("tex3d_linear_u8_F16_gfetch_s"),
+            "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
+            "hbm": {"bound": "hbm", "achieved": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["hbm_source"],
+                    "compulsory_bytes_per_launch": hbm_bytes, "note": "volume (16 MiB) + frame (W*H*8 B); far below HBM peak by construction"},
+            "note": "with exact empty-space skipping most of the kernel's time is traversal, not fetching; see DESIGN.md §7 for the "
+                    "no-skip figures (68 % of the LSU gather peak; tex3D path 54-73 % of the trilinear texture peak)",
         }
-        if l1_peak:
-            loads = samples_fetched * 8.0 / (ms * 1e-3) / 1e9
-            roofline["binding"] = {"bound": "l1tex-gather", "achieved": loads, "peak": l1_peak, "unit": "Gload/s", "frac": loads / l1_peak,
-                                   "peak_source": "profiles/microbench_r01.json ldg8_gather_F16"}
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "volume": "xor bit pattern (shaders/xor.wgsl:46-53) quantised to u8, 16 MiB", "resolution": [W, H],
                        "l2": "flushed between timed frames (write of a 256 MiB buffer, untimed)", "layout": "LINEAR (manual fp32 trilinear, parity path)",
-                       "parallelism": "single GPU" if world == 1 else f"sort-first image tiles over {world} GPUs, peer writes into rank 0's frame"},
+                       "parallelism": "single GPU" if world == 1 else
+                       f"sort-first over {world} GPUs ({args.granularity} dealt round-robin), volume replicated, kernels store pixels into rank 0's frame ring over NVLink"},
             "ray_samples_per_s": samples_ref * fps, "fetched_samples_per_s": samples_fetched * fps,
             "samples_per_frame": {"reference": samples_ref, "fetched": samples_fetched},
-            "ms_per_step_warm_l2": float(warm_ms.mean()), "fps_warm_l2": 1e3 / float(warm_ms.mean()),
-            "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
+            "ms_per_step_warm_l2": warm_total_ms / K, "fps_warm_l2": K / (warm_total_ms * 1e-3),
+            "wall_ms_per_step_incl_flush": 1e3 * t_wall / K, "wall_ms_per_step_warm_l2": 1e3 * t_wall_warm / K,
             "frame_ms_p10_p50_p90": [float(np.percentile(frame_ms, q)) for q in (10, 50, 90)],
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K, "clocks": clock_info,
+            "sortfirst_wait_timeouts": (timeouts if group is not None else None),
         }
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -335,6 +379,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
+    ap.add_argument("--granularity", default="frames", choices=["frames", "tiles"], help="sort-first granularity for N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -192,6 +192,10 @@ VKRT_API int vkrt_readback_aux(VkrtContext* ctx, uint32_t* aux /* W*H */);
  * the raycast of frame i+1 (the reference's Fifo presentation is similarly one frame deep). */
 VKRT_API int vkrt_frame_host(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un,
                              uint8_t* rgba8);
+/* Page-locked host memory for result buffers: vkrt_frame_host / vkrt_readback* DMA straight into a
+ * buffer obtained here (a pageable buffer is staged through the context's own pinned slots). */
+VKRT_API int vkrt_alloc_host(size_t bytes, void** out);
+VKRT_API int vkrt_free_host(void* ptr);
 VKRT_API int vkrt_frame_host_async(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un,
                                    int slot /* 0 or 1 */);
 VKRT_API int vkrt_frame_host_wait(VkrtContext* ctx, int slot, uint8_t* rgba8 /* may be NULL */);
@@ -211,6 +215,40 @@ VKRT_API int vkrt_reset_stats(VkrtContext* ctx);
 VKRT_API int vkrt_timing_enable(VkrtContext* ctx, int capacity);
 VKRT_API int vkrt_timing_read(VkrtContext* ctx, float* ms, int n);
 VKRT_API int vkrt_flush_l2(VkrtContext* ctx);
+/* ------------------------------------------------------------------------------------------ */
+/* Sort-first across the GPUs of one node, one process (one context) per GPU. The reference is
+ * single-device; its `tile` entry point + Offset table (shaders/raycast_compute.wgsl:139-144,
+ * examples/xor/main.rs:80-95) is the seam this uses: the volume is replicated, every participating
+ * rank renders a disjoint set of tiles (or, for small frames, whole frames in turn) and its kernel
+ * stores the pixels straight into a ring of frames in rank 0's memory over NVLink (CUDA IPC peer
+ * mapping); arrival and slot reuse are signalled with device-side flags. No host round trip per frame.
+ *   rank 0 : vkrt_sortfirst_create_root(world, slots) -> ship the handle to the other processes
+ *   rank r : vkrt_sortfirst_join
+ *   ranks taking part in frame f : vkrt_sortfirst_render(..., f) with their tiles (NULL/0 = whole frame)
+ *   rank 0, for f = 0, 1, 2, ... in order : vkrt_sortfirst_wait(f, arrivals_target) then use the frame
+ *            (vkrt_readback*, vkrt_present) then vkrt_sortfirst_consume(f) to free the ring slot.
+ * arrivals_target = cumulative number of vkrt_sortfirst_render calls (over all ranks and all frames
+ * so far, this one included) that target f's ring slot (slot = f % slots). */
+typedef struct VkrtSortFirstHandle {
+    unsigned char ipc[64];
+    int32_t width, height, world, slots;
+} VkrtSortFirstHandle;
+VKRT_API int vkrt_sortfirst_create_root(VkrtContext* ctx, int world, int slots, VkrtSortFirstHandle* out);
+VKRT_API int vkrt_sortfirst_join(VkrtContext* ctx, int rank, const VkrtSortFirstHandle* handle);
+VKRT_API int vkrt_sortfirst_leave(VkrtContext* ctx);
+/* This rank's share of the tile grid (tiles intersecting the frame, dealt round-robin). Returns the count. */
+VKRT_API int vkrt_sortfirst_partition(int width, int height, int tile_size, int rank, int world, VkrtOffset* out, int cap);
+VKRT_API int vkrt_sortfirst_render(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un,
+                                   const VkrtOffset* offsets, int n, uint64_t frame_index);
+VKRT_API int vkrt_sortfirst_wait(VkrtContext* ctx, uint64_t frame_index, uint64_t arrivals_target);
+VKRT_API int vkrt_sortfirst_consume(VkrtContext* ctx, uint64_t frame_index, int do_present);
+/* Number of device-side waits that gave up after 10 s (a peer died); 0 on a healthy group. Synchronises. */
+VKRT_API int vkrt_sortfirst_timeouts(VkrtContext* ctx, uint64_t* out);
+/* Eight user events on the context's stream: vkrt_mark records one, vkrt_mark_elapsed returns the
+ * device time between two (ms). */
+VKRT_API int vkrt_mark(VkrtContext* ctx, int idx);
+VKRT_API int vkrt_mark_elapsed(VkrtContext* ctx, int from, int to, float* ms);
+
 /* kind: 0 none, 1 rgba16f pair, 2 scalar. bricks = 8^3-voxel cells of the occupancy grid. */
 VKRT_API int vkrt_volume_info(VkrtContext* ctx, int* kind, int* dtype, int dims[3], uint64_t* bricks_total,
                               uint64_t* bricks_occupied);

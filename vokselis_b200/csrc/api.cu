@@ -62,6 +62,13 @@ struct VkrtContext {
     size_t ring_next = 0, ring_count = 0;
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
+    // sort-first group state (vkrt_sortfirst_*): a ring of two frames + a mailbox in rank 0's memory,
+    // mapped into every peer through CUDA IPC
+    int sf_rank = -1, sf_world = 0, sf_slots = 2;
+    cudaEvent_t marks[8] = {};
+    unsigned char* sf_base = nullptr;  // [mailbox 4 KiB][frame slot 0][frame slot 1]
+    bool sf_owner = false;
+    uint2* own_frame = nullptr;        // the context's private frame while c->frame points into the ring
     // volume resources
     int kind = VOL_NONE, dtype = 0;
     int nx = 0, ny = 0, nz = 0, nbx = 0, nby = 0, nbz = 0;
@@ -98,7 +105,18 @@ void free_volume(VkrtContext* c) {
     c->dist = nullptr;
     c->kind = VOL_NONE;
 }
+void sf_release(VkrtContext* c) {
+    if (!c->sf_base) return;
+    if (c->own_frame) c->frame = c->own_frame;
+    c->own_frame = nullptr;
+    if (c->sf_owner) cudaFree(c->sf_base);
+    else cudaIpcCloseMemHandle(c->sf_base);
+    c->sf_base = nullptr;
+    c->sf_rank = -1;
+    c->sf_world = 0;
+}
 void free_frame(VkrtContext* c) {
+    sf_release(c);
     if (c->frame) cudaFree(c->frame);
     if (c->rgba8) cudaFree(c->rgba8);
     if (c->aux) cudaFree(c->aux);
@@ -229,7 +247,7 @@ bool params_ok(const VkrtParams* p, std::string& why) {
     return true;
 }
 
-int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, const VkrtOffset* offsets, int n) {
+int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, const VkrtOffset* offsets, int n, bool bracket = true) {
     if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
     if (!cam || !un) return fail(VKRT_ERR_INVALID, "camera/uniform is NULL");
     CK(cudaSetDevice(c->device));
@@ -288,6 +306,10 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     }
     A.aux = dbg ? c->aux : nullptr;
     A.counters = dbg ? c->counters : nullptr;
+    if (!bracket) {
+        CK(launch_raycast(A, P.mode, layout, c->dtype, skip, dbg, c->stream));
+        return VKRT_OK;
+    }
     cudaEvent_t eb = c->ev_begin, ee = c->ev_end;
     if (!c->ring_begin.empty()) {
         eb = c->ring_begin[c->ring_next];
@@ -375,6 +397,7 @@ int vkrt_destroy(VkrtContext* c) {
     if (c->flush_buf) cudaFree(c->flush_buf);
     for (cudaEvent_t e : c->ring_begin) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ring_end) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->marks) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_slot_ready[i]) cudaEventDestroy(c->ev_slot_ready[i]);
         if (c->ev_slot_copied[i]) cudaEventDestroy(c->ev_slot_copied[i]);
@@ -560,6 +583,28 @@ int vkrt_frame_host_async(VkrtContext* c, const VkrtCameraUniform* cam, const Vk
     return VKRT_OK;
 }
 
+int vkrt_alloc_host(size_t bytes, void** out) {
+    if (!out || bytes == 0) return fail(VKRT_ERR_INVALID, "bad argument");
+    CK(cudaMallocHost(out, bytes));
+    return VKRT_OK;
+}
+
+int vkrt_free_host(void* p) {
+    if (p) CK(cudaFreeHost(p));
+    return VKRT_OK;
+}
+
+namespace {
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
 int vkrt_frame_host_wait(VkrtContext* c, int slot, uint8_t* rgba8) {
     if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
     if (slot < 0 || slot > 1 || !c->host_slot[slot]) return fail(VKRT_ERR_INVALID, "slot has no frame in flight");
@@ -575,7 +620,18 @@ const uint8_t* vkrt_frame_host_slot_ptr(VkrtContext* c, int slot) {
 }
 
 int vkrt_frame_host(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, uint8_t* rgba8) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
     if (!rgba8) return fail(VKRT_ERR_INVALID, "rgba8 is NULL");
+    if (is_pinned_host(rgba8)) {
+        // caller's buffer is page-locked (vkrt_alloc_host / cudaHostAlloc): DMA straight into it
+        CK(cudaSetDevice(c->device));
+        int rc = do_render(c, cam, un, nullptr, 0);
+        if (rc) return rc;
+        CK(launch_present(c->frame, c->rgba8, c->W, c->H, c->stream));
+        CK(cudaMemcpyAsync(rgba8, c->rgba8, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return VKRT_OK;
+    }
     int rc = vkrt_frame_host_async(c, cam, un, 0);
     if (rc) return rc;
     return vkrt_frame_host_wait(c, 0, rgba8);
@@ -649,6 +705,155 @@ int vkrt_flush_l2(VkrtContext* c) {
         CK(cudaMalloc(&c->flush_buf, c->flush_bytes));
     }
     CK(launch_flush_l2((uint4*)c->flush_buf, c->flush_bytes / 16, c->stream));
+    return VKRT_OK;
+}
+
+// ---- sort-first over several GPUs, one process per GPU --------------------------------------------
+// Shared block in rank 0's memory: [mailbox 4 KiB: u64 consumed, u64 timeouts, u64 arrive[slots]][slot 0]...[slot S-1]
+namespace {
+constexpr size_t kSfMailbox = 4096;
+constexpr int kSfMaxSlots = 64;
+inline size_t sf_frame_bytes(const VkrtContext* c) { return (size_t)c->W * c->H * sizeof(uint2); }
+inline unsigned long long* sf_consumed(VkrtContext* c) { return reinterpret_cast<unsigned long long*>(c->sf_base); }
+inline unsigned long long* sf_timeouts(VkrtContext* c) { return reinterpret_cast<unsigned long long*>(c->sf_base) + 1; }
+inline unsigned long long* sf_arrive(VkrtContext* c, int slot) { return reinterpret_cast<unsigned long long*>(c->sf_base) + 2 + slot; }
+inline uint2* sf_slot(VkrtContext* c, int slot) { return reinterpret_cast<uint2*>(c->sf_base + kSfMailbox + (size_t)slot * sf_frame_bytes(c)); }
+}  // namespace
+
+int vkrt_sortfirst_create_root(VkrtContext* c, int world, int slots, VkrtSortFirstHandle* out) {
+    if (!c || !out || world < 1 || slots < 2 || slots > kSfMaxSlots) return fail(VKRT_ERR_INVALID, "bad argument (2 <= slots <= 64)");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    sf_release(c);
+    const size_t bytes = kSfMailbox + (size_t)slots * sf_frame_bytes(c);
+    CK(cudaMalloc(&c->sf_base, bytes));
+    // on the context's stream and completed before the handle leaves: the legacy default stream does
+    // not order against our non-blocking stream, nor against the peers
+    CK(cudaMemsetAsync(c->sf_base, 0, bytes, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->sf_owner = true;
+    c->sf_rank = 0;
+    c->sf_world = world;
+    c->sf_slots = slots;
+    c->own_frame = c->frame;
+    memset(out, 0, sizeof *out);
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->sf_base));
+    static_assert(sizeof(h) <= sizeof(out->ipc), "IPC handle size");
+    memcpy(out->ipc, &h, sizeof h);
+    out->width = c->W;
+    out->height = c->H;
+    out->world = world;
+    out->slots = slots;
+    return VKRT_OK;
+}
+
+int vkrt_sortfirst_join(VkrtContext* c, int rank, const VkrtSortFirstHandle* h) {
+    if (!c || !h || rank < 1 || rank >= h->world) return fail(VKRT_ERR_INVALID, "bad argument");
+    if (h->width != c->W || h->height != c->H) return fail(VKRT_ERR_INVALID, "frame size differs from the root's");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    sf_release(c);
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, h->ipc, sizeof ih);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+    c->sf_base = (unsigned char*)p;
+    c->sf_owner = false;
+    c->sf_rank = rank;
+    c->sf_world = h->world;
+    c->sf_slots = h->slots;
+    c->own_frame = c->frame;
+    return VKRT_OK;
+}
+
+int vkrt_sortfirst_leave(VkrtContext* c) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    sf_release(c);
+    return VKRT_OK;
+}
+
+int vkrt_sortfirst_partition(int width, int height, int tile_size, int rank, int world, VkrtOffset* out, int cap) {
+    if (width <= 0 || height <= 0 || tile_size <= 0 || world < 1 || rank < 0 || rank >= world) return fail(VKRT_ERR_INVALID, "bad partition arguments");
+    // tiles that intersect the frame, row-major, dealt round-robin: rank r takes tiles r, r+world, ...
+    const int cols = (width + tile_size - 1) / tile_size, rows = (height + tile_size - 1) / tile_size;
+    int k = 0;
+    for (int t = rank; t < cols * rows; t += world, ++k)
+        if (out && k < cap) {
+            out[k].x = (float)((t % cols) * tile_size);
+            out[k].y = (float)((t / cols) * tile_size);
+        }
+    return k;
+}
+
+int vkrt_sortfirst_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, const VkrtOffset* offsets, int n,
+                          uint64_t frame_index) {
+    if (!c || !c->sf_base) return fail(VKRT_ERR_INVALID, "context is not in a sort-first group");
+    CK(cudaSetDevice(c->device));
+    const int slot = (int)(frame_index % (uint64_t)c->sf_slots);
+    cudaEvent_t eb = nullptr, ee = nullptr;
+    if (!c->ring_begin.empty()) {
+        eb = c->ring_begin[c->ring_next];
+        ee = c->ring_end[c->ring_next];
+        c->ring_next = (c->ring_next + 1) % c->ring_begin.size();
+        if (c->ring_count < c->ring_begin.size()) ++c->ring_count;
+    }
+    // slot reuse: the frame that used this slot last (frame_index - slots) must have been consumed
+    if (frame_index >= (uint64_t)c->sf_slots)
+        CK(launch_flag_wait(sf_consumed(c), frame_index - (uint64_t)c->sf_slots + 1, sf_timeouts(c), c->stream));
+    if (eb) CK(cudaEventRecord(eb, c->stream));
+    c->frame = sf_slot(c, slot);  // root: local memory; peers: rank 0's memory over NVLink
+    int rc = do_render(c, cam, un, (offsets && n > 0) ? offsets : nullptr, (offsets && n > 0) ? n : 0, false);
+    if (rc) return rc;
+    CK(launch_flag_add(sf_arrive(c, slot), 1ull, c->stream));  // after the kernel: its (peer) stores are performed
+    if (ee) CK(cudaEventRecord(ee, c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_sortfirst_wait(VkrtContext* c, uint64_t frame_index, uint64_t arrivals_target) {
+    if (!c || !c->sf_base || c->sf_rank != 0) return fail(VKRT_ERR_INVALID, "only the root waits for frames");
+    CK(cudaSetDevice(c->device));
+    const int slot = (int)(frame_index % (uint64_t)c->sf_slots);
+    CK(launch_flag_wait(sf_arrive(c, slot), arrivals_target, sf_timeouts(c), c->stream));
+    c->frame = sf_slot(c, slot);
+    return VKRT_OK;
+}
+
+int vkrt_sortfirst_timeouts(VkrtContext* c, uint64_t* out) {
+    if (!c || !c->sf_base || !out) return fail(VKRT_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    unsigned long long v = 0;
+    CK(cudaMemcpy(&v, sf_timeouts(c), sizeof v, cudaMemcpyDeviceToHost));
+    *out = v;
+    return VKRT_OK;
+}
+
+int vkrt_sortfirst_consume(VkrtContext* c, uint64_t frame_index, int do_present) {
+    if (!c || !c->sf_base || c->sf_rank != 0) return fail(VKRT_ERR_INVALID, "only the root consumes frames");
+    CK(cudaSetDevice(c->device));
+    const int slot = (int)(frame_index % (uint64_t)c->sf_slots);
+    c->frame = sf_slot(c, slot);
+    if (do_present) CK(launch_present(c->frame, c->rgba8, c->W, c->H, c->stream));
+    CK(launch_flag_set(sf_consumed(c), frame_index + 1, c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_mark(VkrtContext* c, int idx) {
+    if (!c || idx < 0 || idx >= 8) return fail(VKRT_ERR_INVALID, "mark index must be 0..7");
+    CK(cudaSetDevice(c->device));
+    if (!c->marks[idx]) CK(cudaEventCreate(&c->marks[idx]));
+    CK(cudaEventRecord(c->marks[idx], c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_mark_elapsed(VkrtContext* c, int from, int to, float* ms) {
+    if (!c || !ms || from < 0 || from >= 8 || to < 0 || to >= 8 || !c->marks[from] || !c->marks[to]) return fail(VKRT_ERR_INVALID, "bad marks");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->marks[to]));
+    CK(cudaEventElapsedTime(ms, c->marks[from], c->marks[to]));
     return VKRT_OK;
 }
 

@@ -49,6 +49,9 @@ cudaError_t launch_distance_transform(uint8_t* dist, uint8_t* scratch, int nbx, 
 cudaError_t launch_generate_xor(uint2* color, uint2* normal, int n, float time, int which, cudaStream_t s);
 
 cudaError_t launch_flush_l2(uint4* buf, size_t n16, cudaStream_t s);
+cudaError_t launch_flag_wait(const unsigned long long* flag, unsigned long long target, unsigned long long* timeouts, cudaStream_t s);
+cudaError_t launch_flag_add(unsigned long long* flag, unsigned long long v, cudaStream_t s);
+cudaError_t launch_flag_set(unsigned long long* flag, unsigned long long v, cudaStream_t s);
 
 // present.cu
 cudaError_t launch_present(const uint2* frame, uint32_t* rgba8, int W, int H, cudaStream_t s);

@@ -176,7 +176,50 @@ __global__ void __launch_bounds__(256) flush_l2_kernel(uint4* __restrict__ buf, 
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) buf[i] = make_uint4(tag, tag, tag, tag);
 }
 
+// ---- device-side flags for the sort-first exchange (system scope: they live in rank 0's memory and
+// are touched by every GPU of the node over NVLink) ------------------------------------------------
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Spins until *flag >= target. Gives up after 10 s (a dead peer must not hang the GPU) and counts
+// the timeout in `timeouts` so the host can report it.
+__global__ void flag_wait_kernel(const unsigned long long* flag, unsigned long long target, unsigned long long* timeouts) {
+    const volatile unsigned long long* f = flag;
+    const unsigned long long t0 = global_timer_ns();
+    while (*f < target) {
+        __nanosleep(200);
+        if (global_timer_ns() - t0 > 10000000000ull) {
+            atomicAdd_system(timeouts, 1ull);
+            break;
+        }
+    }
+    __threadfence_system();
+}
+__global__ void flag_add_kernel(unsigned long long* flag, unsigned long long v) {
+    __threadfence_system();  // (the preceding kernel in this stream has completed: its peer stores are performed)
+    atomicAdd_system(flag, v);
+}
+__global__ void flag_set_kernel(unsigned long long* flag, unsigned long long v) {
+    __threadfence_system();
+    *(volatile unsigned long long*)flag = v;
+}
+
 }  // namespace
+
+cudaError_t launch_flag_wait(const unsigned long long* flag, unsigned long long target, unsigned long long* timeouts, cudaStream_t s) {
+    flag_wait_kernel<<<1, 1, 0, s>>>(flag, target, timeouts);
+    return cudaGetLastError();
+}
+cudaError_t launch_flag_add(unsigned long long* flag, unsigned long long v, cudaStream_t s) {
+    flag_add_kernel<<<1, 1, 0, s>>>(flag, v);
+    return cudaGetLastError();
+}
+cudaError_t launch_flag_set(unsigned long long* flag, unsigned long long v, cudaStream_t s) {
+    flag_set_kernel<<<1, 1, 0, s>>>(flag, v);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_flush_l2(uint4* buf, size_t n16, cudaStream_t s) {
     static uint32_t tag = 0;

@@ -26,6 +26,9 @@ EXPORTS = [
     "vkrt_readback_aux", "vkrt_sync", "vkrt_frame_host", "vkrt_frame_host_async", "vkrt_frame_host_wait",
     "vkrt_frame_host_slot_ptr", "vkrt_frame_device_ptr", "vkrt_frame_rgba8_device_ptr", "vkrt_stream", "vkrt_stats",
     "vkrt_reset_stats", "vkrt_timing_enable", "vkrt_timing_read", "vkrt_flush_l2", "vkrt_volume_info", "vkrt_camera_uniform", "vkrt_dispatch_optimal",
+    "vkrt_sortfirst_create_root", "vkrt_sortfirst_join", "vkrt_sortfirst_leave", "vkrt_sortfirst_partition", "vkrt_sortfirst_render",
+    "vkrt_sortfirst_consume", "vkrt_sortfirst_timeouts", "vkrt_sortfirst_wait", "vkrt_mark", "vkrt_mark_elapsed",
+    "vkrt_alloc_host", "vkrt_free_host",
 ]
 
 
@@ -84,6 +87,18 @@ def lib() -> C.CDLL:
                                   C.POINTER(C.c_uint64)]),
         "vkrt_camera_uniform": (ci, [cf, cf, cf, C.POINTER(cf * 3), cf, C.POINTER(CameraUniform)]),
         "vkrt_dispatch_optimal": (C.c_uint32, [C.c_uint32, C.c_uint32]),
+        "vkrt_sortfirst_create_root": (ci, [vp, ci, ci, vp]),
+        "vkrt_sortfirst_wait": (ci, [vp, C.c_uint64, C.c_uint64]),
+        "vkrt_mark": (ci, [vp, ci]),
+        "vkrt_alloc_host": (ci, [C.c_size_t, C.POINTER(vp)]),
+        "vkrt_free_host": (ci, [vp]),
+        "vkrt_mark_elapsed": (ci, [vp, ci, ci, C.POINTER(cf)]),
+        "vkrt_sortfirst_join": (ci, [vp, ci, vp]),
+        "vkrt_sortfirst_leave": (ci, [vp]),
+        "vkrt_sortfirst_partition": (ci, [ci, ci, ci, ci, ci, vp, ci]),
+        "vkrt_sortfirst_render": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp, ci, C.c_uint64]),
+        "vkrt_sortfirst_consume": (ci, [vp, C.c_uint64, ci]),
+        "vkrt_sortfirst_timeouts": (ci, [vp, C.POINTER(C.c_uint64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -265,8 +280,9 @@ class Context:
         _check(lib().vkrt_readback(self._h, _vp(out)))
         return out
 
-    def readback_rgba8(self) -> np.ndarray:
-        out = np.empty((self.height, self.width, 4), np.uint8)
+    def readback_rgba8(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.uint8)
         _check(lib().vkrt_readback_rgba8(self._h, _vp(out)))
         return out
 
@@ -305,6 +321,43 @@ class Context:
     def flush_l2(self):
         _check(lib().vkrt_flush_l2(self._h))
 
+    # -- sort-first group (one process per GPU) ---------------------------------------------
+    def sortfirst_create_root(self, world: int, slots: int = 2) -> bytes:
+        h = (C.c_ubyte * 80)()
+        _check(lib().vkrt_sortfirst_create_root(self._h, world, slots, C.byref(h)))
+        return bytes(h)
+
+    def sortfirst_wait(self, frame_index: int, arrivals_target: int):
+        _check(lib().vkrt_sortfirst_wait(self._h, frame_index, arrivals_target))
+
+    def mark(self, idx: int):
+        _check(lib().vkrt_mark(self._h, idx))
+
+    def mark_elapsed(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        _check(lib().vkrt_mark_elapsed(self._h, a, b, C.byref(ms)))
+        return float(ms.value)
+
+    def sortfirst_join(self, rank: int, handle: bytes):
+        h = (C.c_ubyte * 80).from_buffer_copy(handle)
+        _check(lib().vkrt_sortfirst_join(self._h, rank, C.byref(h)))
+
+    def sortfirst_leave(self):
+        _check(lib().vkrt_sortfirst_leave(self._h))
+
+    def sortfirst_render(self, cam: CameraUniform, offsets: np.ndarray, frame_index: int, uniform: Uniform | None = None):
+        un = uniform if uniform is not None else self.global_uniform
+        n = 0 if offsets is None else offsets.shape[0]
+        _check(lib().vkrt_sortfirst_render(self._h, C.byref(cam), C.byref(un), _vp(offsets), n, frame_index))
+
+    def sortfirst_consume(self, frame_index: int, present: bool = False):
+        _check(lib().vkrt_sortfirst_consume(self._h, frame_index, 1 if present else 0))
+
+    def sortfirst_timeouts(self) -> int:
+        v = C.c_uint64()
+        _check(lib().vkrt_sortfirst_timeouts(self._h, C.byref(v)))
+        return int(v.value)
+
     def reset_stats(self):
         _check(lib().vkrt_reset_stats(self._h))
 
@@ -315,6 +368,39 @@ class Context:
     @property
     def stream(self) -> int:
         return int(lib().vkrt_stream(self._h) or 0)
+
+
+class PinnedArray:
+    """A numpy view of page-locked host memory from vkrt_alloc_host (freed on close / garbage collection)."""
+
+    def __init__(self, shape, dtype=np.uint8):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._p = C.c_void_p()
+        _check(lib().vkrt_alloc_host(self.nbytes, C.byref(self._p)))
+        buf = (C.c_ubyte * self.nbytes).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def close(self):
+        if getattr(self, "_p", None) and self._p.value:
+            self.array = None
+            lib().vkrt_free_host(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sortfirst_partition(width: int, height: int, tile_size: int, rank: int, world: int) -> np.ndarray:
+    """This rank's tiles (float32 [n, 2] origins): the tiles intersecting the frame, dealt round-robin."""
+    n = lib().vkrt_sortfirst_partition(width, height, tile_size, rank, world, None, 0)
+    if n < 0:
+        _check(n)
+    out = np.zeros((n, 2), np.float32)
+    lib().vkrt_sortfirst_partition(width, height, tile_size, rank, world, _vp(out), n)
+    return out
 
 
 class RaycastPipeline:

@@ -1,0 +1,132 @@
+"""Sort-first rendering across the GPUs of one node: one process per GPU (torchrun), the volume
+replicated, the image work dealt out, every rank's raycast kernel storing its pixels straight into a
+ring of frames in rank 0's memory over NVLink (vkrt_sortfirst_* in include/vokselis_rt.h).
+torch.distributed is only the plumbing: it ships the 80-byte IPC handle and provides barriers; there
+is no data-path collective — the pixel exchange IS the kernel's own peer stores, and arrival /
+slot-reuse are device-side flags.
+
+Two granularities of the same scheme:
+  * "tiles"  — every frame is split into tiles dealt round-robin over the ranks (the reference's own
+               `tile` entry + Offset table, shaders/raycast_compute.wgsl:139-144,
+               examples/xor/main.rs:80-95,242-253). Cuts the latency of big frames (4K, large volumes).
+  * "frames" — whole frames are dealt round-robin (tile = the frame). For frames that one GPU
+               renders in a fraction of a millisecond, splitting them only adds tail effects; dealing
+               frames keeps every GPU busy and rank 0 still receives every frame, in order.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import rt
+
+
+def partition_tiles(width: int, height: int, tile: int, rank: int, world: int) -> np.ndarray:
+    return rt.sortfirst_partition(width, height, tile, rank, world)
+
+
+def frame_owner(frame_index: int, world: int) -> int:
+    """'frames' granularity: which rank renders frame f."""
+    return frame_index % world
+
+
+class SortFirstGroup:
+    def __init__(self, ctx: rt.Context, rank: int, world: int, granularity: str = "tiles", tile: int = 120, slots: int | None = None,
+                 dist=None):
+        if dist is None:
+            import torch.distributed as dist  # noqa: PLC0415
+        if granularity not in ("tiles", "frames"):
+            raise ValueError(granularity)
+        self.ctx, self.rank, self.world, self.dist, self.granularity = ctx, rank, world, dist, granularity
+        self.slots = slots if slots is not None else (2 if granularity == "tiles" else 2 * world)
+        self.tiles = None
+        if granularity == "tiles":
+            p = ctx.get_params()
+            p.tile_size = tile
+            ctx.set_params(p)
+            self.tiles = partition_tiles(ctx.width, ctx.height, tile, rank, world)
+        box = [ctx.sortfirst_create_root(world, self.slots) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            ctx.sortfirst_join(rank, box[0])
+        dist.barrier()
+        self.frame = 0       # next frame index to submit (same on every rank)
+        self.consumed = 0    # root: next frame to wait for
+
+    def participants(self, f: int) -> int:
+        return self.world if self.granularity == "tiles" else 1
+
+    def arrivals_target(self, f: int) -> int:
+        """Cumulative arrivals on f's slot once f is complete (see vkrt_sortfirst_wait)."""
+        return (f // self.slots + 1) * self.participants(f)
+
+    def submit(self, cam) -> int:
+        """Every rank calls this once per frame, in the same order. Asynchronous. Returns the frame index."""
+        f = self.frame
+        self.frame += 1
+        if self.granularity == "tiles":
+            self.ctx.sortfirst_render(cam, self.tiles, f)
+        elif frame_owner(f, self.world) == self.rank:
+            self.ctx.sortfirst_render(cam, None, f)
+        return f
+
+    def wait(self, f: int):
+        """Root only: enqueue the device-side wait for frame f; afterwards readback/present see frame f."""
+        assert self.rank == 0 and f == self.consumed, "frames are consumed in order"
+        self.ctx.sortfirst_wait(f, self.arrivals_target(f))
+
+    def consume(self, f: int, present: bool = False):
+        assert self.rank == 0 and f == self.consumed
+        self.ctx.sortfirst_consume(f, present)
+        self.consumed += 1
+
+    def render(self, cam, present: bool = False) -> int:
+        """submit + (root) wait + consume. Asynchronous on every rank."""
+        f = self.submit(cam)
+        if self.rank == 0:
+            self.wait(f)
+            self.consume(f, present)
+        return f
+
+    def close(self):
+        self.ctx.sync()
+        self.dist.barrier()
+        self.ctx.sortfirst_leave()
+        self.dist.barrier()
+
+    # -- measurement helpers used by bench.py -----------------------------------------------------
+    def my_frames(self, first: int, count: int) -> int:
+        if self.granularity == "tiles":
+            return count
+        return sum(1 for f in range(first, first + count) if frame_owner(f, self.world) == self.rank)
+
+    def e2e(self, cams, K: int, warmup: int) -> dict:
+        """End to end on the root, pipelined: every rank submits its share; the root waits for each frame
+        in order, presents it and copies the RGBA8 image into host memory (blocking D2H per frame). Wall
+        clock on the root from the first submit to the last frame's pixels on the host. The L2 flush
+        before each rendered frame is INSIDE the timed region here (conservative)."""
+        ctx, dist = self.ctx, self.dist
+        pinned = rt.PinnedArray((ctx.height, ctx.width, 4), np.uint8) if self.rank == 0 else None
+        out = pinned.array if pinned is not None else None
+        ctx.sync()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            f_next = self.frame
+            if self.granularity == "tiles" or frame_owner(f_next, self.world) == self.rank:
+                ctx.flush_l2()
+            f = self.submit(cams[(warmup + i) % len(cams)])
+            if self.rank == 0:
+                self.wait(f)
+                ctx.present()
+                ctx.readback_rgba8(out)
+                self.consume(f)
+        ctx.sync()
+        tot = time.perf_counter() - t0
+        dist.barrier()
+        fps = K / tot if self.rank == 0 and tot > 0 else 0.0
+        return {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": (144 + 48) * self.participants(0),
+                "d2h_bytes_per_step": ctx.width * ctx.height * 4,
+                "how": f"pipelined sort-first ({self.granularity}): ranks render into rank 0's ring by peer stores; rank 0 waits for each frame "
+                       "in order, presents, copies RGBA8 to host (blocking); wall clock on rank 0 over all K frames, L2 flushes included"}
