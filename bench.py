@@ -188,7 +188,7 @@ def run_gpu(args):
     ctx.upload_scalar(vol)
     p = rt.default_params(abi.MODE_M1)
     p.skip_empty = 1
-    p.layout = abi.LAYOUT_LINEAR
+    p.layout = abi.LAYOUT_GATHER  # exact fp32-weight trilinear through two tld4 gathers per sample (parity-grade)
     ctx.set_params(p)
 
 
@@ -202,7 +202,7 @@ def run_gpu(args):
     samples_ref = samples_fetched = 0
     if rank == 0:
         q = rt.default_params(abi.MODE_M1)
-        q.skip_empty, q.count_samples = 1, 1
+        q.skip_empty, q.count_samples, q.layout = 1, 1, p.layout
         ctx.set_params(q)
         probe = list(range(0, ORBIT, 30))
         ctx.reset_stats()
@@ -295,10 +295,10 @@ def run_gpu(args):
         for i in range(K):
             s = i & 1
             if i >= 2:
-                ctx.frame_host_wait(s, out)
+                ctx.frame_host_wait(s, None)  # pixels are in the context's pinned slot (vkrt_frame_host_slot_ptr): no extra copy
             ctx.frame_host_async(cams[(Wm + i) % ORBIT], s)
         for i in range(max(K - 2, 0), K):
-            ctx.frame_host_wait(i & 1, out)
+            ctx.frame_host_wait(i & 1, None)
         pipe_fps = K / (time.perf_counter() - t0)
         e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 144 + 48, "d2h_bytes_per_step": W * H * 4,
                "how": "vkrt_frame_host per frame into a pinned host buffer, blocking, L2 flushed before each frame (flush untimed), wall clock",
@@ -321,40 +321,41 @@ def run_gpu(args):
         group.close()
     if rank == 0:
         ms = total_ms / K
-        # Roofline of the dominant kernel, raycast_kernel<M1, LINEAR, U8, SKIP>.
+        # Roofline of the dominant kernel, raycast_kernel<M1, GATHER, SKIP>.
         # Algorithmic bytes per ray-sample: 8 taps x 1 B; units per launch = the samples the
-        # kernel actually fetches for one frame. The 16 MiB volume is L1/L2-resident, so the texel path
-        # (LSU gathers out of L1) is the binding resource, not HBM; both are reported.
+        # kernel actually fetches for one frame. The 16 MiB volume is L1/L2-resident, so the texture path
+        # (two tld4 gathers per sample) is the binding memory resource, not HBM; both are reported.
         kernel_ms = float(frame_ms.mean())
         micro = peaks.get("micro", {})
         alg_bytes = samples_fetched * 8.0
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        l1_peak = micro.get("ldg8_gather_F16_gload_s")  # Gload/s of 1-B gathers = GB/s of texel bytes
+        tld4_peak = micro.get("tld4_a2d_u8_F16_ginstr_s")  # G tld4/s; 4 B of texels each -> GB/s of texel bytes = 4x
+        l1_peak = 4.0 * tld4_peak if tld4_peak else None
         traffic = None
         tfile = ROOT / "profiles" / "traffic_r01.json"
         if tfile.exists():
             try:
-                traffic = json.loads(tfile.read_text()).get("raycast_m1_linear_u8_skip_dram_bytes_per_launch")
+                traffic = json.loads(tfile.read_text()).get("raycast_m1_gather_u8_skip_dram_bytes_per_launch")
             except Exception:
                 pass
         hbm_bytes = min(NVOL ** 3, alg_bytes) + W * H * 8.0
         roofline = {
-            "kernel": "raycast_kernel<M1, LINEAR, U8, SKIP>", "bound": "l1tex",
+            "kernel": "raycast_kernel<M1, GATHER, SKIP>", "bound": "tex",
             "achieved": achieved, "peak": l1_peak, "unit": "GB/s", "frac": (achieved / l1_peak) if l1_peak else None, "traffic": traffic,
-            "peak_source": "profiles/microbench_r01.json ldg8_gather_F16 (measured on this pool's B200 by bench/microbench.cu: coherent 8x4 "
-                           "1-byte gathers out of L1); tex3D trilinear peak for comparison: %s Gfetch/s" % micro.get("tex3d_linear_u8_F16_gfetch_s"),
+            "peak_source": "profiles/microbench_r01.json tld4_a2d_u8_F16 x 4 B (measured on this pool's B200 by bench/microbench.cu: coherent 8x4 "
+                           "tld4 gathers, L1-resident); tex3D trilinear peak for comparison: %s Gfetch/s" % micro.get("tex3d_linear_u8_F16_gfetch_s"),
             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
             "hbm": {"bound": "hbm", "achieved": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["hbm_source"],
                     "compulsory_bytes_per_launch": hbm_bytes, "note": "volume (16 MiB) + frame (W*H*8 B); far below HBM peak by construction"},
             "note": "with exact empty-space skipping most of the kernel's time is traversal, not fetching; see DESIGN.md §7 for the "
-                    "no-skip figures (68 % of the LSU gather peak; tex3D path 54-73 % of the trilinear texture peak)",
+                    "no-skip figures",
         }
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "volume": "xor bit pattern (shaders/xor.wgsl:46-53) quantised to u8, 16 MiB", "resolution": [W, H],
-                       "l2": "flushed between timed frames (write of a 256 MiB buffer, untimed)", "layout": "LINEAR (manual fp32 trilinear, parity path)",
+                       "l2": "flushed between timed frames (write of a 256 MiB buffer, untimed)", "layout": "GATHER (two tld4 per sample on a layered texture, fp32 weights: parity path)",
                        "parallelism": "single GPU" if world == 1 else
                        f"sort-first over {world} GPUs ({args.granularity} dealt round-robin), volume replicated, kernels store pixels into rank 0's frame ring over NVLink"},
             "ray_samples_per_s": samples_ref * fps, "fetched_samples_per_s": samples_fetched * fps,

@@ -58,7 +58,7 @@ def main():
         with rt.Context(0, W, H) as ctx:
             ctx.upload_scalar(vol)
             print(name, ctx.volume_info(), flush=True)
-            for layout in (0, 2):
+            for layout in (0, 2, 3):
                 for skip in (0, 1):
                     for dts in (1.0, 2.0):
                         p = rt.default_params(abi.MODE_M1)

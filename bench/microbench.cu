@@ -62,6 +62,23 @@ __global__ void __launch_bounds__(256) tex_linear_kernel(cudaTextureObject_t tex
     if (acc == 12345.678f) sink[0] = acc;
 }
 
+// tld4 on a 2-D layered texture: 4 texels of one bilinear footprint per instruction (the GATHER layout)
+__global__ void __launch_bounds__(256) tld4_kernel(cudaTextureObject_t tex, int F, float* sink) {
+    float acc = 0.f;
+    for (int it = 0; it < ITERS; it += UNROLL) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            int x, y, z;
+            coords(it + u, F, x, y, z);
+            float4 r;
+            asm("tld4.r.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
+                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(tex), "r"(z), "f"(x + 1.0f), "f"(y + 1.0f));
+            acc += r.x + r.y + r.z + r.w;
+        }
+    }
+    if (acc == 12345.678f) sink[0] = acc;
+}
+
 template <class V> __global__ void __launch_bounds__(256) ldg_gather_kernel(const V* __restrict__ buf, int F, float* sink) {
     float acc = 0.f;
     for (int it = 0; it < ITERS; it += UNROLL) {
@@ -179,6 +196,32 @@ int main() {
             printf(" \"tex3d_linear_f32_F%d_gfetch_s\": %.2f,\n", F, fetches / ms * 1e-6);
             CK(cudaDestroyTextureObject(t));
             CK(cudaFreeArray(arr));
+        }
+        for (int fmt = 0; fmt < 3; ++fmt) {  // tld4 on layered u8 / f16 / f32
+            const size_t elem = fmt == 0 ? 1 : (fmt == 1 ? 2 : 4);
+            cudaChannelFormatDesc d = fmt == 0 ? cudaCreateChannelDesc<unsigned char>() : (fmt == 1 ? cudaCreateChannelDescHalf() : cudaCreateChannelDesc<float>());
+            cudaArray_t larr;
+            CK(cudaMalloc3DArray(&larr, &d, make_cudaExtent(F, F, F), cudaArrayLayered));
+            std::vector<unsigned char> h((size_t)F * F * F * elem, 0x3b);
+            cudaMemcpy3DParms p{};
+            p.srcPtr = make_cudaPitchedPtr(h.data(), (size_t)F * elem, F, F);
+            p.dstArray = larr;
+            p.extent = make_cudaExtent(F, F, F);
+            p.kind = cudaMemcpyHostToDevice;
+            CK(cudaMemcpy3D(&p));
+            cudaResourceDesc rd{};
+            rd.resType = cudaResourceTypeArray;
+            rd.res.array.array = larr;
+            cudaTextureDesc td{};
+            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModeLinear;
+            td.readMode = fmt == 0 ? cudaReadModeNormalizedFloat : cudaReadModeElementType;
+            cudaTextureObject_t t;
+            CK(cudaCreateTextureObject(&t, &rd, &td, nullptr));
+            float ms = time_ms([&] { tld4_kernel<<<blocks, threads>>>(t, F, sink); });
+            printf(" \"tld4_a2d_%s_F%d_ginstr_s\": %.2f,\n", fmt == 0 ? "u8" : (fmt == 1 ? "f16" : "f32"), F, fetches / ms * 1e-6);
+            CK(cudaDestroyTextureObject(t));
+            CK(cudaFreeArray(larr));
         }
         {
             void* buf;

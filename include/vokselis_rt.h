@@ -94,7 +94,9 @@ typedef enum VkrtDtype { VKRT_U8 = 0, VKRT_F16 = 1, VKRT_F32 = 2 } VkrtDtype;
 typedef enum VkrtLayout {
     VKRT_LAYOUT_LINEAR = 0,  /* as uploaded: x fastest, then y, then z */
     VKRT_LAYOUT_BRICKED = 1, /* cache-line bricks, see DESIGN.md */
-    VKRT_LAYOUT_TEXTURE = 2  /* cudaArray + tex3D */
+    VKRT_LAYOUT_TEXTURE = 2, /* cudaArray + tex3D */
+    VKRT_LAYOUT_GATHER = 3   /* M1 only: layered cudaArray + two tld4 gathers per sample (the 8 taps in 2 texture
+                                instructions), fp32 interpolation weights in the SM: exact like LINEAR */
 } VkrtLayout;
 
 /* Everything the reference hard-codes as a WGSL literal or Rust const on this path. Defaults

@@ -179,7 +179,10 @@ def test_m0_constant_alpha_closed_form(rt, oracle, xor_cam):
 
 @pytest.mark.parametrize("dtype", [np.uint8, np.float16, np.float32])
 @pytest.mark.parametrize("skip", [0, 1])
-def test_m1_linear_matches_oracle(rt, oracle, xor_cam, dtype, skip):
+@pytest.mark.parametrize("layout", [abi.LAYOUT_LINEAR, abi.LAYOUT_GATHER])
+def test_m1_exact_paths_match_oracle(rt, oracle, xor_cam, dtype, skip, layout):
+    """Both fp32-weight trilinear paths — LINEAR (8 loads) and GATHER (two tld4 on a layered texture) —
+    are parity-grade: 2/255, 50 dB, bit-exact hit mask."""
     from vokselis_b200 import volumes
 
     W, H, n = 480, 270, 64
@@ -191,7 +194,7 @@ def test_m1_linear_matches_oracle(rt, oracle, xor_cam, dtype, skip):
     with rt.Context(0, W, H) as ctx:
         ctx.upload_scalar(vol)
         q = rt.default_params(abi.MODE_M1)
-        q.skip_empty, q.count_samples = skip, 1
+        q.skip_empty, q.count_samples, q.layout = skip, 1, layout
         ctx.set_params(q)
         ctx.render(cam)
         ctx.present()
@@ -228,6 +231,53 @@ def test_m1_texture_within_stated_tolerance(rt, oracle):
     check_images(got8, oracle.present(ref), max_delta=8, min_psnr=45.0)
 
 
+# ---- committed golden vectors (outputs of the reference's own WGSL, tests/golden/make_golden.py) ---
+def _cam_from(arr):
+    return abi.CameraUniform.from_buffer_copy(arr.tobytes())
+
+
+@pytest.mark.parametrize("layout", LAYOUTS_M0)
+def test_golden_g1_xor_pipeline(rt, oracle, layout):
+    from pathlib import Path
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "g1_xor32_160x90.npz")
+    cam = _cam_from(g["cam"])
+    with rt.Context(0, 160, 90) as ctx:
+        ctx.upload_rgba16f(g["color"], g["normal"])
+        q = rt.default_params(abi.MODE_M0)
+        q.layout, q.skip_empty, q.tile_size = layout, 1, int(g["tile_size"])
+        ctx.set_params(q)
+        ctx.render(cam)
+        ctx.present()
+        single, single8 = ctx.readback(), ctx.readback_rgba8()
+        ctx.resize(160, 90)
+        ctx.render_tiles(cam, g["table"])
+        tiled = ctx.readback()
+    assert np.array_equal(single, tiled)
+    check_images(single8, g["present"])
+    md, ok = hdr_close(single, g["single"])
+    assert ok, md
+
+
+def test_golden_g2_adversarial_volume(rt, oracle):
+    """NaN/inf normals, negative alpha, dims straddling the dt floor, eye inside the box."""
+    from pathlib import Path
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "g2_random192x12x10_128x72.npz")
+    with rt.Context(0, 128, 72) as ctx:
+        ctx.upload_rgba16f(g["color"], g["normal"])
+        for layout in LAYOUTS_M0:
+            for skip in (0, 1):
+                q = rt.default_params(abi.MODE_M0)
+                q.layout, q.skip_empty = layout, skip
+                ctx.set_params(q)
+                for ck, fk in (("cam", "frame"), ("cam_inside", "frame_inside")):
+                    ctx.render(_cam_from(g[ck]))
+                    got = ctx.readback()
+                    assert not np.isnan(got.view(np.float16).astype(np.float32)).any()
+                    check_images(oracle.present(got), oracle.present(g[fk]))
+
+
 def test_present_matches_oracle(rt, oracle, noise64, xor_cam):
     W, H = 640, 360
     color, normal = noise64
@@ -243,8 +293,10 @@ def test_present_matches_oracle(rt, oracle, noise64, xor_cam):
 
 def test_generate_xor_close_to_oracle(rt, oracle):
     """Device generator (shaders/xor.wgsl) vs oracle. `hash` is fract(sin(h)*43758.5453): one ulp of
-    sin() moves the hash by ~2.6e-3, so parity is stated as: alpha within 0.02 everywhere, 0.002 mean;
-    identical empty-space (alpha == 0) mask."""
+    sin() moves the hash by ~2.6e-3 and, where the product sits next to an integer, wraps it by ~1
+    (measured on B200: mean |delta alpha| 1.2e-4, max 0.48 on a handful of voxels). Parity is therefore
+    stated statistically: mean <= 1e-3, at most 0.5 % of voxels off by more than 0.01, identical
+    empty-space (alpha == 0) and NaN-normal masks. Raycast parity tests use oracle-generated bytes."""
     n = 64
     with rt.Context(0, 64, 64) as ctx:
         ctx.generate_xor(n, 0)
@@ -253,7 +305,9 @@ def test_generate_xor_close_to_oracle(rt, oracle):
     a = color[..., 3].view(np.float16).astype(np.float32)
     ra = rc[..., 3].view(np.float16).astype(np.float32)
     assert np.array_equal(a == 0, ra == 0)
-    assert np.abs(a - ra).max() <= 0.02 and np.abs(a - ra).mean() <= 0.002
+    d = np.abs(a - ra)
+    print(f"generator alpha: max |delta| {d.max():.5f}, mean {d.mean():.6f}, frac > 1e-3: {(d > 1e-3).mean():.4f}")
+    assert d.mean() <= 1e-3 and (d > 0.01).mean() <= 5e-3, (d.max(), d.mean(), (d > 0.01).mean())
     assert np.array_equal(np.isnan(normal.view(np.float16)[..., 0]), np.isnan(rn.view(np.float16)[..., 0]))
 
 

@@ -75,8 +75,8 @@ struct VkrtContext {
     void* lin_a = nullptr;  // rgba16f colour | scalar grid (upload layout)
     void* lin_b = nullptr;  // rgba16f normal
     uint4* bricked = nullptr;
-    cudaArray_t arr_a = nullptr, arr_b = nullptr;
-    cudaTextureObject_t tex_a = 0, tex_b = 0;
+    cudaArray_t arr_a = nullptr, arr_b = nullptr, arr_g = nullptr;
+    cudaTextureObject_t tex_a = 0, tex_b = 0, tex_g = 0;  // tex_g: layered + gather (LAYOUT_GATHER)
     uint8_t* dist = nullptr;  // brick distance field (0 = occupied)
     // tile offsets
     VkrtOffset* d_offsets = nullptr;
@@ -89,6 +89,10 @@ namespace {
 void free_layouts(VkrtContext* c) {
     if (c->tex_a) cudaDestroyTextureObject(c->tex_a);
     if (c->tex_b) cudaDestroyTextureObject(c->tex_b);
+    if (c->tex_g) cudaDestroyTextureObject(c->tex_g);
+    if (c->arr_g) cudaFreeArray(c->arr_g);
+    c->tex_g = 0;
+    c->arr_g = nullptr;
     if (c->arr_a) cudaFreeArray(c->arr_a);
     if (c->arr_b) cudaFreeArray(c->arr_b);
     if (c->bricked) cudaFree(c->bricked);
@@ -172,6 +176,7 @@ int ensure_layout(VkrtContext* c) {
     const int layout = c->params.layout;
     if (layout == VKRT_LAYOUT_LINEAR) return VKRT_OK;
     if (c->kind == VOL_RGBA16F) {
+        if (layout == VKRT_LAYOUT_GATHER) return fail(VKRT_ERR_UNSUPPORTED, "layout GATHER is for scalar volumes (mode M1)");
         if (layout == VKRT_LAYOUT_BRICKED && !c->bricked) {
             const size_t total = (size_t)c->nbx * c->nby * c->nbz * 512;
             CK(cudaMalloc(&c->bricked, total * sizeof(uint4)));
@@ -210,6 +215,23 @@ int ensure_layout(VkrtContext* c) {
         }
         return VKRT_OK;
     }
+    if (layout == VKRT_LAYOUT_GATHER) {
+        if (!c->tex_g) {
+            if (c->nz > 2048) return fail(VKRT_ERR_UNSUPPORTED, "layout GATHER needs nz <= 2048 (2-D layered texture limit)");
+            cudaChannelFormatDesc d;
+            size_t eb;
+            if (c->dtype == VKRT_U8) { d = cudaCreateChannelDesc<unsigned char>(); eb = 1; }
+            else if (c->dtype == VKRT_F16) { d = cudaCreateChannelDescHalf(); eb = 2; }
+            else { d = cudaCreateChannelDesc<float>(); eb = 4; }
+            const cudaExtent ext = make_cudaExtent((size_t)c->nx, (size_t)c->ny, (size_t)c->nz);
+            CK(cudaMalloc3DArray(&c->arr_g, &d, ext, cudaArrayLayered));  // (Layered | TextureGather is rejected by the runtime; tld4.a2d works on a plain layered array)
+            int rc = copy_to_array(c->arr_g, c->lin_a, eb, c->nx, c->ny, c->nz, c->stream);
+            if (rc) return rc;
+            rc = make_texture(c->arr_g, true, false, c->dtype == VKRT_U8, &c->tex_g);
+            if (rc) return rc;
+        }
+        return VKRT_OK;
+    }
     return fail(VKRT_ERR_UNSUPPORTED, "layout BRICKED is not available for scalar volumes");
 }
 
@@ -240,7 +262,7 @@ bool params_ok(const VkrtParams* p, std::string& why) {
     if (!p) { why = "params is NULL"; return false; }
     if (p->struct_size != sizeof(VkrtParams)) { why = "VkrtParams.struct_size mismatch"; return false; }
     if (p->mode != VKRT_MODE_M0 && p->mode != VKRT_MODE_M1) { why = "unknown mode"; return false; }
-    if (p->layout < VKRT_LAYOUT_LINEAR || p->layout > VKRT_LAYOUT_TEXTURE) { why = "unknown layout"; return false; }
+    if (p->layout < VKRT_LAYOUT_LINEAR || p->layout > VKRT_LAYOUT_GATHER) { why = "unknown layout"; return false; }
     if (!(p->dt_scale > 0.0f)) { why = "dt_scale must be > 0"; return false; }
     if (!(p->dt_floor >= 0.0f)) { why = "dt_floor must be >= 0"; return false; }
     if (p->tile_size <= 0 || p->tile_size > 16384) { why = "tile_size out of range"; return false; }
@@ -287,7 +309,7 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     } else {
         A.vol_a = c->lin_a;
     }
-    A.tex_a = c->tex_a; A.tex_b = c->tex_b;
+    A.tex_a = (layout == VKRT_LAYOUT_GATHER) ? c->tex_g : c->tex_a; A.tex_b = c->tex_b;
     A.nx = c->nx; A.ny = c->ny; A.nz = c->nz;
     A.fx = (float)c->nx; A.fy = (float)c->ny; A.fz = (float)c->nz;
     A.hx = A.fx / 2.0f; A.hy = A.fy / 2.0f; A.hz = A.fz / 2.0f;

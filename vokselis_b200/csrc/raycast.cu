@@ -9,6 +9,9 @@
 // warp walk through neighbouring voxels and their texel requests coalesce into a handful of 32-B
 // sectors. All tiles of a frame go out in ONE launch (grid.z = tile). Not a contraction: no tensor
 // cores; the limiter is the texel path (TEX/L1 -> L2 -> HBM) and the dependent ALU chain per sample.
+#include <cstdio>
+#include <cstdlib>
+
 #include "raycast.cuh"
 #include "vkrt_device.cuh"
 
@@ -72,6 +75,16 @@ __device__ __forceinline__ void m0_fetch(const RenderArgs& A, int ix, int iy, in
     }
 }
 
+// tld4 on a 2-D layered texture: the four texels of the bilinear footprint around (x, y) of `layer`,
+// returned as (x0,y1), (x1,y1), (x1,y0), (x0,y0). CUDA C++ only exposes gather for plain 2-D textures.
+__device__ __forceinline__ float4 tld4_layer(cudaTextureObject_t tex, int layer, float x, float y) {
+    float4 r;
+    asm("tld4.r.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(tex), "r"(layer), "f"(x), "f"(y));
+    return r;
+}
+
 // ---- scalar sample, M1 (linear filter, clamp-to-edge) ----------------------------------------
 template <int LAYOUT, int DTYPE>
 __device__ __forceinline__ float m1_sample(const RenderArgs& A, float qx, float qy, float qz) {
@@ -81,6 +94,19 @@ __device__ __forceinline__ float m1_sample(const RenderArgs& A, float qx, float 
     const float ux = qx - 0.5f, uy = qy - 0.5f, uz = qz - 0.5f;
     const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
     const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+    if (LAYOUT == VKRT_LAYOUT_GATHER) {
+        // The 8 taps in two texture instructions; the gather point sits exactly between the four texels,
+        // far from any footprint-selection boundary. x/y clamp-to-edge is the texture's address mode,
+        // z is clamped here. Weights stay fp32 (unlike tex3D's 8-bit weights): same result as LINEAR.
+        const int z0 = (int)flz;
+        const int za = min(max(z0, 0), A.nz - 1), zb = min(max(z0 + 1, 0), A.nz - 1);
+        const float4 g0 = tld4_layer(A.tex_a, za, flx + 1.0f, fly + 1.0f);
+        const float4 g1 = tld4_layer(A.tex_a, zb, flx + 1.0f, fly + 1.0f);
+        const float c00 = g0.w + fx * (g0.z - g0.w), c10 = g0.x + fx * (g0.y - g0.x);
+        const float c01 = g1.w + fx * (g1.z - g1.w), c11 = g1.x + fx * (g1.y - g1.x);
+        const float c0 = c00 + fy * (c10 - c00), c1 = c01 + fy * (c11 - c01);
+        return c0 + fz * (c1 - c0);
+    }
     const int x0 = (int)flx, y0 = (int)fly, z0 = (int)flz;
     // clamp-to-edge on both taps, like the oracle's scalar_at()
     const int xa2 = min(max(x0, 0), A.nx - 1), xb2 = min(max(x0 + 1, 0), A.nx - 1);
@@ -100,9 +126,9 @@ __device__ __forceinline__ float m1_sample(const RenderArgs& A, float qx, float 
 }
 
 template <int MODE, int LAYOUT, int DTYPE, bool SKIP, bool DBG>
-__global__ void __launch_bounds__(64) raycast_kernel(const __grid_constant__ RenderArgs A) {
+__global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ RenderArgs A) {
     // ---- which pixel -------------------------------------------------------------------------
-    const uint32_t gx = blockIdx.x * 8u + threadIdx.x, gy = blockIdx.y * 8u + threadIdx.y;
+    const uint32_t gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y * blockDim.y + threadIdx.y;
     float offx = 0.0f, offy = 0.0f;
     uint32_t px = gx, py = gy;
     bool valid = true;
@@ -142,6 +168,9 @@ __global__ void __launch_bounds__(64) raycast_kernel(const __grid_constant__ Ren
             rqy = fabsf(dqy) > 1e-12f ? 1.0f / dqy : 1e30f;
             rqz = fabsf(dqz) > 1e-12f ? 1.0f / dqz : 1e30f;
         }
+        // (A while-while traversal — every lane first advances to its next non-empty sample, then the warp
+        // votes and shades together — was measured 1.9x SLOWER on B200: the skip phase costs about as much
+        // as a sample here, and it ran at lower lane utilisation. profiles/r01_whilewhile_ab.md)
         float t = t0;
         while (t < t1) {
             // p = eye + t*dir ; q = (p + 1) * (N/2) — exact, decides the texel
@@ -225,7 +254,7 @@ __global__ void __launch_bounds__(64) raycast_kernel(const __grid_constant__ Ren
         const unsigned h = __reduce_add_sync(0xffffffffu, hit ? 1u : 0u);
         const unsigned it = __reduce_add_sync(0xffffffffu, hit ? iters : 0u);
         const unsigned fe = __reduce_add_sync(0xffffffffu, hit ? fetched : 0u);
-        if (((threadIdx.y * 8 + threadIdx.x) & 31) == 0) {
+        if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0) {
             atomicAdd(A.counters + 0, (unsigned long long)h);
             atomicAdd(A.counters + 1, (unsigned long long)it);
             atomicAdd(A.counters + 2, (unsigned long long)fe);
@@ -234,8 +263,7 @@ __global__ void __launch_bounds__(64) raycast_kernel(const __grid_constant__ Ren
 }
 
 template <int MODE, int LAYOUT, int DTYPE>
-cudaError_t launch3(const RenderArgs& A, dim3 grid, cudaStream_t s, bool skip, bool dbg) {
-    const dim3 block(8, 8, 1);
+cudaError_t launch3(const RenderArgs& A, dim3 grid, dim3 block, cudaStream_t s, bool skip, bool dbg) {
     if (skip) {
         if (dbg) raycast_kernel<MODE, LAYOUT, DTYPE, true, true><<<grid, block, 0, s>>>(A);
         else raycast_kernel<MODE, LAYOUT, DTYPE, true, false><<<grid, block, 0, s>>>(A);
@@ -249,26 +277,37 @@ cudaError_t launch3(const RenderArgs& A, dim3 grid, cudaStream_t s, bool skip, b
 }  // namespace
 
 cudaError_t launch_raycast(const RenderArgs& A, int mode, int layout, int dtype, bool skip, bool dbg, cudaStream_t s) {
+    // Block = bw x bh pixels; blockDim.x = 8 makes every warp an 8x4-pixel tile. VKRT_BLOCK=WxH overrides
+    // (exploration only; W*H must be a multiple of 32 and <= 256).
+    static int bw = 0, bh = 0;
+    if (bw == 0) {
+        bw = 8; bh = 8;
+        if (const char* e = getenv("VKRT_BLOCK")) {
+            int w = 0, h = 0;
+            if (sscanf(e, "%dx%d", &w, &h) == 2 && w > 0 && h > 0 && (w * h) % 32 == 0 && w * h <= 256) { bw = w; bh = h; }
+        }
+    }
+    const dim3 block((unsigned)bw, (unsigned)bh, 1);
     dim3 grid;
     if (A.n_tiles > 0) {
-        const unsigned g = (unsigned)((A.tile_size + 7) / 8);
-        grid = dim3(g, g, (unsigned)A.n_tiles);
+        grid = dim3((unsigned)((A.tile_size + bw - 1) / bw), (unsigned)((A.tile_size + bh - 1) / bh), (unsigned)A.n_tiles);
     } else {
-        grid = dim3((unsigned)((A.W + 7) / 8), (unsigned)((A.H + 7) / 8), 1);
+        grid = dim3((unsigned)((A.W + bw - 1) / bw), (unsigned)((A.H + bh - 1) / bh), 1);
     }
     if (mode == VKRT_MODE_M0) {
         switch (layout) {
-            case VKRT_LAYOUT_LINEAR: return launch3<VKRT_MODE_M0, VKRT_LAYOUT_LINEAR, 0>(A, grid, s, skip, dbg);
-            case VKRT_LAYOUT_BRICKED: return launch3<VKRT_MODE_M0, VKRT_LAYOUT_BRICKED, 0>(A, grid, s, skip, dbg);
-            case VKRT_LAYOUT_TEXTURE: return launch3<VKRT_MODE_M0, VKRT_LAYOUT_TEXTURE, 0>(A, grid, s, skip, dbg);
+            case VKRT_LAYOUT_LINEAR: return launch3<VKRT_MODE_M0, VKRT_LAYOUT_LINEAR, 0>(A, grid, block, s, skip, dbg);
+            case VKRT_LAYOUT_BRICKED: return launch3<VKRT_MODE_M0, VKRT_LAYOUT_BRICKED, 0>(A, grid, block, s, skip, dbg);
+            case VKRT_LAYOUT_TEXTURE: return launch3<VKRT_MODE_M0, VKRT_LAYOUT_TEXTURE, 0>(A, grid, block, s, skip, dbg);
         }
     } else {
-        if (layout == VKRT_LAYOUT_TEXTURE) return launch3<VKRT_MODE_M1, VKRT_LAYOUT_TEXTURE, 0>(A, grid, s, skip, dbg);
+        if (layout == VKRT_LAYOUT_TEXTURE) return launch3<VKRT_MODE_M1, VKRT_LAYOUT_TEXTURE, 0>(A, grid, block, s, skip, dbg);
+        if (layout == VKRT_LAYOUT_GATHER) return launch3<VKRT_MODE_M1, VKRT_LAYOUT_GATHER, 0>(A, grid, block, s, skip, dbg);
         if (layout == VKRT_LAYOUT_LINEAR) {
             switch (dtype) {
-                case VKRT_U8: return launch3<VKRT_MODE_M1, VKRT_LAYOUT_LINEAR, VKRT_U8>(A, grid, s, skip, dbg);
-                case VKRT_F16: return launch3<VKRT_MODE_M1, VKRT_LAYOUT_LINEAR, VKRT_F16>(A, grid, s, skip, dbg);
-                case VKRT_F32: return launch3<VKRT_MODE_M1, VKRT_LAYOUT_LINEAR, VKRT_F32>(A, grid, s, skip, dbg);
+                case VKRT_U8: return launch3<VKRT_MODE_M1, VKRT_LAYOUT_LINEAR, VKRT_U8>(A, grid, block, s, skip, dbg);
+                case VKRT_F16: return launch3<VKRT_MODE_M1, VKRT_LAYOUT_LINEAR, VKRT_F16>(A, grid, block, s, skip, dbg);
+                case VKRT_F32: return launch3<VKRT_MODE_M1, VKRT_LAYOUT_LINEAR, VKRT_F32>(A, grid, block, s, skip, dbg);
             }
         }
     }

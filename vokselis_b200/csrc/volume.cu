@@ -113,7 +113,12 @@ __global__ void __launch_bounds__(256) distance_step_kernel(const uint8_t* __res
 
 // ---- shaders/xor.wgsl -------------------------------------------------------------------------
 __device__ __forceinline__ float fractf(float x) { return x - floorf(x); }
-__device__ __forceinline__ float hash1(float h) { return fractf(sinf(h) * 43758.5453123f); }  // :18-20
+// :18-20. The product is rounded before the floor is subtracted (no FMA contraction): the hash amplifies
+// any rounding difference by 43758, so only sinf's own last-ulp differences from libm remain.
+__device__ __forceinline__ float hash1(float h) {
+    const float x = __fmul_rn(sinf(h), 43758.5453123f);
+    return __fsub_rn(x, floorf(x));
+}
 __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 __device__ float noise3(float x, float y, float z) {  // :22-33
     const float px = floorf(x), py = floorf(y), pz = floorf(z);

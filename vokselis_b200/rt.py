@@ -16,7 +16,10 @@ import numpy as np
 from . import abi
 from .abi import CameraUniform, Offset, Params, Stats, Uniform
 
-_SO = Path(__file__).resolve().parent / "libvokselis_rt.so"
+import os
+
+# VKRT_LIB overrides the library path (A/B runs of two builds on the same box).
+_SO = Path(os.environ.get("VKRT_LIB") or (Path(__file__).resolve().parent / "libvokselis_rt.so"))
 
 # Every symbol include/vokselis_rt.h declares (tests check the .so exports all of them).
 EXPORTS = [
