@@ -156,6 +156,12 @@ VKRT_API int vkrt_upload_scalar(VkrtContext* ctx, const void* data, int dtype, i
  * shaders/xor.wgsl `cs_main`, writing both rgba16f volumes on the device. `which`: 0 = live
  * `noise_volume` (:55-61), 1 = the dead bit-pattern `volume` (:46-53). Only `un->time` is read. */
 VKRT_API int vkrt_generate_xor(VkrtContext* ctx, const VkrtUniform* un, int n, int which);
+/* Synthetic scalar volumes of the shapes BASELINE.json names, generated on the device (no reference
+ * counterpart: the reference's only dataset, bonsai_256x256x256_uint8.raw, is missing from it).
+ * kind 0: hash noise box-filtered 3^3 (config 3); 1: 90 % empty 64^3 super-bricks, dense balls in the
+ * rest (config 4); 2: smooth lattice noise (config 5). Deterministic in (kind, seed, voxel coordinates). */
+VKRT_API int vkrt_generate_synthetic(VkrtContext* ctx, int kind, int dtype, int nx, int ny, int nz, uint32_t seed);
+VKRT_API int vkrt_download_scalar(VkrtContext* ctx, void* out);
 /* Read the device-resident rgba16f volumes back in the upload layout (tests, screenshots). */
 VKRT_API int vkrt_download_rgba16f(VkrtContext* ctx, uint16_t* color, uint16_t* normal);
 

@@ -208,6 +208,32 @@ def test_m1_exact_paths_match_oracle(rt, oracle, xor_cam, dtype, skip, layout):
     check_images(got8, oracle.present(ref))
 
 
+@pytest.mark.parametrize("kind,dtype,n", [(0, np.float16, 64), (1, np.uint8, 192), (2, np.float32, 64)])
+def test_synthetic_configs_small_match_oracle(rt, oracle, kind, dtype, n):
+    """The device-generated volumes of BASELINE configs 3-5 at reduced size: CUDA (GATHER, skipping on,
+    per-voxel steps) vs the oracle on the downloaded bytes — 2/255, 50 dB, bit-exact hit mask."""
+    W, H = 320, 180
+    cam = oracle.camera_uniform(2.6, -0.4, 0.9, (0, 0, 0), W / H)
+    with rt.Context(0, W, H) as ctx:
+        ctx.generate_synthetic(kind, dtype, n, seed=4)
+        vol = ctx.download_scalar()
+        assert vol.shape == (n, n, n) and vol.dtype == np.dtype(dtype)
+        if kind == 1:
+            assert 0 < (vol > 0).mean() < 0.35
+        q = rt.default_params(abi.MODE_M1)
+        q.dt_scale, q.skip_empty, q.count_samples, q.layout = 2.0, 1, 1, abi.LAYOUT_GATHER
+        ctx.set_params(q)
+        ctx.render(cam)
+        ctx.present()
+        got8, aux = ctx.readback_rgba8(), ctx.readback_aux()
+    p = abi.default_params(abi.MODE_M1)
+    p.dt_scale = 2.0
+    ref, ref_aux, _ = oracle.render(p, cam, W, H, scalar=vol)
+    assert np.array_equal(aux >> 31, ref_aux >> 31)
+    assert (aux != ref_aux).mean() <= 1e-3
+    check_images(got8, oracle.present(ref))
+
+
 def test_m1_texture_within_stated_tolerance(rt, oracle):
     """tex3D hardware trilinear uses 8-bit interpolation weights, so it is NOT the parity
     path (measured on B200: max |delta| 5/255 on this case). Its own, looser tolerance is stated here:

@@ -510,6 +510,33 @@ int vkrt_generate_xor(VkrtContext* c, const VkrtUniform* un, int n, int which) {
     return build_occupancy(c);
 }
 
+int vkrt_generate_synthetic(VkrtContext* c, int kind, int dtype, int nx, int ny, int nz, uint32_t seed) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    if (kind < 0 || kind > 2) return fail(VKRT_ERR_INVALID, "kind must be 0 (noise), 1 (sparse blobs) or 2 (smooth lattice)");
+    if (dtype < VKRT_U8 || dtype > VKRT_F32) return fail(VKRT_ERR_INVALID, "unknown dtype");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    free_volume(c);
+    int rc = set_dims(c, nx, ny, nz);
+    if (rc) return rc;
+    const size_t eb = dtype == VKRT_U8 ? 1 : (dtype == VKRT_F16 ? 2 : 4);
+    CK(cudaMalloc(&c->lin_a, (size_t)nx * ny * nz * eb));
+    CK(launch_synth(c->lin_a, kind, dtype, nx, ny, nz, 0, 0, 0, nx, ny, nz, seed, c->stream));
+    c->kind = VOL_SCALAR;
+    c->dtype = dtype;
+    return build_occupancy(c);
+}
+
+int vkrt_download_scalar(VkrtContext* c, void* out) {
+    if (!c || !out) return fail(VKRT_ERR_INVALID, "NULL argument");
+    if (c->kind != VOL_SCALAR) return fail(VKRT_ERR_NO_VOLUME, "no scalar volume resident");
+    CK(cudaSetDevice(c->device));
+    const size_t eb = c->dtype == VKRT_U8 ? 1 : (c->dtype == VKRT_F16 ? 2 : 4);
+    CK(cudaMemcpyAsync(out, c->lin_a, (size_t)c->nx * c->ny * c->nz * eb, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return VKRT_OK;
+}
+
 int vkrt_download_rgba16f(VkrtContext* c, uint16_t* color, uint16_t* normal) {
     if (!c || !color || !normal) return fail(VKRT_ERR_INVALID, "NULL argument");
     if (c->kind != VOL_RGBA16F) return fail(VKRT_ERR_NO_VOLUME, "no rgba16f volume resident");

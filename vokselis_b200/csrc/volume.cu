@@ -181,6 +181,72 @@ __global__ void __launch_bounds__(256) flush_l2_kernel(uint4* __restrict__ buf, 
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) buf[i] = make_uint4(tag, tag, tag, tag);
 }
 
+// ---- synthetic scalar volumes of the shapes BASELINE.json names (generated on the device: configs 3-5
+// are 2 GiB .. 256 GiB and cannot be staged from host files). Integer hashes + exactly rounded fp32
+// operations only, so the same (kind, seed, coordinates) give the same voxel on any GPU and any window.
+__device__ __forceinline__ uint32_t hash3(uint32_t x, uint32_t y, uint32_t z, uint32_t seed) {
+    uint32_t v = (x * 0x9E3779B1u) ^ (y * 0x85EBCA77u) ^ (z * 0xC2B2AE3Du) ^ (seed * 0x27D4EB2Fu);
+    v ^= v >> 15; v *= 0x2C1B3C6Du;
+    v ^= v >> 12; v *= 0x297A2D39u;
+    v ^= v >> 15;
+    return v;
+}
+__device__ __forceinline__ float hash01(int x, int y, int z, uint32_t seed) {
+    return (float)(hash3((uint32_t)x, (uint32_t)y, (uint32_t)z, seed) >> 8) * (1.0f / 16777216.0f);
+}
+// kind 0: uniform hash noise, box-filtered 3^3 once, mapped to a thin fog 0.08 + 0.14 * noise (config 3):
+// most values sit just above the transfer function's 0.1 threshold, so rays traverse the whole volume
+// (~N samples per ray) instead of terminating after a few samples
+__device__ float synth_noise(int x, int y, int z, int gnx, int gny, int gnz, uint32_t seed) {
+    float acc = 0.0f;
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx)
+                acc = __fadd_rn(acc, hash01(min(max(x + dx, 0), gnx - 1), min(max(y + dy, 0), gny - 1), min(max(z + dz, 0), gnz - 1), seed));
+    return __fadd_rn(0.08f, __fmul_rn(0.14f, __fmul_rn(acc, 1.0f / 27.0f)));
+}
+// kind 1: 90 % of the 64^3 super-bricks exactly 0 (Bernoulli per super-brick, so empties are spatially
+// coherent); an occupied super-brick holds a dense ball that fades to 0 before its faces (config 4)
+__device__ float synth_sparse(int x, int y, int z, uint32_t seed) {
+    const int sx = x >> 6, sy = y >> 6, sz = z >> 6;
+    if (hash3((uint32_t)sx, (uint32_t)sy, (uint32_t)sz, seed ^ 0xA511E9B3u) % 10u != 0u) return 0.0f;
+    const float fx = __fmul_rn((float)((x & 63) - 32) + 0.5f, 1.0f / 32.0f), fy = __fmul_rn((float)((y & 63) - 32) + 0.5f, 1.0f / 32.0f),
+                fz = __fmul_rn((float)((z & 63) - 32) + 0.5f, 1.0f / 32.0f);
+    const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)), __fmul_rn(fz, fz));
+    const float fall = fmaxf(__fsub_rn(1.0f, __fmul_rn(r2, 1.2f)), 0.0f);  // 0 for r >= 0.913: zero on the faces
+    const float grain = __fadd_rn(0.75f, __fmul_rn(0.25f, hash01(x >> 2, y >> 2, z >> 2, seed)));
+    return fminf(__fmul_rn(__fmul_rn(fall, 1.6f), grain), 1.0f);
+}
+// kind 2: smooth lattice noise, period 16 voxels, trilinear between hashed lattice points (config 5)
+__device__ float synth_smooth(int x, int y, int z, uint32_t seed) {
+    const int lx = x >> 4, ly = y >> 4, lz = z >> 4;
+    const float fx = (float)(x & 15) * (1.0f / 16.0f), fy = (float)(y & 15) * (1.0f / 16.0f), fz = (float)(z & 15) * (1.0f / 16.0f);
+    float c[2][2][2];
+    for (int k = 0; k < 2; ++k)
+        for (int j = 0; j < 2; ++j)
+            for (int i = 0; i < 2; ++i) c[k][j][i] = hash01(lx + i, ly + j, lz + k, seed);
+    float r[2];
+    for (int k = 0; k < 2; ++k) {
+        const float a = __fadd_rn(c[k][0][0], __fmul_rn(fx, __fsub_rn(c[k][0][1], c[k][0][0])));
+        const float b = __fadd_rn(c[k][1][0], __fmul_rn(fx, __fsub_rn(c[k][1][1], c[k][1][0])));
+        r[k] = __fadd_rn(a, __fmul_rn(fy, __fsub_rn(b, a)));
+    }
+    const float v = __fadd_rn(r[0], __fmul_rn(fz, __fsub_rn(r[1], r[0])));
+    return __fmul_rn(__fmul_rn(v, v), 0.9f);  // skew towards low values: part of the field is transparent
+}
+
+template <int DTYPE>
+__global__ void __launch_bounds__(256) synth_kernel(void* __restrict__ out, int kind, int nx, int ny, int nz, int ox, int oy, int oz,
+                                                    int gnx, int gny, int gnz, uint32_t seed) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nx * ny * nz) return;
+    const int x = (int)(i % (size_t)nx) + ox, y = (int)((i / (size_t)nx) % (size_t)ny) + oy, z = (int)(i / ((size_t)nx * ny)) + oz;
+    float v = kind == 0 ? synth_noise(x, y, z, gnx, gny, gnz, seed) : (kind == 1 ? synth_sparse(x, y, z, seed) : synth_smooth(x, y, z, seed));
+    if (DTYPE == VKRT_U8) ((uint8_t*)out)[i] = (uint8_t)__float2int_rn(__fmul_rn(fminf(fmaxf(v, 0.0f), 1.0f), 255.0f));
+    else if (DTYPE == VKRT_F16) ((__half*)out)[i] = __float2half_rn(v);
+    else ((float*)out)[i] = v;
+}
+
 // ---- device-side flags for the sort-first exchange (system scope: they live in rank 0's memory and
 // are touched by every GPU of the node over NVLink) ------------------------------------------------
 __device__ __forceinline__ unsigned long long global_timer_ns() {
@@ -212,6 +278,19 @@ __global__ void flag_set_kernel(unsigned long long* flag, unsigned long long v) 
 }
 
 }  // namespace
+
+cudaError_t launch_synth(void* out, int kind, int dtype, int nx, int ny, int nz, int ox, int oy, int oz, int gnx, int gny, int gnz,
+                         uint32_t seed, cudaStream_t s) {
+    const size_t total = (size_t)nx * ny * nz;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    switch (dtype) {
+        case VKRT_U8: synth_kernel<VKRT_U8><<<blocks, 256, 0, s>>>(out, kind, nx, ny, nz, ox, oy, oz, gnx, gny, gnz, seed); break;
+        case VKRT_F16: synth_kernel<VKRT_F16><<<blocks, 256, 0, s>>>(out, kind, nx, ny, nz, ox, oy, oz, gnx, gny, gnz, seed); break;
+        case VKRT_F32: synth_kernel<VKRT_F32><<<blocks, 256, 0, s>>>(out, kind, nx, ny, nz, ox, oy, oz, gnx, gny, gnz, seed); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
 
 cudaError_t launch_flag_wait(const unsigned long long* flag, unsigned long long target, unsigned long long* timeouts, cudaStream_t s) {
     flag_wait_kernel<<<1, 1, 0, s>>>(flag, target, timeouts);

@@ -31,7 +31,7 @@ EXPORTS = [
     "vkrt_reset_stats", "vkrt_timing_enable", "vkrt_timing_read", "vkrt_flush_l2", "vkrt_volume_info", "vkrt_camera_uniform", "vkrt_dispatch_optimal",
     "vkrt_sortfirst_create_root", "vkrt_sortfirst_join", "vkrt_sortfirst_leave", "vkrt_sortfirst_partition", "vkrt_sortfirst_render",
     "vkrt_sortfirst_consume", "vkrt_sortfirst_timeouts", "vkrt_sortfirst_wait", "vkrt_mark", "vkrt_mark_elapsed",
-    "vkrt_alloc_host", "vkrt_free_host",
+    "vkrt_alloc_host", "vkrt_free_host", "vkrt_generate_synthetic", "vkrt_download_scalar",
 ]
 
 
@@ -94,6 +94,8 @@ def lib() -> C.CDLL:
         "vkrt_sortfirst_wait": (ci, [vp, C.c_uint64, C.c_uint64]),
         "vkrt_mark": (ci, [vp, ci]),
         "vkrt_alloc_host": (ci, [C.c_size_t, C.POINTER(vp)]),
+        "vkrt_generate_synthetic": (ci, [vp, ci, ci, ci, ci, ci, C.c_uint32]),
+        "vkrt_download_scalar": (ci, [vp, vp]),
         "vkrt_free_host": (ci, [vp]),
         "vkrt_mark_elapsed": (ci, [vp, ci, ci, C.POINTER(cf)]),
         "vkrt_sortfirst_join": (ci, [vp, ci, vp]),
@@ -242,6 +244,19 @@ class Context:
     def generate_xor(self, n: int = 256, which: int = 0, uniform: Uniform | None = None):
         un = uniform if uniform is not None else self.global_uniform
         _check(lib().vkrt_generate_xor(self._h, C.byref(un), n, which))
+
+    def generate_synthetic(self, kind: int, dtype, nx: int, ny: int | None = None, nz: int | None = None, seed: int = 1):
+        """kind 0 noise / 1 sparse blobs / 2 smooth lattice; dtype numpy uint8/float16/float32."""
+        dt = {np.dtype(np.uint8): abi.DTYPE_U8, np.dtype(np.float16): abi.DTYPE_F16, np.dtype(np.float32): abi.DTYPE_F32}[np.dtype(dtype)]
+        _check(lib().vkrt_generate_synthetic(self._h, kind, dt, nx, ny or nx, nz or nx, seed))
+
+    def download_scalar(self) -> np.ndarray:
+        info = self.volume_info()
+        nx, ny, nz = info["dims"]
+        dt = {abi.DTYPE_U8: np.uint8, abi.DTYPE_F16: np.float16, abi.DTYPE_F32: np.float32}[info["dtype"]]
+        out = np.empty((nz, ny, nx), dt)
+        _check(lib().vkrt_download_scalar(self._h, _vp(out)))
+        return out
 
     def download_rgba16f(self):
         kind, dims = C.c_int(), (C.c_int * 3)()
