@@ -7,7 +7,7 @@ SRC := vokselis_b200/csrc
 OBJ := build/obj
 LIB := vokselis_b200/libvokselis_rt.so
 
-CU := $(SRC)/raycast.cu $(SRC)/volume.cu $(SRC)/present.cu $(SRC)/api.cu
+CU := $(SRC)/raycast.cu $(SRC)/sortlast.cu $(SRC)/volume.cu $(SRC)/present.cu $(SRC)/api.cu
 CUO := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(CU))
 HDR := $(SRC)/raycast.cuh $(SRC)/vkrt_device.cuh include/vokselis_rt.h vokselis_b200/host/vokselis.hpp
 

@@ -252,6 +252,28 @@ VKRT_API int vkrt_sortfirst_wait(VkrtContext* ctx, uint64_t frame_index, uint64_
 VKRT_API int vkrt_sortfirst_consume(VkrtContext* ctx, uint64_t frame_index, int do_present);
 /* Number of device-side waits that gave up after 10 s (a peer died); 0 on a healthy group. Synchronises. */
 VKRT_API int vkrt_sortfirst_timeouts(VkrtContext* ctx, uint64_t* out);
+/* ------------------------------------------------------------------------------------------ */
+/* Sort-last for volumes larger than one GPU (BASELINE config 5). The global grid gn[3] is cut into
+ * axis-aligned bricks (bounds multiples of 8); a context holds ONE brick [own_lo, own_hi) plus a
+ * one-voxel halo (the "window"). Every rank walks the same global t sequence per ray and evaluates
+ * the samples whose voxel index lies in its brick. A frame, with ranks in visibility order:
+ *   all   : vkrt_partial_alpha(cam, d_T)            T = per-pixel transmittance of the rank's brick
+ *   (all-gather T across ranks — any transport; vokselis_b200/sortlast.py uses NCCL)
+ *   all   : vkrt_partial_ain(d_T_all, ranks in front of me, n, d_ain)
+ *   all   : vkrt_partial_color(cam, d_ain, d_rgba)  premultiplied rgb + alpha, early termination exact
+ *   (sum d_rgba over ranks onto rank 0 — NCCL reduce)
+ *   rank 0: vkrt_partial_finalize(cam, d_sum)       writes the context's rgba16f frame
+ * All d_* are DEVICE pointers owned by the caller: W*H floats (T, ain), world*W*H (T_all), W*H*4 (rgba). */
+VKRT_API int vkrt_upload_window(VkrtContext* ctx, const void* a, const void* b /* M0 normals or NULL */, int dtype /* -1 = rgba16f pair */,
+                                const int gn[3], const int own_lo[3], const int own_hi[3]);
+VKRT_API int vkrt_generate_synthetic_window(VkrtContext* ctx, int kind, int dtype, const int gn[3], const int own_lo[3],
+                                            const int own_hi[3], uint32_t seed);
+VKRT_API int vkrt_window_info(VkrtContext* ctx, int win_lo[3], int win_n[3]);
+VKRT_API int vkrt_partial_alpha(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un, float* d_T);
+VKRT_API int vkrt_partial_ain(VkrtContext* ctx, const float* d_T_all, const int* ranks_before, int n_before, float* d_ain);
+VKRT_API int vkrt_partial_color(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un, const float* d_ain, float* d_rgba);
+VKRT_API int vkrt_partial_finalize(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un, const float* d_sum_rgba);
+
 /* Eight user events on the context's stream: vkrt_mark records one, vkrt_mark_elapsed returns the
  * device time between two (ms). */
 VKRT_API int vkrt_mark(VkrtContext* ctx, int idx);

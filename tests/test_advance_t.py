@@ -1,0 +1,54 @@
+"""The closed-form replacement of n repeated fp32 additions (advance_t in vkrt_device.cuh), restated in
+Python and checked against literal repeated addition. The CUDA function itself is covered on the GPU by
+test_empty_space_skipping_is_bit_exact (frames and iteration counts identical with skipping on/off)."""
+import numpy as np
+import pytest
+
+
+def advance_t(t: np.float32, dt: np.float32, n: int) -> np.float32:
+    db = int(np.float32(dt).view(np.uint32))
+    e_d, M = db >> 23, (db & 0x7FFFFF) | 0x800000
+    t = np.float32(t)
+    while n > 0:
+        tb = int(t.view(np.uint32))
+        e = tb >> 23
+        shift = e - e_d
+        if shift < 0 or e_d == 0 or e == 0:
+            t = np.float32(t + dt); n -= 1
+            continue
+        if shift > 24:
+            return t
+        if shift == 0:
+            inc = M
+        else:
+            m, rem, half = M >> shift, M & ((1 << shift) - 1), 1 << (shift - 1)
+            if rem == half:
+                t = np.float32(t + dt); n -= 1
+                continue
+            inc = m + (1 if rem > half else 0)
+        T = (tb & 0x7FFFFF) | 0x800000
+        room = (0xFFFFFF - T) // inc if inc else 0
+        k = min(n, room)
+        if k == 0:
+            t = np.float32(t + dt); n -= 1
+            continue
+        t = np.uint32(tb + k * inc).view(np.float32)
+        n -= k
+    return t
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_closed_form_equals_repeated_addition(seed):
+    rng = np.random.default_rng(seed)
+    cases = [(np.float32(1.5458316), np.float32(0.01), 277), (np.float32(0.0), np.float32(0.01), 300),
+             (np.float32(0.031), np.float32(0.01), 40), (np.float32(2.7), np.float32(1 / 4096), 5000)]
+    for _ in range(60):
+        t0 = np.float32(rng.uniform(0, 6) if rng.uniform() < 0.8 else rng.uniform(0, 0.05))
+        dt = np.float32(10 ** rng.uniform(-4, -1.5))
+        cases.append((t0, dt, int(rng.integers(1, 3000))))
+    for t0, dt, n in cases:
+        ref = np.float32(t0)
+        for _ in range(n):
+            ref = np.float32(ref + dt)
+        got = advance_t(t0, dt, n)
+        assert got.view(np.uint32) == ref.view(np.uint32), (t0, dt, n, got, ref)

@@ -63,3 +63,50 @@ def test_sortfirst_two_gpus_bit_exact():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29611", str(ROOT / "tests" / "mgpu_sortfirst_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+# ---- sort-last host logic (CPU) ------------------------------------------------------------------
+def test_brick_partition_covers_grid_once():
+    from vokselis_b200 import sortlast
+
+    for world in (1, 2, 4, 8):
+        grid = sortlast.brick_grid(world)
+        assert grid[0] * grid[1] * grid[2] == world
+        for gn in ((256, 256, 256), (4096, 4096, 4096), (200, 96, 72)):
+            cover = np.zeros(tuple(-(-n // 8) for n in gn)[::-1], np.int32)
+            for r in range(world):
+                lo, hi = sortlast.brick_range(gn, grid, r)
+                assert all(l % 8 == 0 for l in lo) and all(h % 8 == 0 or h == n for h, n in zip(hi, gn))
+                cover[lo[2] // 8:-(-hi[2] // 8), lo[1] // 8:-(-hi[1] // 8), lo[0] // 8:-(-hi[0] // 8)] += 1
+            assert (cover == 1).all(), (world, gn)
+
+
+def test_visibility_order_is_front_to_back_for_every_ray(oracle):
+    """For random eyes and rays: the bricks a ray crosses, in crossing order, appear in that order in
+    visibility_order()."""
+    from vokselis_b200 import sortlast
+
+    rng = np.random.default_rng(5)
+    gn = (256, 256, 256)
+    for world in (2, 4, 8):
+        grid = sortlast.brick_grid(world)
+        ranges = [sortlast.brick_range(gn, grid, r) for r in range(world)]
+        for _ in range(40):
+            eye = rng.uniform(-3, 3, 3)
+            order = sortlast.visibility_order(eye, gn, grid)
+            pos = {r: i for i, r in enumerate(order)}
+            for _ in range(50):
+                tgt = rng.uniform(-1, 1, 3)
+                d = (tgt - eye) / np.linalg.norm(tgt - eye)
+                ts = np.linspace(0, 8, 4000)
+                q = ((eye[None, :] + ts[:, None] * d[None, :]) + 1.0) * 128.0
+                inside = ((q >= 0) & (q < 256)).all(axis=1)
+                seq = []
+                for v in q[inside].astype(int):
+                    for r, (lo, hi) in enumerate(ranges):
+                        if all(lo[a] <= v[a] < hi[a] for a in range(3)):
+                            if not seq or seq[-1] != r:
+                                seq.append(r)
+                            break
+                assert len(seq) == len(set(seq)), "a ray re-entered a brick"
+                assert [pos[r] for r in seq] == sorted(pos[r] for r in seq), (eye, seq, order)

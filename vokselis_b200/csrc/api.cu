@@ -78,6 +78,11 @@ struct VkrtContext {
     cudaArray_t arr_a = nullptr, arr_b = nullptr, arr_g = nullptr;
     cudaTextureObject_t tex_a = 0, tex_b = 0, tex_g = 0;  // tex_g: layered + gather (LAYOUT_GATHER)
     uint8_t* dist = nullptr;  // brick distance field (0 = occupied)
+    // brick-partitioned (sort-last) state: the resident volume is a window of a larger global grid
+    bool windowed = false;
+    int gn[3] = {0, 0, 0}, win_lo[3] = {0, 0, 0}, own_lo[3] = {0, 0, 0}, own_hi[3] = {0, 0, 0};
+    int cell_lo[3] = {0, 0, 0}, cell_n[3] = {0, 0, 0};
+    int* d_before = nullptr;
     // tile offsets
     VkrtOffset* d_offsets = nullptr;
     int offsets_cap = 0;
@@ -108,6 +113,7 @@ void free_volume(VkrtContext* c) {
     c->lin_a = c->lin_b = nullptr;
     c->dist = nullptr;
     c->kind = VOL_NONE;
+    c->windowed = false;
 }
 void sf_release(VkrtContext* c) {
     if (!c->sf_base) return;
@@ -274,6 +280,7 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     if (!cam || !un) return fail(VKRT_ERR_INVALID, "camera/uniform is NULL");
     CK(cudaSetDevice(c->device));
     if (c->kind == VOL_NONE) return fail(VKRT_ERR_NO_VOLUME, "render before any volume upload/generate");
+    if (c->windowed) return fail(VKRT_ERR_INVALID, "the resident volume is one brick of a partitioned grid: use vkrt_partial_*");
     const VkrtParams& P = c->params;
     if (P.mode == VKRT_MODE_M0 && c->kind != VOL_RGBA16F) return fail(VKRT_ERR_INVALID, "mode M0 needs an rgba16f volume pair (vkrt_upload_rgba16f / vkrt_generate_xor)");
     if (P.mode == VKRT_MODE_M1 && c->kind != VOL_SCALAR) return fail(VKRT_ERR_INVALID, "mode M1 needs a scalar volume (vkrt_upload_scalar)");
@@ -416,6 +423,7 @@ int vkrt_destroy(VkrtContext* c) {
     free_frame(c);
     if (c->counters) cudaFree(c->counters);
     if (c->d_offsets) cudaFree(c->d_offsets);
+    if (c->d_before) cudaFree(c->d_before);
     if (c->flush_buf) cudaFree(c->flush_buf);
     for (cudaEvent_t e : c->ring_begin) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ring_end) cudaEventDestroy(e);
@@ -887,6 +895,159 @@ int vkrt_sortfirst_consume(VkrtContext* c, uint64_t frame_index, int do_present)
     c->frame = sf_slot(c, slot);
     if (do_present) CK(launch_present(c->frame, c->rgba8, c->W, c->H, c->stream));
     CK(launch_flag_set(sf_consumed(c), frame_index + 1, c->stream));
+    return VKRT_OK;
+}
+
+// ---- sort-last: one brick of a partitioned grid per context ------------------------------------------
+namespace {
+int fill_partial_args(VkrtContext* c, const VkrtCameraUniform* cam, PartialArgs& A) {
+    if (!c->windowed) return fail(VKRT_ERR_INVALID, "no windowed volume resident (vkrt_upload_window / vkrt_generate_synthetic_window)");
+    const VkrtParams& P = c->params;
+    if ((P.mode == VKRT_MODE_M0) != (c->kind == VOL_RGBA16F)) return fail(VKRT_ERR_INVALID, "mode does not match the resident volume kind");
+    if (P.mode == VKRT_MODE_M0 && P.clear_color[3] != 0.0f) return fail(VKRT_ERR_UNSUPPORTED, "sort-last needs clear_color.a == 0");
+    memset(&A, 0, sizeof A);
+    if (cam) memcpy(A.inv, cam->inv_proj, sizeof A.inv);
+    A.W = c->W; A.H = c->H;
+    A.gnx = c->gn[0]; A.gny = c->gn[1]; A.gnz = c->gn[2];
+    A.fx = (float)A.gnx; A.fy = (float)A.gny; A.fz = (float)A.gnz;
+    A.hx = A.fx / 2.0f; A.hy = A.fy / 2.0f; A.hz = A.fz / 2.0f;
+    A.vol_a = c->lin_a; A.vol_b = c->lin_b;
+    A.wx = c->win_lo[0]; A.wy = c->win_lo[1]; A.wz = c->win_lo[2];
+    A.nx = c->nx; A.ny = c->ny; A.nz = c->nz;
+    for (int i = 0; i < 3; ++i) { A.own_lo[i] = c->own_lo[i]; A.own_hi[i] = c->own_hi[i]; }
+    A.dist = c->dist;
+    A.cox = c->cell_lo[0]; A.coy = c->cell_lo[1]; A.coz = c->cell_lo[2];
+    A.cnx = c->cell_n[0]; A.cny = c->cell_n[1]; A.cnz = c->cell_n[2];
+    const int gmax = A.gnx > A.gny ? (A.gnx > A.gnz ? A.gnx : A.gnz) : (A.gny > A.gnz ? A.gny : A.gnz);
+    A.leap_eps = 16.0f * 1.1920929e-07f * (float)gmax;
+    A.dt_scale = P.dt_scale; A.dt_floor = P.dt_floor; A.alpha_threshold = P.alpha_threshold;
+    memcpy(A.clear, P.clear_color, sizeof A.clear);
+    return VKRT_OK;
+}
+
+int install_window(VkrtContext* c, int kind, int dtype, const int gn[3], const int own_lo[3], const int own_hi[3]) {
+    for (int i = 0; i < 3; ++i) {
+        if (gn[i] <= 0 || gn[i] > 8192 || own_lo[i] < 0 || own_hi[i] > gn[i] || own_lo[i] >= own_hi[i]) return fail(VKRT_ERR_INVALID, "bad grid / brick range");
+        if (own_lo[i] % 8 != 0 || (own_hi[i] % 8 != 0 && own_hi[i] != gn[i])) return fail(VKRT_ERR_INVALID, "brick bounds must be multiples of 8 (or the grid edge)");
+        c->gn[i] = gn[i]; c->own_lo[i] = own_lo[i]; c->own_hi[i] = own_hi[i];
+        c->win_lo[i] = own_lo[i] > 0 ? own_lo[i] - 1 : 0;  // one-voxel halo, clamped to the grid
+        c->cell_lo[i] = own_lo[i] >> 3;
+        c->cell_n[i] = ((own_hi[i] - 1) >> 3) - c->cell_lo[i] + 1;
+    }
+    c->nx = (own_hi[0] < gn[0] ? own_hi[0] + 1 : gn[0]) - c->win_lo[0];
+    c->ny = (own_hi[1] < gn[1] ? own_hi[1] + 1 : gn[1]) - c->win_lo[1];
+    c->nz = (own_hi[2] < gn[2] ? own_hi[2] + 1 : gn[2]) - c->win_lo[2];
+    c->nbx = c->nby = c->nbz = 0;
+    c->kind = kind;
+    c->dtype = dtype;
+    c->windowed = true;
+    return VKRT_OK;
+}
+
+int build_window_occupancy(VkrtContext* c) {
+    PartialArgs A;
+    const int mode = c->kind == VOL_RGBA16F ? VKRT_MODE_M0 : VKRT_MODE_M1;
+    VkrtParams keep = c->params;
+    vkrt_default_params(mode, &c->params);
+    int rc = fill_partial_args(c, nullptr, A);
+    c->params = keep;
+    if (rc) return rc;
+    const size_t cells = (size_t)A.cnx * A.cny * A.cnz;
+    uint8_t* scratch = nullptr;
+    CK(cudaMalloc(&c->dist, cells));
+    CK(cudaMalloc(&scratch, cells));
+    cudaError_t e = launch_window_occupancy(A, mode, c->dtype, c->dist, c->stream);
+    // outside the own cells is other ranks' territory (or outside the grid): no-ops for this rank
+    if (e == cudaSuccess) e = launch_distance_transform(c->dist, scratch, A.cnx, A.cny, A.cnz, 255, kMaxLeapBricks, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(scratch);
+    if (e != cudaSuccess) return cuda_fail(e, "build_window_occupancy");
+    return VKRT_OK;
+}
+}  // namespace
+
+int vkrt_upload_window(VkrtContext* c, const void* a, const void* b, int dtype, const int gn[3], const int own_lo[3], const int own_hi[3]) {
+    if (!c || !a || !gn || !own_lo || !own_hi) return fail(VKRT_ERR_INVALID, "NULL argument");
+    if (dtype < -1 || dtype > VKRT_F32) return fail(VKRT_ERR_INVALID, "dtype must be -1 (rgba16f pair) or a VkrtDtype");
+    if (dtype == -1 && !b) return fail(VKRT_ERR_INVALID, "rgba16f window needs both arrays");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    free_volume(c);
+    int rc = install_window(c, dtype == -1 ? VOL_RGBA16F : VOL_SCALAR, dtype == -1 ? 0 : dtype, gn, own_lo, own_hi);
+    if (rc) return rc;
+    const size_t eb = dtype == -1 ? 8 : (dtype == VKRT_U8 ? 1 : (dtype == VKRT_F16 ? 2 : 4));
+    const size_t bytes = (size_t)c->nx * c->ny * c->nz * eb;
+    CK(cudaMalloc(&c->lin_a, bytes));
+    CK(cudaMemcpyAsync(c->lin_a, a, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (dtype == -1) {
+        CK(cudaMalloc(&c->lin_b, bytes));
+        CK(cudaMemcpyAsync(c->lin_b, b, bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    return build_window_occupancy(c);
+}
+
+int vkrt_generate_synthetic_window(VkrtContext* c, int kind, int dtype, const int gn[3], const int own_lo[3], const int own_hi[3], uint32_t seed) {
+    if (!c || !gn || !own_lo || !own_hi) return fail(VKRT_ERR_INVALID, "NULL argument");
+    if (kind < 0 || kind > 2 || dtype < VKRT_U8 || dtype > VKRT_F32) return fail(VKRT_ERR_INVALID, "bad kind / dtype");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    free_volume(c);
+    int rc = install_window(c, VOL_SCALAR, dtype, gn, own_lo, own_hi);
+    if (rc) return rc;
+    const size_t eb = dtype == VKRT_U8 ? 1 : (dtype == VKRT_F16 ? 2 : 4);
+    CK(cudaMalloc(&c->lin_a, (size_t)c->nx * c->ny * c->nz * eb));
+    CK(launch_synth(c->lin_a, kind, dtype, c->nx, c->ny, c->nz, c->win_lo[0], c->win_lo[1], c->win_lo[2], gn[0], gn[1], gn[2], seed, c->stream));
+    return build_window_occupancy(c);
+}
+
+int vkrt_window_info(VkrtContext* c, int win_lo[3], int win_n[3]) {
+    if (!c || !c->windowed) return fail(VKRT_ERR_INVALID, "no windowed volume resident");
+    for (int i = 0; i < 3; ++i) if (win_lo) win_lo[i] = c->win_lo[i];
+    if (win_n) { win_n[0] = c->nx; win_n[1] = c->ny; win_n[2] = c->nz; }
+    return VKRT_OK;
+}
+
+int vkrt_partial_alpha(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, float* d_T) {
+    if (!c || !cam || !un || !d_T) return fail(VKRT_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    PartialArgs A;
+    int rc = fill_partial_args(c, cam, A);
+    if (rc) return rc;
+    A.T_out = d_T;
+    CK(launch_partial(A, c->params.mode, c->dtype, 1, c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_partial_ain(VkrtContext* c, const float* d_T_all, const int* ranks_before, int n_before, float* d_ain) {
+    if (!c || !d_ain || n_before < 0 || (n_before > 0 && (!d_T_all || !ranks_before))) return fail(VKRT_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(c->device));
+    if (!c->d_before) CK(cudaMalloc(&c->d_before, 1024 * sizeof(int)));
+    if (n_before > 1024) return fail(VKRT_ERR_INVALID, "too many ranks");
+    if (n_before > 0) CK(cudaMemcpyAsync(c->d_before, ranks_before, (size_t)n_before * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    const size_t n = (size_t)c->W * c->H;
+    CK(launch_partial_ain(d_T_all, n, c->d_before, n_before, c->params.initial_alpha, d_ain, n, c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_partial_color(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, const float* d_ain, float* d_rgba) {
+    if (!c || !cam || !un || !d_ain || !d_rgba) return fail(VKRT_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    PartialArgs A;
+    int rc = fill_partial_args(c, cam, A);
+    if (rc) return rc;
+    A.a_in = d_ain;
+    A.rgba_out = reinterpret_cast<float4*>(d_rgba);
+    CK(launch_partial(A, c->params.mode, c->dtype, 2, c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_partial_finalize(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, const float* d_sum_rgba) {
+    if (!c || !cam || !un || !d_sum_rgba) return fail(VKRT_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    PartialArgs A;
+    int rc = fill_partial_args(c, cam, A);
+    if (rc) return rc;
+    CK(launch_partial_finalize(A, reinterpret_cast<const float4*>(d_sum_rgba), c->frame, c->params.mode, c->params.m1_srgb, c->stream));
     return VKRT_OK;
 }
 

@@ -35,6 +35,31 @@ struct RenderArgs {
     unsigned long long* counters;  // optional [3]: rays_hit, samples_reference, samples_fetched
 };
 
+// One rank's view of a brick-partitioned volume (sortlast.cu): a WINDOW of the global grid.
+struct PartialArgs {
+    float inv[16];
+    int W, H;
+    int gnx, gny, gnz;             // global grid (drives ray/sample arithmetic: identical on every rank)
+    float fx, fy, fz, hx, hy, hz;  // global dims as f32, and halves
+    const void* vol_a;             // window array: scalar grid (M1) | colour texels (M0), x fastest
+    const void* vol_b;             // M0: normal texels
+    int wx, wy, wz;                // window origin in global voxel coordinates
+    int nx, ny, nz;                // window dims
+    int own_lo[3], own_hi[3];      // owned voxel range (multiples of 8, or the grid edge)
+    const uint8_t* dist;           // distance field over the OWN 8^3 cells
+    int cox, coy, coz, cnx, cny, cnz;  // first own cell (global cell coords) and own cells per axis
+    float leap_eps;
+    float dt_scale, dt_floor, alpha_threshold;
+    float clear[4];
+    const float* a_in;   // PASS_COLOR input,  W*H
+    float* T_out;        // PASS_ALPHA output, W*H
+    float4* rgba_out;    // PASS_COLOR output, W*H (premultiplied rgb, alpha out)
+};
+cudaError_t launch_partial(const PartialArgs& A, int mode, int dtype, int pass, cudaStream_t s);
+cudaError_t launch_partial_ain(const float* T_all, size_t stride, const int* before, int n_before, float a0, float* a_in, size_t n, cudaStream_t s);
+cudaError_t launch_partial_finalize(const PartialArgs& A, const float4* sum, uint2* frame, int mode, int m1_srgb, cudaStream_t s);
+cudaError_t launch_window_occupancy(const PartialArgs& A, int mode, int dtype, uint8_t* dist, cudaStream_t s);
+
 cudaError_t launch_raycast(const RenderArgs& A, int mode, int layout, int dtype, bool skip, bool dbg, cudaStream_t s);
 
 // volume.cu

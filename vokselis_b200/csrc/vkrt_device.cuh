@@ -68,6 +68,53 @@ __device__ __forceinline__ float step_dt(f3 dir, float nx, float ny, float nz, f
     return xmul(dt_scale, fmaxf(fminf(dx, fminf(dy, dz)), dt_floor));
 }
 
+// Exact result of `n` repeated additions t = fl(t + dt) (round-to-nearest-even), without executing them
+// one by one. Inside one binade every addition moves the 24-bit significand of t by the same integer
+// (dt expressed in ulps of t, rounded once), so the whole run is one integer multiply-add on the bit
+// pattern; binade crossings and the rare exact-tie case fall back to a real FADD for that step.
+// Requires t >= 0, dt > 0 (finite). Used to leap over empty space / other ranks' bricks while landing
+// on exactly the floats the reference's `t = t + dt` loop visits.
+__device__ __forceinline__ float advance_t(float t, float dt, int n) {
+    const uint32_t db = __float_as_uint(dt);
+    const int e_d = (int)(db >> 23);
+    const uint32_t M = (db & 0x7fffffu) | 0x800000u;
+    while (n > 0) {
+        const uint32_t tb = __float_as_uint(t);
+        const int e = (int)(tb >> 23);
+        const int shift = e - e_d;
+        // t in a lower binade than dt (incl. t == 0 / subnormal), or dt subnormal: plain step
+        if (shift < 0 || e_d == 0 || e == 0) {
+            t = xadd(t, dt);
+            --n;
+            continue;
+        }
+        if (shift > 24) return t;  // dt < ulp(t)/2: the reference loop would not advance either
+        uint32_t inc;
+        if (shift == 0) {
+            inc = M;
+        } else {
+            const uint32_t m = M >> shift, rem = M & ((1u << shift) - 1u), half = 1u << (shift - 1);
+            if (rem == half) {  // exact tie: result depends on the parity of t; take this step for real
+                t = xadd(t, dt);
+                --n;
+                continue;
+            }
+            inc = m + (rem > half ? 1u : 0u);
+        }
+        const uint32_t T = (tb & 0x7fffffu) | 0x800000u;
+        const uint32_t room = inc ? (0xffffffu - T) / inc : 0u;  // steps that stay inside this binade
+        const uint32_t k = min((uint32_t)n, room);
+        if (k == 0u) {  // the next step crosses into the next binade
+            t = xadd(t, dt);
+            --n;
+            continue;
+        }
+        t = __uint_as_float(tb + k * inc);
+        n -= (int)k;
+    }
+    return t;
+}
+
 // ---- shading (tolerance-checked, FMA allowed) ----------------------------------------------
 // smoothstep with compile-time edges: the division by (e1 - e0) becomes a multiplication by its
 // reciprocal (an IEEE fdiv is ~10 instructions plus a slow path for zero numerators; profiles/).

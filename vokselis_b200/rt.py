@@ -32,6 +32,8 @@ EXPORTS = [
     "vkrt_sortfirst_create_root", "vkrt_sortfirst_join", "vkrt_sortfirst_leave", "vkrt_sortfirst_partition", "vkrt_sortfirst_render",
     "vkrt_sortfirst_consume", "vkrt_sortfirst_timeouts", "vkrt_sortfirst_wait", "vkrt_mark", "vkrt_mark_elapsed",
     "vkrt_alloc_host", "vkrt_free_host", "vkrt_generate_synthetic", "vkrt_download_scalar",
+    "vkrt_upload_window", "vkrt_generate_synthetic_window", "vkrt_window_info", "vkrt_partial_alpha", "vkrt_partial_ain",
+    "vkrt_partial_color", "vkrt_partial_finalize",
 ]
 
 
@@ -96,6 +98,13 @@ def lib() -> C.CDLL:
         "vkrt_alloc_host": (ci, [C.c_size_t, C.POINTER(vp)]),
         "vkrt_generate_synthetic": (ci, [vp, ci, ci, ci, ci, ci, C.c_uint32]),
         "vkrt_download_scalar": (ci, [vp, vp]),
+        "vkrt_upload_window": (ci, [vp, vp, vp, ci, C.POINTER(ci * 3), C.POINTER(ci * 3), C.POINTER(ci * 3)]),
+        "vkrt_generate_synthetic_window": (ci, [vp, ci, ci, C.POINTER(ci * 3), C.POINTER(ci * 3), C.POINTER(ci * 3), C.c_uint32]),
+        "vkrt_window_info": (ci, [vp, C.POINTER(ci * 3), C.POINTER(ci * 3)]),
+        "vkrt_partial_alpha": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp]),
+        "vkrt_partial_ain": (ci, [vp, vp, vp, ci, vp]),
+        "vkrt_partial_color": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp, vp]),
+        "vkrt_partial_finalize": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp]),
         "vkrt_free_host": (ci, [vp]),
         "vkrt_mark_elapsed": (ci, [vp, ci, ci, C.POINTER(cf)]),
         "vkrt_sortfirst_join": (ci, [vp, ci, vp]),
@@ -375,6 +384,41 @@ class Context:
         v = C.c_uint64()
         _check(lib().vkrt_sortfirst_timeouts(self._h, C.byref(v)))
         return int(v.value)
+
+    # -- sort-last: this context holds one brick of a partitioned grid ------------------------
+    def upload_window(self, gn, own_lo, own_hi, *, scalar=None, color=None, normal=None):
+        """The window array = the global grid restricted to [own_lo-1, own_hi+1) (clamped): pass that slice."""
+        i3 = C.c_int * 3
+        if scalar is not None:
+            a = np.ascontiguousarray(scalar)
+            dt = {np.dtype(np.uint8): abi.DTYPE_U8, np.dtype(np.float16): abi.DTYPE_F16, np.dtype(np.float32): abi.DTYPE_F32}[a.dtype]
+            b = None
+        else:
+            a = np.ascontiguousarray(color).view(np.uint16)
+            b = np.ascontiguousarray(normal).view(np.uint16)
+            dt = -1
+        _check(lib().vkrt_upload_window(self._h, _vp(a), _vp(b), dt, C.byref(i3(*gn)), C.byref(i3(*own_lo)), C.byref(i3(*own_hi))))
+
+    def generate_synthetic_window(self, kind: int, dtype, gn, own_lo, own_hi, seed: int = 1):
+        i3 = C.c_int * 3
+        dt = {np.dtype(np.uint8): abi.DTYPE_U8, np.dtype(np.float16): abi.DTYPE_F16, np.dtype(np.float32): abi.DTYPE_F32}[np.dtype(dtype)]
+        _check(lib().vkrt_generate_synthetic_window(self._h, kind, dt, C.byref(i3(*gn)), C.byref(i3(*own_lo)), C.byref(i3(*own_hi)), seed))
+
+    def partial_alpha(self, cam: CameraUniform, d_T: int, uniform: Uniform | None = None):
+        un = uniform if uniform is not None else self.global_uniform
+        _check(lib().vkrt_partial_alpha(self._h, C.byref(cam), C.byref(un), d_T))
+
+    def partial_ain(self, d_T_all: int, ranks_before, d_ain: int):
+        rb = np.ascontiguousarray(np.asarray(list(ranks_before), np.int32))
+        _check(lib().vkrt_partial_ain(self._h, d_T_all, _vp(rb) if rb.size else None, int(rb.size), d_ain))
+
+    def partial_color(self, cam: CameraUniform, d_ain: int, d_rgba: int, uniform: Uniform | None = None):
+        un = uniform if uniform is not None else self.global_uniform
+        _check(lib().vkrt_partial_color(self._h, C.byref(cam), C.byref(un), d_ain, d_rgba))
+
+    def partial_finalize(self, cam: CameraUniform, d_sum: int, uniform: Uniform | None = None):
+        un = uniform if uniform is not None else self.global_uniform
+        _check(lib().vkrt_partial_finalize(self._h, C.byref(cam), C.byref(un), d_sum))
 
     def reset_stats(self):
         _check(lib().vkrt_reset_stats(self._h))

@@ -1,0 +1,106 @@
+"""Sort-last rendering of a volume that exceeds one GPU (BASELINE config 5): the global grid is cut into
+px x py x pz axis-aligned bricks, one per rank (one process per GPU). Host-side logic only; the kernels
+and the per-rank API are vkrt_partial_* (include/vokselis_rt.h, vokselis_b200/csrc/sortlast.cu).
+
+Per frame: every rank marches its brick alpha-only -> all-gather of the per-pixel
+transmittances (NCCL) -> each rank derives the alpha entering its brick from the bricks in front of
+it -> colour pass with exact early termination -> the premultiplied partials are SUMMED onto rank 0
+(NCCL reduce; with the alpha pre-pass the composite is commutative) -> rank 0 finalizes the frame.
+
+The reference has no counterpart: it is single-device. Its compositing operator,
+shaders/raycast_compute.wgsl:88-91, is what the partial passes split.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def brick_grid(world: int) -> tuple[int, int, int]:
+    """2 -> 2x1x1, 4 -> 2x2x1, 8 -> 2x2x2, ... (powers of two, split x then y then z round-robin)."""
+    g = [1, 1, 1]
+    i = 0
+    w = world
+    while w > 1:
+        if w % 2:
+            raise ValueError("world size must be a power of two")
+        g[i % 3] *= 2
+        w //= 2
+        i += 1
+    return tuple(g)
+
+
+def brick_range(gn, grid, rank: int):
+    """Owned voxel range [lo, hi) of `rank`; interior bounds are multiples of 8."""
+    px, py, pz = grid
+    b = (rank % px, (rank // px) % py, rank // (px * py))
+    lo, hi = [], []
+    for n, parts, k in zip(gn, grid, b):
+        cells = -(-n // 8)
+        c0, c1 = (cells * k) // parts, (cells * (k + 1)) // parts
+        lo.append(c0 * 8)
+        hi.append(min(c1 * 8, n))
+    return tuple(lo), tuple(hi)
+
+
+def visibility_order(eye, gn, grid) -> list[int]:
+    """Ranks front to back for rays leaving `eye` (world coordinates; the volume is the box [-1,1]^3).
+    Along any ray |coordinate - eye| grows monotonically on every axis, so per axis the bricks are met
+    in order of their distance from the eye's brick; two bricks that are ordered differently on two
+    axes are never crossed by the same ray. Any linear extension of the component-wise order is
+    therefore valid for ALL pixels: sort by the sum of per-axis nearness ranks."""
+    px, py, pz = grid
+    keys = []
+    for r in range(px * py * pz):
+        b = (r % px, (r // px) % py, r // (px * py))
+        s = 0
+        for axis in range(3):
+            n, parts = gn[axis], grid[axis]
+            # brick index the eye falls in (clamped): voxel coordinate of the eye on this axis
+            q = (eye[axis] + 1.0) * n / 2.0
+            cells = -(-n // 8)
+            bounds = [((cells * k) // parts) * 8 for k in range(parts)] + [n]
+            e = sum(1 for k in range(1, parts) if q >= bounds[k])
+            s += abs(b[axis] - e)
+        keys.append((s, r))
+    return [r for _, r in sorted(keys)]
+
+
+class SortLastGroup:
+    """Drives one frame across the ranks. `torch` tensors hold the exchange buffers; collectives run on
+    the context's own stream (torch.cuda.ExternalStream), so no host synchronisation is needed."""
+
+    def __init__(self, ctx, rank: int, world: int, gn, dist=None, grid=None):
+        import torch
+
+        if dist is None:
+            import torch.distributed as dist  # noqa: PLC0415
+        self.torch, self.dist = torch, dist
+        self.ctx, self.rank, self.world, self.gn = ctx, rank, world, tuple(gn)
+        self.grid = grid or brick_grid(world)
+        self.own_lo, self.own_hi = brick_range(self.gn, self.grid, rank)
+        n = ctx.width * ctx.height
+        dev = torch.device("cuda", ctx.device)
+        self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+        self.T = torch.empty(n, dtype=torch.float32, device=dev)
+        self.T_all = torch.empty(world * n, dtype=torch.float32, device=dev)
+        self.ain = torch.empty(n, dtype=torch.float32, device=dev)
+        self.rgba = torch.empty(n * 4, dtype=torch.float32, device=dev)
+
+    def render(self, cam):
+        """All ranks call this; rank 0's context frame holds the result afterwards. Asynchronous."""
+        torch, dist, ctx = self.torch, self.dist, self.ctx
+        eye = tuple(cam.view_position[:3])
+        order = visibility_order(eye, self.gn, self.grid)
+        before = order[: order.index(self.rank)]
+        with torch.cuda.stream(self.stream):
+            ctx.partial_alpha(cam, self.T.data_ptr())
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.T_all, self.T)
+            else:
+                self.T_all.copy_(self.T)
+            ctx.partial_ain(self.T_all.data_ptr(), before, self.ain.data_ptr())
+            ctx.partial_color(cam, self.ain.data_ptr(), self.rgba.data_ptr())
+            if self.world > 1:
+                dist.reduce(self.rgba, dst=0, op=dist.ReduceOp.SUM)
+            if self.rank == 0:
+                ctx.partial_finalize(cam, self.rgba.data_ptr())
