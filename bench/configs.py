@@ -8,7 +8,7 @@ per step on the dominant axis, like raycast_naive.wgsl:97-99). Prints one JSON l
 frames/s (device-timed per frame, max over ranks), ray-samples/s, the HBM roofline (these volumes
 exceed L2) and size-independent parity properties checked at FULL size: skip on == skip off and
 tile == single, bit for bit; for N > 1 the sort-first frame equals the single-GPU frame.
-usage: configs.py [--config 3|4|all] [--n N override of the volume edge] [--frames F] [--res WxH]
+usage: configs.py [--config 3|4|all] [--edge N override of the volume edge] [--frames F] [--res WxH]
 """
 import argparse
 import json
@@ -33,7 +33,7 @@ CONFIGS = {
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="all")
-    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--edge", dest="n", type=int, default=0)
     ap.add_argument("--frames", type=int, default=24)
     ap.add_argument("--res", default="3840x2160")
     ap.add_argument("--granularity", default="tiles")

@@ -159,7 +159,8 @@ VKRT_API int vkrt_generate_xor(VkrtContext* ctx, const VkrtUniform* un, int n, i
 /* Synthetic scalar volumes of the shapes BASELINE.json names, generated on the device (no reference
  * counterpart: the reference's only dataset, bonsai_256x256x256_uint8.raw, is missing from it).
  * kind 0: hash noise box-filtered 3^3 (config 3); 1: 90 % empty 64^3 super-bricks, dense balls in the
- * rest (config 4); 2: smooth lattice noise (config 5). Deterministic in (kind, seed, voxel coordinates). */
+ * rest (config 4); 2: smooth lattice noise; 3: the same as a thin fog (config 5). Deterministic in (kind, seed, voxel
+ * coordinates). */
 VKRT_API int vkrt_generate_synthetic(VkrtContext* ctx, int kind, int dtype, int nx, int ny, int nz, uint32_t seed);
 VKRT_API int vkrt_download_scalar(VkrtContext* ctx, void* out);
 /* Read the device-resident rgba16f volumes back in the upload layout (tests, screenshots). */

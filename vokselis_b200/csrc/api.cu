@@ -520,7 +520,7 @@ int vkrt_generate_xor(VkrtContext* c, const VkrtUniform* un, int n, int which) {
 
 int vkrt_generate_synthetic(VkrtContext* c, int kind, int dtype, int nx, int ny, int nz, uint32_t seed) {
     if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
-    if (kind < 0 || kind > 2) return fail(VKRT_ERR_INVALID, "kind must be 0 (noise), 1 (sparse blobs) or 2 (smooth lattice)");
+    if (kind < 0 || kind > 3) return fail(VKRT_ERR_INVALID, "kind must be 0 (noise fog), 1 (sparse blobs), 2 (smooth lattice) or 3 (thin smooth fog)");
     if (dtype < VKRT_U8 || dtype > VKRT_F32) return fail(VKRT_ERR_INVALID, "unknown dtype");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
@@ -988,7 +988,7 @@ int vkrt_upload_window(VkrtContext* c, const void* a, const void* b, int dtype, 
 
 int vkrt_generate_synthetic_window(VkrtContext* c, int kind, int dtype, const int gn[3], const int own_lo[3], const int own_hi[3], uint32_t seed) {
     if (!c || !gn || !own_lo || !own_hi) return fail(VKRT_ERR_INVALID, "NULL argument");
-    if (kind < 0 || kind > 2 || dtype < VKRT_U8 || dtype > VKRT_F32) return fail(VKRT_ERR_INVALID, "bad kind / dtype");
+    if (kind < 0 || kind > 3 || dtype < VKRT_U8 || dtype > VKRT_F32) return fail(VKRT_ERR_INVALID, "bad kind / dtype");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     free_volume(c);
