@@ -163,6 +163,11 @@ VKRT_API int vkrt_generate_xor(VkrtContext* ctx, const VkrtUniform* un, int n, i
  * coordinates). */
 VKRT_API int vkrt_generate_synthetic(VkrtContext* ctx, int kind, int dtype, int nx, int ny, int nz, uint32_t seed);
 VKRT_API int vkrt_download_scalar(VkrtContext* ctx, void* out);
+/* "Next" row N3: turn the resident scalar volume into the rgba16f pair raycast_compute.wgsl consumes —
+ * colour = (a/2, a/2, a/2, a), normal = normalised one-voxel backward-difference gradient of a and its
+ * length: shaders/xor.wgsl cs_main (:69-78) / gradient (:63-67) on a sampled field. After it, mode M0
+ * renders e.g. the bonsai scan through the compute raycaster (BASELINE configs[0]). */
+VKRT_API int vkrt_scalar_to_rgba16f(VkrtContext* ctx);
 /* Read the device-resident rgba16f volumes back in the upload layout (tests, screenshots). */
 VKRT_API int vkrt_download_rgba16f(VkrtContext* ctx, uint16_t* color, uint16_t* normal);
 

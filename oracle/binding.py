@@ -52,6 +52,8 @@ def lib() -> C.CDLL:
                                          C.c_int, C.POINTER(Brick), C.c_void_p, C.c_void_p, C.c_int]
         L.vko_generate_xor.restype = C.c_int
         L.vko_generate_xor.argtypes = [C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.vko_scalar_to_rgba16f.restype = C.c_int
+        L.vko_scalar_to_rgba16f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.vko_present.restype = C.c_int
         L.vko_present.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.vko_camera_uniform.restype = C.c_int
@@ -146,6 +148,17 @@ def render_partial(params: Params, cam: CameraUniform, W: int, H: int, lo, hi, *
         raise RuntimeError(f"vko_render_partial failed: {rc}")
     del keep
     return out
+
+
+def scalar_to_rgba16f(scalar: np.ndarray):
+    scalar = np.ascontiguousarray(scalar)
+    nz, ny, nx = scalar.shape
+    dt = {np.dtype(np.uint8): 0, np.dtype(np.float16): 1, np.dtype(np.float32): 2}[scalar.dtype]
+    color = np.empty((nz, ny, nx, 4), np.uint16)
+    normal = np.empty((nz, ny, nx, 4), np.uint16)
+    rc = lib().vko_scalar_to_rgba16f(_ptr(scalar), dt, nx, ny, nz, _ptr(color), _ptr(normal))
+    assert rc == 0
+    return color, normal
 
 
 def present(frame: np.ndarray) -> np.ndarray:

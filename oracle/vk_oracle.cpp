@@ -603,6 +603,27 @@ int vko_generate_xor(int n, float time, int which, uint16_t* color, uint16_t* no
     return VKRT_OK;
 }
 
+// "Next" row N3 — scalar grid -> rgba16f pair, the construction of shaders/xor.wgsl cs_main (:69-78) and
+// gradient (:63-67) on a sampled field: colour = (a/2, a/2, a/2, a); normal = normalize(a(p) - (a(p-ex),
+// a(p-ey), a(p-ez))) with one-voxel backward differences clamped at the border; normal.w = length(normal).
+int vko_scalar_to_rgba16f(const void* scalar, int dtype, int nx, int ny, int nz, uint16_t* color, uint16_t* normal) {
+    if (!scalar || !color || !normal || nx <= 0 || ny <= 0 || nz <= 0 || dtype < VKRT_U8 || dtype > VKRT_F32) return VKRT_ERR_INVALID;
+    VkoVolume V{};
+    V.nx = nx; V.ny = ny; V.nz = nz; V.dtype = dtype; V.scalar = scalar;
+#pragma omp parallel for schedule(static)
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x) {
+                const float a = scalar_at(&V, x, y, z);
+                v3 d = v3{a, a, a} - v3{scalar_at(&V, x - 1, y, z), scalar_at(&V, x, y - 1, z), scalar_at(&V, x, y, z - 1)};
+                v3 n = normalize3(d);
+                const size_t i = (((size_t)z * ny + y) * nx + x) * 4;
+                color[i] = f32_to_f16(a / 2.0f); color[i + 1] = f32_to_f16(a / 2.0f); color[i + 2] = f32_to_f16(a / 2.0f); color[i + 3] = f32_to_f16(a);
+                normal[i] = f32_to_f16(n.x); normal[i + 1] = f32_to_f16(n.y); normal[i + 2] = f32_to_f16(n.z); normal[i + 3] = f32_to_f16(length3(n));
+            }
+    return VKRT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // shaders/present.wgsl:23-35,111-119 — ACES then sRGB, written to an Rgba8Unorm target.
 // 1:1 (backbuffer size == target size): the bilinear `textureSample` at pixel centres returns the

@@ -58,6 +58,9 @@ VKO_API int vko_render_partial(const VkoVolume* vol, const VkrtParams* params, c
 /* shaders/xor.wgsl cs_main: which = 0 noise_volume (:55-61), 1 = bit-pattern volume (:46-53). */
 VKO_API int vko_generate_xor(int n, float time, int which, uint16_t* color, uint16_t* normal, int nthreads);
 
+/* N3: scalar grid -> (colour, normal) rgba16f pair (xor.wgsl cs_main/gradient on a sampled field). */
+VKO_API int vko_scalar_to_rgba16f(const void* scalar, int dtype, int nx, int ny, int nz, uint16_t* color, uint16_t* normal);
+
 /* shaders/present.wgsl:23-35,111-119 at 1:1 scale (no stretch): rgba16f -> rgba8 unorm. */
 VKO_API int vko_present(const uint16_t* frame, int W, int H, uint8_t* rgba8);
 

@@ -337,6 +337,40 @@ def test_generate_xor_close_to_oracle(rt, oracle):
     assert np.array_equal(np.isnan(normal.view(np.float16)[..., 0]), np.isnan(rn.view(np.float16)[..., 0]))
 
 
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_bonsai_through_compute_raycaster_baseline_config0(rt, oracle, dtype):
+    """BASELINE configs[0]: the bonsai scan (here its synthetic stand-in: the .raw is missing from the
+    reference) through raycast_compute.wgsl at 1280x720, one frame, the bonsai example's camera
+    (examples/bonsai/main.rs:68-74 remapped to the [-1,1]^3 box). N3 turns the scalar grid into the
+    rgba16f pair on the device; the conversion is bit-exact against the oracle and the frame is within
+    the parity tolerance."""
+    from vokselis_b200 import volumes
+
+    W, H, n = 1280, 720, 64
+    vol8 = volumes.bonsai_standin_u8(n, seed=1, blobs=12)
+    vol = vol8 if dtype == np.uint8 else (vol8.astype(np.float32) / 255.0)
+    cam = oracle.camera_uniform(2.0, 0.5, 1.0, (0, 0, 0), W / H)
+    rc, rn = oracle.scalar_to_rgba16f(vol)
+    p = abi.default_params(abi.MODE_M0)
+    ref, ref_aux, _ = oracle.render(p, cam, W, H, color=rc, normal=rn)
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_scalar(vol)
+        ctx.scalar_to_rgba16f()
+        color, normal = ctx.download_rgba16f()
+        assert np.array_equal(color, rc)
+        gn, on = normal.view(np.float16), rn.view(np.float16)
+        nan = np.isnan(on)  # zero gradient -> NaN normal on both sides; NaN payload bits are not compared
+        assert np.array_equal(np.isnan(gn), nan) and np.array_equal(normal[~nan], rn[~nan])
+        q = rt.default_params(abi.MODE_M0)
+        q.skip_empty, q.count_samples, q.layout = 1, 1, abi.LAYOUT_TEXTURE
+        ctx.set_params(q)
+        ctx.render(cam)
+        ctx.present()
+        got8, aux = ctx.readback_rgba8(), ctx.readback_aux()
+    assert np.array_equal(aux >> 31, ref_aux >> 31)
+    check_images(got8, oracle.present(ref))
+
+
 def test_frame_host_equals_render_present(rt, noise64, xor_cam):
     W, H = 640, 360
     color, normal = noise64

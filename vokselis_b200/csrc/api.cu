@@ -535,6 +535,27 @@ int vkrt_generate_synthetic(VkrtContext* c, int kind, int dtype, int nx, int ny,
     return build_occupancy(c);
 }
 
+int vkrt_scalar_to_rgba16f(VkrtContext* c) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    if (c->kind != VOL_SCALAR || c->windowed) return fail(VKRT_ERR_NO_VOLUME, "no (whole) scalar volume resident");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t bytes = (size_t)c->nx * c->ny * c->nz * 8;
+    void *col = nullptr, *nrm = nullptr;
+    CK(cudaMalloc(&col, bytes));
+    CK(cudaMalloc(&nrm, bytes));
+    CK(launch_scalar_to_rgba16f(c->lin_a, c->dtype, (uint2*)col, (uint2*)nrm, c->nx, c->ny, c->nz, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const int nx = c->nx, ny = c->ny, nz = c->nz;
+    free_volume(c);
+    int rc = set_dims(c, nx, ny, nz);
+    if (rc) { cudaFree(col); cudaFree(nrm); return rc; }
+    c->lin_a = col;
+    c->lin_b = nrm;
+    c->kind = VOL_RGBA16F;
+    return build_occupancy(c);
+}
+
 int vkrt_download_scalar(VkrtContext* c, void* out) {
     if (!c || !out) return fail(VKRT_ERR_INVALID, "NULL argument");
     if (c->kind != VOL_SCALAR) return fail(VKRT_ERR_NO_VOLUME, "no scalar volume resident");

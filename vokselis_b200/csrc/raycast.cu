@@ -95,6 +95,10 @@ __device__ __forceinline__ float m1_sample(const RenderArgs& A, float qx, float 
     const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
     const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
     if (LAYOUT == VKRT_LAYOUT_GATHER) {
+        // (Measured, ncu: in the dense case this path is bound by the texture DATA pipe — l1tex throughput
+        // 97 %, data_pipe_tex_wavefronts 83 %, ~35 sectors per warp-level tld4 because the lanes of a warp sit
+        // in different layers. Packing (z, z+1) pairs into two-channel texels so that both gathers share a
+        // footprint was tried and changed nothing: profiles/r01_gather_notes.md.)
         // The 8 taps in two texture instructions; the gather point sits exactly between the four texels,
         // far from any footprint-selection boundary. x/y clamp-to-edge is the texture's address mode,
         // z is clamped here. Weights stay fp32 (unlike tex3D's 8-bit weights): same result as LINEAR.
@@ -216,6 +220,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
                     } else if (n >= 48) {
                         t = advance_t(t, dt, n);  // closed form, bit-identical to n additions
                     } else {
+#pragma unroll 4
                         for (int j = 0; j < n; ++j) t = xadd(t, dt);
                     }
                     continue;

@@ -73,6 +73,7 @@ cudaError_t launch_occupancy_m1(const void* scalar, int dtype, int nx, int ny, i
 cudaError_t launch_distance_transform(uint8_t* dist, uint8_t* scratch, int nbx, int nby, int nbz, int border, int max_d, cudaStream_t s);
 cudaError_t launch_generate_xor(uint2* color, uint2* normal, int n, float time, int which, cudaStream_t s);
 
+cudaError_t launch_scalar_to_rgba16f(const void* vol, int dtype, uint2* color, uint2* normal, int nx, int ny, int nz, cudaStream_t s);
 cudaError_t launch_synth(void* out, int kind, int dtype, int nx, int ny, int nz, int ox, int oy, int oz, int gnx, int gny, int gnz,
                          uint32_t seed, cudaStream_t s);
 cudaError_t launch_flush_l2(uint4* buf, size_t n16, cudaStream_t s);

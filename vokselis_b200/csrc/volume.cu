@@ -181,6 +181,31 @@ __global__ void __launch_bounds__(256) flush_l2_kernel(uint4* __restrict__ buf, 
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) buf[i] = make_uint4(tag, tag, tag, tag);
 }
 
+// ---- "next" row N3: scalar volume -> the rgba16f pair raycast_compute.wgsl consumes, so that M0's lighting
+// works on u8/f16/f32 data (e.g. the bonsai scan through the compute raycaster = BASELINE configs[0]).
+// Same construction as shaders/xor.wgsl cs_main (:69-78) on a sampled field: colour = (a/2, a/2, a/2, a)
+// with a = the scalar; normal = normalize(a(p) - (a(p-ex), a(p-ey), a(p-ez))) — gradient() (:63-67) with
+// the one-voxel backward differences a grid offers, clamped at the border; normal.w = length(normal).
+// A zero gradient gives NaN normals, exactly like the reference's empty space.
+template <int DTYPE>
+__global__ void __launch_bounds__(256) scalar_to_rgba16f_kernel(const void* __restrict__ vol, uint2* __restrict__ color, uint2* __restrict__ normal,
+                                                                int nx, int ny, int nz) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nx * ny * nz) return;
+    const int x = (int)(i % (size_t)nx), y = (int)((i / (size_t)nx) % (size_t)ny), z = (int)(i / ((size_t)nx * ny));
+    const float a = load_scalar<DTYPE>(vol, i);
+    const float ax = load_scalar<DTYPE>(vol, i - (x > 0 ? 1 : 0));
+    const float ay = load_scalar<DTYPE>(vol, i - (y > 0 ? (size_t)nx : 0));
+    const float az = load_scalar<DTYPE>(vol, i - (z > 0 ? (size_t)nx * ny : 0));
+    const float dx = __fsub_rn(a, ax), dy = __fsub_rn(a, ay), dz = __fsub_rn(a, az);
+    const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const float n0 = __fdiv_rn(dx, len), n1 = __fdiv_rn(dy, len), n2 = __fdiv_rn(dz, len);
+    const float nl = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(n0, n0), __fmul_rn(n1, n1)), __fmul_rn(n2, n2)));
+    const float h = __fdiv_rn(a, 2.0f);
+    color[i] = pack_rgba16f(h, h, h, a);
+    normal[i] = pack_rgba16f(n0, n1, n2, nl);
+}
+
 // ---- synthetic scalar volumes of the shapes BASELINE.json names (generated on the device: configs 3-5
 // are 2 GiB .. 256 GiB and cannot be staged from host files). Integer hashes + exactly rounded fp32
 // operations only, so the same (kind, seed, coordinates) give the same voxel on any GPU and any window.
@@ -281,6 +306,18 @@ __global__ void flag_set_kernel(unsigned long long* flag, unsigned long long v) 
 }
 
 }  // namespace
+
+cudaError_t launch_scalar_to_rgba16f(const void* vol, int dtype, uint2* color, uint2* normal, int nx, int ny, int nz, cudaStream_t s) {
+    const size_t total = (size_t)nx * ny * nz;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    switch (dtype) {
+        case VKRT_U8: scalar_to_rgba16f_kernel<VKRT_U8><<<blocks, 256, 0, s>>>(vol, color, normal, nx, ny, nz); break;
+        case VKRT_F16: scalar_to_rgba16f_kernel<VKRT_F16><<<blocks, 256, 0, s>>>(vol, color, normal, nx, ny, nz); break;
+        case VKRT_F32: scalar_to_rgba16f_kernel<VKRT_F32><<<blocks, 256, 0, s>>>(vol, color, normal, nx, ny, nz); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
 
 cudaError_t launch_synth(void* out, int kind, int dtype, int nx, int ny, int nz, int ox, int oy, int oz, int gnx, int gny, int gnz,
                          uint32_t seed, cudaStream_t s) {

@@ -31,7 +31,7 @@ EXPORTS = [
     "vkrt_reset_stats", "vkrt_timing_enable", "vkrt_timing_read", "vkrt_flush_l2", "vkrt_volume_info", "vkrt_camera_uniform", "vkrt_dispatch_optimal",
     "vkrt_sortfirst_create_root", "vkrt_sortfirst_join", "vkrt_sortfirst_leave", "vkrt_sortfirst_partition", "vkrt_sortfirst_render",
     "vkrt_sortfirst_consume", "vkrt_sortfirst_timeouts", "vkrt_sortfirst_wait", "vkrt_mark", "vkrt_mark_elapsed",
-    "vkrt_alloc_host", "vkrt_free_host", "vkrt_generate_synthetic", "vkrt_download_scalar",
+    "vkrt_alloc_host", "vkrt_free_host", "vkrt_generate_synthetic", "vkrt_download_scalar", "vkrt_scalar_to_rgba16f",
     "vkrt_upload_window", "vkrt_generate_synthetic_window", "vkrt_window_info", "vkrt_partial_alpha", "vkrt_partial_ain",
     "vkrt_partial_color", "vkrt_partial_finalize",
 ]
@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
         "vkrt_alloc_host": (ci, [C.c_size_t, C.POINTER(vp)]),
         "vkrt_generate_synthetic": (ci, [vp, ci, ci, ci, ci, ci, C.c_uint32]),
         "vkrt_download_scalar": (ci, [vp, vp]),
+        "vkrt_scalar_to_rgba16f": (ci, [vp]),
         "vkrt_upload_window": (ci, [vp, vp, vp, ci, C.POINTER(ci * 3), C.POINTER(ci * 3), C.POINTER(ci * 3)]),
         "vkrt_generate_synthetic_window": (ci, [vp, ci, ci, C.POINTER(ci * 3), C.POINTER(ci * 3), C.POINTER(ci * 3), C.c_uint32]),
         "vkrt_window_info": (ci, [vp, C.POINTER(ci * 3), C.POINTER(ci * 3)]),
@@ -258,6 +259,10 @@ class Context:
         """kind 0 noise / 1 sparse blobs / 2 smooth lattice; dtype numpy uint8/float16/float32."""
         dt = {np.dtype(np.uint8): abi.DTYPE_U8, np.dtype(np.float16): abi.DTYPE_F16, np.dtype(np.float32): abi.DTYPE_F32}[np.dtype(dtype)]
         _check(lib().vkrt_generate_synthetic(self._h, kind, dt, nx, ny or nx, nz or nx, seed))
+
+    def scalar_to_rgba16f(self):
+        """N3: the resident scalar volume becomes the rgba16f colour/normal pair that mode M0 renders."""
+        _check(lib().vkrt_scalar_to_rgba16f(self._h))
 
     def download_scalar(self) -> np.ndarray:
         info = self.volume_info()
