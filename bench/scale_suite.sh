@@ -5,8 +5,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr
 mkdir -p gpurun_out
 $TR --master-port 29701 tests/mgpu_sortfirst_check.py 2>&1 | grep -E "MISMATCH|timeouts = [1-9]|Error" | head -5; echo "sortfirst check rc=${PIPESTATUS[0]}"
 $TR --master-port 29702 tests/mgpu_sortlast_check.py 2>&1 | grep -E "sort-last|Error" | head -5
-$TR --master-port 29703 bench.py --gpus $N --steps 360 --warmup 20 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; tail -2 gpurun_out/bench_n$N.err | cut -c1-300; python -c "
-import json; d=json.loads([l for l in open("gpurun_out/bench_n$N.json") if l.startswith("{")][0]); print('bench N=$N', d['value'], 'fps; ms/step', d['ms_per_step'], 'wall', d['wall_ms_per_step_incl_flush'], 'e2e', d['e2e']['value'], 'timeouts', d['sortfirst_wait_timeouts'])"
+$TR --master-port 29703 bench.py --gpus $N --steps 360 --warmup 20 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; tail -2 gpurun_out/bench_n$N.err | cut -c1-300; python bench/print_bench.py gpurun_out/bench_n$N.json
 $TR --master-port 29704 bench/configs.py --frames 12 2>&1 | grep '^{"config"' > gpurun_out/configs34_n$N.jsonl; python -c "
 import json
 for l in open('gpurun_out/configs34_n$N.jsonl'):

@@ -1,0 +1,63 @@
+// UNBUILT SOURCE (no Rust toolchain in this image): the binding of libvokselis_rt.so a maintainer adds to the
+// reference crate as src/cuda_rt.rs. See INTEGRATION.md.
+// Link: println!("cargo:rustc-link-lib=dylib=vokselis_rt"); println!("cargo:rustc-link-search=native=<dir>");
+use crate::{camera::CameraUniform, context::Uniform};
+use std::{ffi::CStr, os::raw::{c_char, c_int, c_void}};
+
+#[repr(C)] #[derive(Clone, Copy)] pub struct Offset { pub x: f32, pub y: f32 }          // examples/xor/main.rs:20-25
+#[repr(C)] #[derive(Clone, Copy)] pub struct VkrtParams {
+    pub struct_size: u32, pub mode: i32, pub dt_scale: f32, pub dt_floor: f32, pub alpha_threshold: f32,
+    pub initial_alpha: f32, pub clear_color: [f32; 4], pub tile_size: i32, pub layout: i32,
+    pub skip_empty: i32, pub count_samples: i32, pub m1_srgb: i32, pub reserved: [i32; 7],
+}
+#[repr(C)] pub struct VkrtContext { _private: [u8; 0] }
+
+extern "C" {
+    fn vkrt_create(device: c_int, width: c_int, height: c_int, out: *mut *mut VkrtContext) -> c_int;
+    fn vkrt_destroy(ctx: *mut VkrtContext) -> c_int;
+    fn vkrt_last_error() -> *const c_char;
+    fn vkrt_default_params(mode: c_int, out: *mut VkrtParams);
+    fn vkrt_set_params(ctx: *mut VkrtContext, p: *const VkrtParams) -> c_int;
+    fn vkrt_generate_xor(ctx: *mut VkrtContext, un: *const Uniform, n: c_int, which: c_int) -> c_int;
+    fn vkrt_upload_rgba16f(ctx: *mut VkrtContext, color: *const u16, normal: *const u16, nx: c_int, ny: c_int, nz: c_int) -> c_int;
+    fn vkrt_upload_scalar(ctx: *mut VkrtContext, data: *const c_void, dtype: c_int, nx: c_int, ny: c_int, nz: c_int) -> c_int;
+    fn vkrt_render(ctx: *mut VkrtContext, cam: *const CameraUniform, un: *const Uniform, offset: *const Offset) -> c_int;
+    fn vkrt_render_tiles(ctx: *mut VkrtContext, cam: *const CameraUniform, un: *const Uniform, offsets: *const Offset, n: c_int) -> c_int;
+    fn vkrt_present(ctx: *mut VkrtContext) -> c_int;
+    fn vkrt_readback(ctx: *mut VkrtContext, rgba16f: *mut u16) -> c_int;
+    fn vkrt_readback_rgba8(ctx: *mut VkrtContext, rgba8: *mut u8) -> c_int;
+    fn vkrt_sync(ctx: *mut VkrtContext) -> c_int;
+}
+
+pub struct CudaRaycast { ctx: *mut VkrtContext, pub width: u32, pub height: u32 }
+
+fn check(rc: c_int) -> color_eyre::eyre::Result<()> {
+    if rc == 0 { return Ok(()); }
+    let msg = unsafe { CStr::from_ptr(vkrt_last_error()) }.to_string_lossy().into_owned();
+    Err(color_eyre::eyre::eyre!("vokselis_rt error {rc}: {msg}"))
+}
+
+impl CudaRaycast {
+    pub fn new(device: i32, width: u32, height: u32) -> color_eyre::eyre::Result<Self> {
+        let mut ctx = std::ptr::null_mut();
+        check(unsafe { vkrt_create(device, width as _, height as _, &mut ctx) })?;
+        Ok(Self { ctx, width, height })
+    }
+    pub fn generate_xor(&self, un: &Uniform) -> color_eyre::eyre::Result<()> {
+        check(unsafe { vkrt_generate_xor(self.ctx, un, 256, 0) })
+    }
+    /// `single`: offset = None. `tile`: one call with the whole offset table.
+    pub fn record(&self, cam: &CameraUniform, un: &Uniform, offsets: Option<&[Offset]>) -> color_eyre::eyre::Result<()> {
+        check(unsafe { match offsets {
+            None => vkrt_render(self.ctx, cam, un, std::ptr::null()),
+            Some(t) => vkrt_render_tiles(self.ctx, cam, un, t.as_ptr(), t.len() as _),
+        }})
+    }
+    pub fn capture_frame(&self) -> color_eyre::eyre::Result<Vec<u8>> {
+        let mut px = vec![0u8; (self.width * self.height * 4) as usize];
+        check(unsafe { vkrt_present(self.ctx) })?;
+        check(unsafe { vkrt_readback_rgba8(self.ctx, px.as_mut_ptr()) })?;
+        Ok(px)
+    }
+}
+impl Drop for CudaRaycast { fn drop(&mut self) { unsafe { vkrt_destroy(self.ctx); } } }

@@ -402,3 +402,106 @@ def test_errors_are_codes_not_crashes(rt, xor_cam):
         bad.struct_size = 4
         with pytest.raises(rt.VokselisError):
             ctx.set_params(bad)
+
+
+# ---- edge cases ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("W,H", [(1279, 719), (33, 17), (8, 8), (1, 1)])
+def test_ragged_frame_sizes(rt, oracle, noise64, W, H):
+    """Frame sizes that are not multiples of the 8x8 block (the reference overshoots with ceil-div groups
+    and drops out-of-range stores, examples/xor/main.rs:232-233)."""
+    color, normal = noise64
+    cam = oracle.camera_uniform(3.0, -0.5, 1.0, (0, 0, 0), W / H)
+    ref, ref_aux, _ = oracle.render(abi.default_params(0), cam, W, H, color=color, normal=normal)
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_rgba16f(color, normal)
+        q = rt.default_params(abi.MODE_M0)
+        q.skip_empty, q.count_samples = 1, 1
+        ctx.set_params(q)
+        ctx.render(cam)
+        ctx.present()
+        got8, aux = ctx.readback_rgba8(), ctx.readback_aux()
+    assert np.array_equal(aux >> 31, ref_aux >> 31)
+    check_images(got8, oracle.present(ref))
+
+
+def test_identity_camera_like_the_references_first_frames(rt, oracle, noise64):
+    """The reference's camera buffer holds identity matrices until the first update: rays are
+    then parallel to +z through the near plane z = 0. Must not crash and must match the oracle."""
+    W, H = 320, 180
+    color, normal = noise64
+    cam = abi.CameraUniform()
+    for i in range(4):
+        cam.proj_view[i * 5] = 1.0
+        cam.inv_proj[i * 5] = 1.0
+    ref, ref_aux, st = oracle.render(abi.default_params(0), cam, W, H, color=color, normal=normal)
+    assert st.rays_hit > 0
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_rgba16f(color, normal)
+        for skip in (0, 1):
+            q = rt.default_params(abi.MODE_M0)
+            q.skip_empty, q.count_samples = skip, 1
+            ctx.set_params(q)
+            ctx.render(cam)
+            ctx.present()
+            assert np.array_equal(ctx.readback_aux() >> 31, ref_aux >> 31)
+            check_images(ctx.readback_rgba8(), oracle.present(ref))
+
+
+@pytest.mark.parametrize("dims", [(1, 1, 1), (3, 5, 2), (9, 8, 7), (17, 33, 65)])
+def test_tiny_and_odd_volumes(rt, oracle, xor_cam, dims):
+    """Volumes smaller than one 8^3 brick and dims that are not multiples of 8, both modes, all layouts."""
+    W, H = 256, 144
+    nx, ny, nz = dims
+    rng = np.random.default_rng(nx * 100 + ny * 10 + nz)
+    color = rng.uniform(0, 1, size=(nz, ny, nx, 4)).astype(np.float16)
+    color[..., 3] *= (rng.uniform(size=(nz, ny, nx)) < 0.6)
+    normal = rng.normal(size=(nz, ny, nx, 4)).astype(np.float16)
+    scalar = (rng.uniform(0, 1, size=(nz, ny, nx)) * (rng.uniform(size=(nz, ny, nx)) < 0.6) * 255).astype(np.uint8)
+    ref0, aux0, _ = oracle.render(abi.default_params(0), xor_cam, W, H, color=color.view(np.uint16), normal=normal.view(np.uint16))
+    ref1, aux1, _ = oracle.render(abi.default_params(1), xor_cam, W, H, scalar=scalar)
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_rgba16f(color.view(np.uint16), normal.view(np.uint16))
+        for layout in LAYOUTS_M0:
+            q = rt.default_params(abi.MODE_M0)
+            q.layout, q.skip_empty, q.count_samples = layout, 1, 1
+            ctx.set_params(q)
+            ctx.render(xor_cam)
+            ctx.present()
+            assert np.array_equal(ctx.readback_aux() >> 31, aux0 >> 31)
+            check_images(ctx.readback_rgba8(), oracle.present(ref0))
+        ctx.upload_scalar(scalar)
+        for layout in (abi.LAYOUT_LINEAR, abi.LAYOUT_GATHER):
+            q = rt.default_params(abi.MODE_M1)
+            q.layout, q.skip_empty, q.count_samples = layout, 1, 1
+            ctx.set_params(q)
+            ctx.render(xor_cam)
+            ctx.present()
+            assert np.array_equal(ctx.readback_aux() >> 31, aux1 >> 31)
+            check_images(ctx.readback_rgba8(), oracle.present(ref1))
+
+
+def test_parameters_are_honoured(rt, oracle, noise64, xor_cam):
+    """Every literal of the shader is a VkrtParams field: non-default values must track the oracle —
+    including a non-zero clear alpha, where skipping is not exact and the kernel must fall back."""
+    W, H = 320, 180
+    color, normal = noise64
+    variants = [dict(dt_scale=2.5), dict(dt_floor=0.03), dict(alpha_threshold=0.5), dict(initial_alpha=0.4),
+                dict(clear_color=(0.2, 0.1, 0.05, 0.0)), dict(clear_color=(0.2, 0.1, 0.05, 0.3))]
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_rgba16f(color, normal)
+        for v in variants:
+            p = abi.default_params(abi.MODE_M0)
+            q = rt.default_params(abi.MODE_M0)
+            for k, val in v.items():
+                for dst in (p, q):
+                    if k == "clear_color":
+                        dst.clear_color[:] = list(val)
+                    else:
+                        setattr(dst, k, val)
+            q.skip_empty, q.count_samples = 1, 1
+            ctx.set_params(q)
+            ctx.render(xor_cam)
+            ctx.present()
+            ref, ref_aux, _ = oracle.render(p, xor_cam, W, H, color=color, normal=normal)
+            assert np.array_equal(ctx.readback_aux() >> 31, ref_aux >> 31), v
+            check_images(ctx.readback_rgba8(), oracle.present(ref))

@@ -80,6 +80,7 @@ struct VkrtContext {
     uint8_t* dist = nullptr;  // brick distance field (0 = occupied)
     // brick-partitioned (sort-last) state: the resident volume is a window of a larger global grid
     bool windowed = false;
+    bool win_bricked = false;  // scalar windows are stored as 8^3 bricks (sortlast.cu)
     int gn[3] = {0, 0, 0}, win_lo[3] = {0, 0, 0}, own_lo[3] = {0, 0, 0}, own_hi[3] = {0, 0, 0};
     int cell_lo[3] = {0, 0, 0}, cell_n[3] = {0, 0, 0};
     int* d_before = nullptr;
@@ -855,13 +856,20 @@ int vkrt_sortfirst_leave(VkrtContext* c) {
 
 int vkrt_sortfirst_partition(int width, int height, int tile_size, int rank, int world, VkrtOffset* out, int cap) {
     if (width <= 0 || height <= 0 || tile_size <= 0 || world < 1 || rank < 0 || rank >= world) return fail(VKRT_ERR_INVALID, "bad partition arguments");
-    // tiles that intersect the frame, row-major, dealt round-robin: rank r takes tiles r, r+world, ...
+    // Tiles that intersect the frame, dealt in a skewed round-robin: tile (tx, ty) goes to rank
+    // (tx + 3*ty) mod world. A plain t mod world hands every rank whole COLUMNS of tiles whenever the number
+    // of tile columns is a multiple of world (32 columns at 4K / 120 px), which balances badly on content
+    // that varies across the image; the skew spreads each rank's tiles over both axes.
     const int cols = (width + tile_size - 1) / tile_size, rows = (height + tile_size - 1) / tile_size;
     int k = 0;
-    for (int t = rank; t < cols * rows; t += world, ++k)
-        if (out && k < cap) {
-            out[k].x = (float)((t % cols) * tile_size);
-            out[k].y = (float)((t / cols) * tile_size);
+    for (int ty = 0; ty < rows; ++ty)
+        for (int tx = 0; tx < cols; ++tx) {
+            if ((tx + 3 * ty) % world != rank) continue;
+            if (out && k < cap) {
+                out[k].x = (float)(tx * tile_size);
+                out[k].y = (float)(ty * tile_size);
+            }
+            ++k;
         }
     return k;
 }
@@ -935,6 +943,8 @@ int fill_partial_args(VkrtContext* c, const VkrtCameraUniform* cam, PartialArgs&
     A.vol_a = c->lin_a; A.vol_b = c->lin_b;
     A.wx = c->win_lo[0]; A.wy = c->win_lo[1]; A.wz = c->win_lo[2];
     A.nx = c->nx; A.ny = c->ny; A.nz = c->nz;
+    A.bricked = c->win_bricked ? 1 : 0;
+    A.bnx = (c->nx + 7) >> 3; A.bny = (c->ny + 7) >> 3;
     for (int i = 0; i < 3; ++i) { A.own_lo[i] = c->own_lo[i]; A.own_hi[i] = c->own_hi[i]; }
     A.dist = c->dist;
     A.cox = c->cell_lo[0]; A.coy = c->cell_lo[1]; A.coz = c->cell_lo[2];
@@ -962,6 +972,7 @@ int install_window(VkrtContext* c, int kind, int dtype, const int gn[3], const i
     c->kind = kind;
     c->dtype = dtype;
     c->windowed = true;
+    c->win_bricked = kind == VOL_SCALAR;
     return VKRT_OK;
 }
 
@@ -998,11 +1009,21 @@ int vkrt_upload_window(VkrtContext* c, const void* a, const void* b, int dtype, 
     if (rc) return rc;
     const size_t eb = dtype == -1 ? 8 : (dtype == VKRT_U8 ? 1 : (dtype == VKRT_F16 ? 2 : 4));
     const size_t bytes = (size_t)c->nx * c->ny * c->nz * eb;
-    CK(cudaMalloc(&c->lin_a, bytes));
-    CK(cudaMemcpyAsync(c->lin_a, a, bytes, cudaMemcpyHostToDevice, c->stream));
     if (dtype == -1) {
+        CK(cudaMalloc(&c->lin_a, bytes));
+        CK(cudaMemcpyAsync(c->lin_a, a, bytes, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMalloc(&c->lin_b, bytes));
         CK(cudaMemcpyAsync(c->lin_b, b, bytes, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        void* lin = nullptr;
+        const size_t padded = (size_t)((c->nx + 7) >> 3) * ((c->ny + 7) >> 3) * ((c->nz + 7) >> 3) * 512 * eb;
+        CK(cudaMalloc(&lin, bytes));
+        CK(cudaMalloc(&c->lin_a, padded));
+        CK(cudaMemcpyAsync(lin, a, bytes, cudaMemcpyHostToDevice, c->stream));
+        cudaError_t e = launch_brick_window(lin, c->lin_a, (int)eb, c->nx, c->ny, c->nz, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(lin);
+        if (e != cudaSuccess) return cuda_fail(e, "launch_brick_window");
     }
     return build_window_occupancy(c);
 }
@@ -1016,8 +1037,8 @@ int vkrt_generate_synthetic_window(VkrtContext* c, int kind, int dtype, const in
     int rc = install_window(c, VOL_SCALAR, dtype, gn, own_lo, own_hi);
     if (rc) return rc;
     const size_t eb = dtype == VKRT_U8 ? 1 : (dtype == VKRT_F16 ? 2 : 4);
-    CK(cudaMalloc(&c->lin_a, (size_t)c->nx * c->ny * c->nz * eb));
-    CK(launch_synth(c->lin_a, kind, dtype, c->nx, c->ny, c->nz, c->win_lo[0], c->win_lo[1], c->win_lo[2], gn[0], gn[1], gn[2], seed, c->stream));
+    CK(cudaMalloc(&c->lin_a, (size_t)((c->nx + 7) >> 3) * ((c->ny + 7) >> 3) * ((c->nz + 7) >> 3) * 512 * eb));  // bricked, padded
+    CK(launch_synth(c->lin_a, kind, dtype, c->nx, c->ny, c->nz, c->win_lo[0], c->win_lo[1], c->win_lo[2], gn[0], gn[1], gn[2], seed, c->stream, 1));
     return build_window_occupancy(c);
 }
 

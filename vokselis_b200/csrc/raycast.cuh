@@ -45,6 +45,8 @@ struct PartialArgs {
     const void* vol_b;             // M0: normal texels
     int wx, wy, wz;                // window origin in global voxel coordinates
     int nx, ny, nz;                // window dims
+    int bricked;                   // scalar window stored as 8^3-voxel bricks (2 KB for fp32), x fastest inside a brick
+    int bnx, bny;                  // bricks per axis of the (padded) window
     int own_lo[3], own_hi[3];      // owned voxel range (multiples of 8, or the grid edge)
     const uint8_t* dist;           // distance field over the OWN 8^3 cells
     int cox, coy, coz, cnx, cny, cnz;  // first own cell (global cell coords) and own cells per axis
@@ -75,7 +77,8 @@ cudaError_t launch_generate_xor(uint2* color, uint2* normal, int n, float time, 
 
 cudaError_t launch_scalar_to_rgba16f(const void* vol, int dtype, uint2* color, uint2* normal, int nx, int ny, int nz, cudaStream_t s);
 cudaError_t launch_synth(void* out, int kind, int dtype, int nx, int ny, int nz, int ox, int oy, int oz, int gnx, int gny, int gnz,
-                         uint32_t seed, cudaStream_t s);
+                         uint32_t seed, cudaStream_t s, int bricked = 0);
+cudaError_t launch_brick_window(const void* lin, void* out, int elem_bytes, int nx, int ny, int nz, cudaStream_t s);
 cudaError_t launch_flush_l2(uint4* buf, size_t n16, cudaStream_t s);
 cudaError_t launch_flag_wait(const unsigned long long* flag, unsigned long long target, unsigned long long* timeouts, cudaStream_t s);
 cudaError_t launch_flag_add(unsigned long long* flag, unsigned long long v, cudaStream_t s);

@@ -260,12 +260,32 @@ __device__ float synth_smooth(int x, int y, int z, uint32_t seed) {
     return __fmul_rn(__fmul_rn(v, v), 0.9f);  // skew towards low values: part of the field is transparent
 }
 
+// bricked = 1: the output is laid out as 8^3-voxel bricks (x fastest inside a brick, bricks x fastest), dims
+// padded up to multiples of 8; thread i writes element i of that layout (coalesced), padding voxels get 0.
 template <int DTYPE>
 __global__ void __launch_bounds__(256) synth_kernel(void* __restrict__ out, int kind, int nx, int ny, int nz, int ox, int oy, int oz,
-                                                    int gnx, int gny, int gnz, uint32_t seed) {
+                                                    int gnx, int gny, int gnz, uint32_t seed, int bricked) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)nx * ny * nz) return;
-    const int x = (int)(i % (size_t)nx) + ox, y = (int)((i / (size_t)nx) % (size_t)ny) + oy, z = (int)(i / ((size_t)nx * ny)) + oz;
+    int lx, ly, lz;
+    if (bricked) {
+        const int bnx = (nx + 7) >> 3, bny = (ny + 7) >> 3, bnz = (nz + 7) >> 3;
+        if (i >= (size_t)bnx * bny * bnz * 512) return;
+        const size_t b = i >> 9;
+        const int in = (int)(i & 511);
+        lx = (int)(b % (size_t)bnx) * 8 + (in & 7);
+        ly = (int)((b / (size_t)bnx) % (size_t)bny) * 8 + ((in >> 3) & 7);
+        lz = (int)(b / ((size_t)bnx * bny)) * 8 + (in >> 6);
+        if (lx >= nx || ly >= ny || lz >= nz) {
+            if (DTYPE == VKRT_U8) ((uint8_t*)out)[i] = 0;
+            else if (DTYPE == VKRT_F16) ((__half*)out)[i] = __float2half_rn(0.0f);
+            else ((float*)out)[i] = 0.0f;
+            return;
+        }
+    } else {
+        if (i >= (size_t)nx * ny * nz) return;
+        lx = (int)(i % (size_t)nx); ly = (int)((i / (size_t)nx) % (size_t)ny); lz = (int)(i / ((size_t)nx * ny));
+    }
+    const int x = lx + ox, y = ly + oy, z = lz + oz;
     float v = kind == 0 ? synth_noise(x, y, z, gnx, gny, gnz, seed) : (kind == 1 ? synth_sparse(x, y, z, seed) : synth_smooth(x, y, z, seed));
     // kind 3: the smooth lattice as a very thin fog just around the transfer function's 0.1 threshold, so
     // that rays cross a 4096-voxel grid without saturating (every brick of a sort-last run does work)
@@ -319,14 +339,36 @@ cudaError_t launch_scalar_to_rgba16f(const void* vol, int dtype, uint2* color, u
     return cudaGetLastError();
 }
 
+// linear window -> bricked window (upload path; the generator writes bricked directly)
+template <class T>
+__global__ void __launch_bounds__(256) brick_window_kernel(const T* __restrict__ lin, T* __restrict__ out, int nx, int ny, int nz) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int bnx = (nx + 7) >> 3, bny = (ny + 7) >> 3, bnz = (nz + 7) >> 3;
+    if (i >= (size_t)bnx * bny * bnz * 512) return;
+    const size_t b = i >> 9;
+    const int in = (int)(i & 511);
+    const int lx = (int)(b % (size_t)bnx) * 8 + (in & 7), ly = (int)((b / (size_t)bnx) % (size_t)bny) * 8 + ((in >> 3) & 7),
+              lz = (int)(b / ((size_t)bnx * bny)) * 8 + (in >> 6);
+    out[i] = (lx < nx && ly < ny && lz < nz) ? lin[((size_t)lz * ny + ly) * nx + lx] : T(0);
+}
+
+cudaError_t launch_brick_window(const void* lin, void* out, int elem_bytes, int nx, int ny, int nz, cudaStream_t s) {
+    const size_t total = (size_t)((nx + 7) >> 3) * ((ny + 7) >> 3) * ((nz + 7) >> 3) * 512;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (elem_bytes == 1) brick_window_kernel<uint8_t><<<blocks, 256, 0, s>>>((const uint8_t*)lin, (uint8_t*)out, nx, ny, nz);
+    else if (elem_bytes == 2) brick_window_kernel<uint16_t><<<blocks, 256, 0, s>>>((const uint16_t*)lin, (uint16_t*)out, nx, ny, nz);
+    else brick_window_kernel<uint32_t><<<blocks, 256, 0, s>>>((const uint32_t*)lin, (uint32_t*)out, nx, ny, nz);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_synth(void* out, int kind, int dtype, int nx, int ny, int nz, int ox, int oy, int oz, int gnx, int gny, int gnz,
-                         uint32_t seed, cudaStream_t s) {
-    const size_t total = (size_t)nx * ny * nz;
+                         uint32_t seed, cudaStream_t s, int bricked) {
+    const size_t total = bricked ? (size_t)((nx + 7) >> 3) * ((ny + 7) >> 3) * ((nz + 7) >> 3) * 512 : (size_t)nx * ny * nz;
     const unsigned blocks = (unsigned)((total + 255) / 256);
     switch (dtype) {
-        case VKRT_U8: synth_kernel<VKRT_U8><<<blocks, 256, 0, s>>>(out, kind, nx, ny, nz, ox, oy, oz, gnx, gny, gnz, seed); break;
-        case VKRT_F16: synth_kernel<VKRT_F16><<<blocks, 256, 0, s>>>(out, kind, nx, ny, nz, ox, oy, oz, gnx, gny, gnz, seed); break;
-        case VKRT_F32: synth_kernel<VKRT_F32><<<blocks, 256, 0, s>>>(out, kind, nx, ny, nz, ox, oy, oz, gnx, gny, gnz, seed); break;
+        case VKRT_U8: synth_kernel<VKRT_U8><<<blocks, 256, 0, s>>>(out, kind, nx, ny, nz, ox, oy, oz, gnx, gny, gnz, seed, bricked); break;
+        case VKRT_F16: synth_kernel<VKRT_F16><<<blocks, 256, 0, s>>>(out, kind, nx, ny, nz, ox, oy, oz, gnx, gny, gnz, seed, bricked); break;
+        case VKRT_F32: synth_kernel<VKRT_F32><<<blocks, 256, 0, s>>>(out, kind, nx, ny, nz, ox, oy, oz, gnx, gny, gnz, seed, bricked); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
