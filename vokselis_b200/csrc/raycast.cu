@@ -172,6 +172,8 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
             rqy = fabsf(dqy) > 1e-12f ? 1.0f / dqy : 1e30f;
             rqz = fabsf(dqz) > 1e-12f ? 1.0f / dqz : 1e30f;
         }
+        // one replayed addition moves t off the exact line by <= ulp(t)/2 <= t1 * 2^-24; in units of a step:
+        const float drift_per_step = SKIP ? (t1 * 5.9604645e-08f) / dt * 2.0f : 0.0f;  // x2 safety
         // (A while-while traversal — every lane first advances to its next non-empty sample, then the warp
         // votes and shades together — was measured 1.9x SLOWER on B200: the skip phase costs about as much
         // as a sample here, and it ran at lower lane utilisation. profiles/r01_whilewhile_ab.md)
@@ -195,11 +197,14 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
                     if (d != 0u) {
                         n = 1;
                         // Region = bricks [c-(d-1), c+d) per axis, shrunk by A.leap_eps voxels (covers the
-                        // rounding of p and q); the -1 step covers the drift of the repeated addition.
-                        const int r = (int)d - 1;
-                        const float lox = (float)(((ix >> 3) - r) * 8) + A.leap_eps, loy = (float)(((iy >> 3) - r) * 8) + A.leap_eps,
-                                    loz = (float)(((iz >> 3) - r) * 8) + A.leap_eps;
-                        float hix = (float)(((ix >> 3) + r + 1) * 8), hiy = (float)(((iy >> 3) + r + 1) * 8), hiz = (float)(((iz >> 3) + r + 1) * 8);
+                        // rounding of p and q). s = steps until the ray leaves it (approximate line model);
+                        // the margin covers the drift of the replayed additions: each rounds by <= ulp(t)/2,
+                        // i.e. <= drift_per_step of a step, so after n <= s steps the model is off by at most
+                        // s * drift_per_step steps (+ a fixed 0.02).
+                        const float w = (float)((int)d * 8 - 8);  // (d-1) bricks on either side
+                        const float bx0 = (float)(ix & ~7), by0 = (float)(iy & ~7), bz0 = (float)(iz & ~7);
+                        const float lox = bx0 - w + A.leap_eps, loy = by0 - w + A.leap_eps, loz = bz0 - w + A.leap_eps;
+                        float hix = bx0 + 8.0f + w, hiy = by0 + 8.0f + w, hiz = bz0 + 8.0f + w;
                         if (MODE == VKRT_MODE_M1) {  // clamp-to-edge sampling: outside the grid is NOT empty
                             hix = fminf(hix, A.fx); hiy = fminf(hiy, A.fy); hiz = fminf(hiz, A.fz);
                         }
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
                         const float sy = ((dqy > 0.f ? hiy : loy) - qy) * rqy;
                         const float sz = ((dqz > 0.f ? hiz : loz) - qz) * rqz;
                         const float sm = fminf(fminf(sx, sy), fminf(sz, 4096.0f));
-                        n = max(__float2int_rz(sm) - 1, 1);
+                        n = max(__float2int_rz(sm - (0.02f + sm * drift_per_step)), 1);
                     }
                 }
                 if (n > 0) {
@@ -287,7 +292,7 @@ cudaError_t launch_raycast(const RenderArgs& A, int mode, int layout, int dtype,
     // (exploration only; W*H must be a multiple of 32 and <= 256).
     static int bw = 0, bh = 0;
     if (bw == 0) {
-        bw = 8; bh = 8;
+        bw = 8; bh = 16;  // 8x16: measured best on B200 (profiles/r01_blockshape.md); warps stay 8x4-pixel tiles
         if (const char* e = getenv("VKRT_BLOCK")) {
             int w = 0, h = 0;
             if (sscanf(e, "%dx%d", &w, &h) == 2 && w > 0 && h > 0 && (w * h) % 32 == 0 && w * h <= 256) { bw = w; bh = h; }
