@@ -37,6 +37,20 @@ def advance_t(t: np.float32, dt: np.float32, n: int) -> np.float32:
     return t
 
 
+def leap_t(t, dt, n):
+    """Fast path (leap_t in vkrt_device.cuh): stays inside the binade and no tie -> one integer multiply-add."""
+    db, tb = int(np.float32(dt).view(np.uint32)), int(np.float32(t).view(np.uint32))
+    e, shift = tb >> 23, (tb >> 23) - (db >> 23)
+    if 1 <= shift <= 24 and (db >> 23) != 0:
+        M = (db & 0x7FFFFF) | 0x800000
+        rem, half = M & ((1 << shift) - 1), 1 << (shift - 1)
+        if rem != half:
+            nb = (tb + n * ((M >> shift) + (1 if rem > half else 0))) & 0xFFFFFFFF
+            if (nb >> 23) == e:
+                return np.uint32(nb).view(np.float32)
+    return advance_t(t, dt, n)
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_closed_form_equals_repeated_addition(seed):
     rng = np.random.default_rng(seed)
@@ -52,3 +66,5 @@ def test_closed_form_equals_repeated_addition(seed):
             ref = np.float32(ref + dt)
         got = advance_t(t0, dt, n)
         assert got.view(np.uint32) == ref.view(np.uint32), (t0, dt, n, got, ref)
+        got2 = leap_t(t0, dt, n)
+        assert got2.view(np.uint32) == ref.view(np.uint32), ("leap_t", t0, dt, n, got2, ref)

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -323,6 +324,11 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     A.hx = A.fx / 2.0f; A.hy = A.fy / 2.0f; A.hz = A.fz / 2.0f;
     A.nbx = c->nbx; A.nby = c->nby; A.nbz = c->nbz;
     A.dist = c->dist;
+    {
+        static int lcm = -1;  // VKRT_LEAP_CLOSED_MIN overrides (exploration)
+        if (lcm < 0) { const char* e = getenv("VKRT_LEAP_CLOSED_MIN"); lcm = e ? atoi(e) : 64; }
+        A.leap_closed_min = lcm;
+    }
     // shrink leap regions by ~16 ulp of the largest voxel coordinate (rounding of p and q)
     A.leap_eps = 16.0f * 1.1920929e-07f * (float)(c->nx > c->ny ? (c->nx > c->nz ? c->nx : c->nz) : (c->ny > c->nz ? c->ny : c->nz));
     A.dt_scale = P.dt_scale; A.dt_floor = P.dt_floor; A.alpha_threshold = P.alpha_threshold; A.initial_alpha = P.initial_alpha;

@@ -222,8 +222,8 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
                             ++iters;
                             t = xadd(t, dt);
                         }
-                    } else if (n >= 48) {
-                        t = advance_t(t, dt, n);  // closed form, bit-identical to n additions
+                    } else if (n >= A.leap_closed_min) {
+                        t = leap_t(t, dt, n);  // closed form, bit-identical to n additions
                     } else {
 #pragma unroll 4
                         for (int j = 0; j < n; ++j) t = xadd(t, dt);

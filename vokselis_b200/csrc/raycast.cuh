@@ -25,6 +25,7 @@ struct RenderArgs {
     int nbx, nby, nbz;  // 8^3-voxel bricks per axis (occupancy grid and bricked layout)
     const uint8_t* dist;  // per brick: 0 = occupied, d = bricks within Chebyshev radius d-1 are all empty
     float leap_eps;       // safety shrink of leap regions, in voxels
+    int leap_closed_min;  // leaps of at least this many samples use the closed-form advance (leap_t)
     // parameters (VkrtParams)
     float dt_scale, dt_floor, alpha_threshold, initial_alpha;
     float clear[4];

@@ -115,6 +115,23 @@ __device__ __forceinline__ float advance_t(float t, float dt, int n) {
     return t;
 }
 
+// Fast path of advance_t for the common case — the whole run stays inside t's binade and dt is not an exact
+// tie there: one shift, one compare, one integer multiply-add on the bit pattern; anything else (binade
+// crossing, tie, tiny t) goes through advance_t. Bit-identical to n repeated additions either way.
+__device__ __forceinline__ float leap_t(float t, float dt, int n) {
+    const uint32_t db = __float_as_uint(dt), tb = __float_as_uint(t);
+    const int e = (int)(tb >> 23), shift = e - (int)(db >> 23);
+    if (shift >= 1 && shift <= 24 && (db >> 23) != 0u) {
+        const uint32_t M = (db & 0x7fffffu) | 0x800000u;
+        const uint32_t rem = M & ((1u << shift) - 1u), half = 1u << (shift - 1);
+        if (rem != half) {
+            const uint32_t nb = tb + (uint32_t)n * ((M >> shift) + (rem > half ? 1u : 0u));
+            if ((int)(nb >> 23) == e) return __uint_as_float(nb);
+        }
+    }
+    return advance_t(t, dt, n);
+}
+
 // ---- shading (tolerance-checked, FMA allowed) ----------------------------------------------
 // smoothstep with compile-time edges: the division by (e1 - e0) becomes a multiplication by its
 // reciprocal (an IEEE fdiv is ~10 instructions plus a slow path for zero numerators; profiles/).
