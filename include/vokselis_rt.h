@@ -278,6 +278,13 @@ VKRT_API int vkrt_window_info(VkrtContext* ctx, int win_lo[3], int win_n[3]);
 VKRT_API int vkrt_partial_alpha(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un, float* d_T);
 VKRT_API int vkrt_partial_ain(VkrtContext* ctx, const float* d_T_all, const int* ranks_before, int n_before, float* d_ain);
 VKRT_API int vkrt_partial_color(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un, const float* d_ain, float* d_rgba);
+/* One-march variant (deferred early termination): vkrt_partial_relative marches the brick ONCE from alpha 0
+ * and writes the relative partial + the brick's transmittance; after the all-gather, vkrt_partial_resolve
+ * scales each pixel by the transmittance in front of the brick, zeroes the pixels that ended before it,
+ * and flags (d_ain >= 0) the few pixels whose 0.95 crossing can fall inside the brick; a following
+ * vkrt_partial_color(cam, d_ain, d_rgba) re-marches only those (it skips d_ain < 0). */
+VKRT_API int vkrt_partial_relative(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un, float* d_rgba, float* d_T);
+VKRT_API int vkrt_partial_resolve(VkrtContext* ctx, const float* d_T_all, const int* ranks_before, int n_before, float* d_rgba, float* d_ain);
 VKRT_API int vkrt_partial_finalize(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un, const float* d_sum_rgba);
 
 /* Eight user events on the context's stream: vkrt_mark records one, vkrt_mark_elapsed returns the

@@ -16,32 +16,43 @@ def psnr8(a, b):
     return 99.0 if mse == 0 else 10.0 * np.log10(255.0 ** 2 / mse)
 
 
-def compose(rt, sortlast, torch, ctxs, cam, gn, grid, W, H):
+def compose(rt, sortlast, torch, ctxs, cam, gn, grid, W, H, scheme="two-pass"):
     world = len(ctxs)
     n = W * H
     T_all = torch.empty(world * n, dtype=torch.float32, device="cuda")
     ain = torch.empty(n, dtype=torch.float32, device="cuda")
-    part = torch.empty(n * 4, dtype=torch.float32, device="cuda")
+    parts = [torch.empty(n * 4, dtype=torch.float32, device="cuda") for _ in ctxs]
     total = torch.zeros(n * 4, dtype=torch.float32, device="cuda")
     torch.cuda.synchronize()
     for r, c in enumerate(ctxs):
-        c.partial_alpha(cam, T_all.data_ptr() + r * n * 4)
+        if scheme == "two-pass":
+            c.partial_alpha(cam, T_all.data_ptr() + r * n * 4)
+        else:
+            c.partial_relative(cam, parts[r].data_ptr(), T_all.data_ptr() + r * n * 4)
         c.sync()
     order = sortlast.visibility_order(tuple(cam.view_position[:3]), gn, grid)
+    remarched = 0
     for r, c in enumerate(ctxs):
-        c.partial_ain(T_all.data_ptr(), order[: order.index(r)], ain.data_ptr())
-        c.partial_color(cam, ain.data_ptr(), part.data_ptr())
+        if scheme == "two-pass":
+            c.partial_ain(T_all.data_ptr(), order[: order.index(r)], ain.data_ptr())
+        else:
+            c.partial_resolve(T_all.data_ptr(), order[: order.index(r)], parts[r].data_ptr(), ain.data_ptr())
+            c.sync()
+            remarched += int((ain >= 0).sum().item())
+        c.partial_color(cam, ain.data_ptr(), parts[r].data_ptr())
         c.sync()
-        total += part
+        total += parts[r]
         torch.cuda.synchronize()
+    compose.remarched = remarched
     ctxs[0].partial_finalize(cam, total.data_ptr())
     ctxs[0].present()
     return ctxs[0].readback(), ctxs[0].readback_rgba8()
 
 
+@pytest.mark.parametrize("scheme", ["two-pass", "deferred"])
 @pytest.mark.parametrize("world", [2, 8])
 @pytest.mark.parametrize("mode", [abi.MODE_M0, abi.MODE_M1])
-def test_simulated_ranks_match_single_gpu(oracle, world, mode):
+def test_simulated_ranks_match_single_gpu(oracle, world, mode, scheme):
     import torch
 
     from vokselis_b200 import rt, sortlast
@@ -77,7 +88,9 @@ def test_simulated_ranks_match_single_gpu(oracle, world, mode):
                 full.render(cam)
                 full.present()
                 ref, ref8 = full.readback(), full.readback_rgba8()
-                got, got8 = compose(rt, sortlast, torch, ctxs, cam, gn, grid, W, H)
+                got, got8 = compose(rt, sortlast, torch, ctxs, cam, gn, grid, W, H, scheme)
+                if scheme == "deferred":
+                    assert compose.remarched < world * W * H  # only some pixels are marched twice
                 d = np.abs(got8.astype(np.int32) - ref8.astype(np.int32))
                 assert d.max() <= 2, f"max |delta| {d.max()}/255 (world {world}, mode {mode}, cam {(zoom, pitch, yaw)})"
                 assert psnr8(got8, ref8) >= 50.0

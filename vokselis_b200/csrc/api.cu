@@ -1089,6 +1089,31 @@ int vkrt_partial_color(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtU
     return VKRT_OK;
 }
 
+int vkrt_partial_relative(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, float* d_rgba, float* d_T) {
+    if (!c || !cam || !un || !d_rgba || !d_T) return fail(VKRT_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    PartialArgs A;
+    int rc = fill_partial_args(c, cam, A);
+    if (rc) return rc;
+    A.a_in = nullptr;  // relative pass
+    A.rgba_out = reinterpret_cast<float4*>(d_rgba);
+    A.T_out = d_T;
+    CK(launch_partial(A, c->params.mode, c->dtype, 2, c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_partial_resolve(VkrtContext* c, const float* d_T_all, const int* ranks_before, int n_before, float* d_rgba, float* d_ain) {
+    if (!c || !d_rgba || !d_ain || n_before < 0 || (n_before > 0 && (!d_T_all || !ranks_before))) return fail(VKRT_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(c->device));
+    if (!c->d_before) CK(cudaMalloc(&c->d_before, 1024 * sizeof(int)));
+    if (n_before > 1024) return fail(VKRT_ERR_INVALID, "too many ranks");
+    if (n_before > 0) CK(cudaMemcpyAsync(c->d_before, ranks_before, (size_t)n_before * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    const size_t n = (size_t)c->W * c->H;
+    CK(launch_partial_resolve(d_T_all, n, c->d_before, n_before, c->params.initial_alpha, c->params.alpha_threshold,
+                              reinterpret_cast<float4*>(d_rgba), d_ain, n, c->stream));
+    return VKRT_OK;
+}
+
 int vkrt_partial_finalize(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, const float* d_sum_rgba) {
     if (!c || !cam || !un || !d_sum_rgba) return fail(VKRT_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(c->device));

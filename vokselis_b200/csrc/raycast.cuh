@@ -60,6 +60,8 @@ struct PartialArgs {
 };
 cudaError_t launch_partial(const PartialArgs& A, int mode, int dtype, int pass, cudaStream_t s);
 cudaError_t launch_partial_ain(const float* T_all, size_t stride, const int* before, int n_before, float a0, float* a_in, size_t n, cudaStream_t s);
+cudaError_t launch_partial_resolve(const float* T_all, size_t stride, const int* before, int n_before, float a0, float thr, float4* rgba,
+                                   float* a_in_out, size_t n, cudaStream_t s);
 cudaError_t launch_partial_finalize(const PartialArgs& A, const float4* sum, uint2* frame, int mode, int m1_srgb, cudaStream_t s);
 cudaError_t launch_window_occupancy(const PartialArgs& A, int mode, int dtype, uint8_t* dist, cudaStream_t s);
 

@@ -75,7 +75,13 @@ __global__ void __launch_bounds__(256) partial_kernel(const __grid_constant__ Pa
 
     float T = 1.0f;  // PASS_ALPHA
     Rgba col = {0.f, 0.f, 0.f, 0.f};
-    if (PASS == PASS_COLOR) col.a = hit ? A.a_in[o] : 1.0f;
+    if (PASS == PASS_COLOR) {
+        // a_in == nullptr: RELATIVE pass (march from alpha 0; the result is scaled by the incoming
+        // transmittance afterwards, resolve_kernel). a_in[o] < 0: this pixel needs no (re-)march.
+        const float ain = A.a_in ? A.a_in[o] : 0.0f;
+        if (A.a_in && ain < 0.0f) return;
+        col.a = hit ? ain : 1.0f;
+    }
     bool live = hit && (PASS == PASS_ALPHA || col.a < A.alpha_threshold);
 
     if (live) {
@@ -161,8 +167,42 @@ __global__ void __launch_bounds__(256) partial_kernel(const __grid_constant__ Pa
             }
         }
     }
-    if (PASS == PASS_ALPHA) A.T_out[o] = T;
-    else A.rgba_out[o] = make_float4(col.r, col.g, col.b, col.a);
+    if (PASS == PASS_ALPHA) {
+        A.T_out[o] = T;
+    } else {
+        A.rgba_out[o] = make_float4(col.r, col.g, col.b, col.a);
+        if (A.T_out) A.T_out[o] = hit ? 1.0f - col.a : 1.0f;  // relative pass: transmittance of the brick
+    }
+}
+
+// Deferred early termination (one march instead of two). Input: the RELATIVE partials
+// (premultiplied rgb and alpha accumulated from 0 inside the brick) and every rank's transmittance.
+//   a_in >= threshold                      -> the ray ended in front of this brick: partial = 0
+//   the 0.95 crossing can fall inside the brick, or the relative march stopped on its own alpha
+//                                          -> re-march this pixel from a_in (a_in_out >= 0)
+//   otherwise                              -> partial = (1 - a_in) * relative partial (a_in_out = -1)
+__global__ void __launch_bounds__(256) resolve_kernel(const float* __restrict__ T_all, size_t stride, const int* __restrict__ before,
+                                                      int n_before, float a0, float thr, float4* __restrict__ rgba,
+                                                      float* __restrict__ a_in_out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float T = 1.0f - a0;
+    for (int k = 0; k < n_before; ++k) T *= __ldg(T_all + (size_t)before[k] * stride + i);
+    const float ain = 1.0f - T;
+    float4 c = rgba[i];
+    float flag = -1.0f;
+    if (ain >= thr) {
+        c = make_float4(0.f, 0.f, 0.f, ain);
+    } else {
+        const float a_out = 1.0f - T * (1.0f - c.w);
+        if (a_out >= thr - 1e-4f || c.w >= thr - 1e-4f) {
+            flag = ain;  // exact recurrence needed: PASS_COLOR overwrites rgba[i]
+        } else {
+            c = make_float4(T * c.x, T * c.y, T * c.z, a_out);
+        }
+    }
+    rgba[i] = c;
+    a_in_out[i] = flag;
 }
 
 // a_in = 1 - (1 - a0) * prod_{j in before} T_j   (T_all = [world][W*H])
@@ -251,6 +291,12 @@ cudaError_t launch_partial(const PartialArgs& A, int mode, int dtype, int pass, 
 
 cudaError_t launch_partial_ain(const float* T_all, size_t stride, const int* before, int n_before, float a0, float* a_in, size_t n, cudaStream_t s) {
     ain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(T_all, stride, before, n_before, a0, a_in, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_partial_resolve(const float* T_all, size_t stride, const int* before, int n_before, float a0, float thr, float4* rgba,
+                                   float* a_in_out, size_t n, cudaStream_t s) {
+    resolve_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(T_all, stride, before, n_before, a0, thr, rgba, a_in_out, n);
     return cudaGetLastError();
 }
 

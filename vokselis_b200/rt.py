@@ -33,7 +33,7 @@ EXPORTS = [
     "vkrt_sortfirst_consume", "vkrt_sortfirst_timeouts", "vkrt_sortfirst_wait", "vkrt_mark", "vkrt_mark_elapsed",
     "vkrt_alloc_host", "vkrt_free_host", "vkrt_generate_synthetic", "vkrt_download_scalar", "vkrt_scalar_to_rgba16f",
     "vkrt_upload_window", "vkrt_generate_synthetic_window", "vkrt_window_info", "vkrt_partial_alpha", "vkrt_partial_ain",
-    "vkrt_partial_color", "vkrt_partial_finalize",
+    "vkrt_partial_color", "vkrt_partial_finalize", "vkrt_partial_relative", "vkrt_partial_resolve",
 ]
 
 
@@ -106,6 +106,8 @@ def lib() -> C.CDLL:
         "vkrt_partial_ain": (ci, [vp, vp, vp, ci, vp]),
         "vkrt_partial_color": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp, vp]),
         "vkrt_partial_finalize": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp]),
+        "vkrt_partial_relative": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp, vp]),
+        "vkrt_partial_resolve": (ci, [vp, vp, vp, ci, vp, vp]),
         "vkrt_free_host": (ci, [vp]),
         "vkrt_mark_elapsed": (ci, [vp, ci, ci, C.POINTER(cf)]),
         "vkrt_sortfirst_join": (ci, [vp, ci, vp]),
@@ -420,6 +422,14 @@ class Context:
     def partial_color(self, cam: CameraUniform, d_ain: int, d_rgba: int, uniform: Uniform | None = None):
         un = uniform if uniform is not None else self.global_uniform
         _check(lib().vkrt_partial_color(self._h, C.byref(cam), C.byref(un), d_ain, d_rgba))
+
+    def partial_relative(self, cam: CameraUniform, d_rgba: int, d_T: int, uniform: Uniform | None = None):
+        un = uniform if uniform is not None else self.global_uniform
+        _check(lib().vkrt_partial_relative(self._h, C.byref(cam), C.byref(un), d_rgba, d_T))
+
+    def partial_resolve(self, d_T_all: int, ranks_before, d_rgba: int, d_ain: int):
+        rb = np.ascontiguousarray(np.asarray(list(ranks_before), np.int32))
+        _check(lib().vkrt_partial_resolve(self._h, d_T_all, _vp(rb) if rb.size else None, int(rb.size), d_rgba, d_ain))
 
     def partial_finalize(self, cam: CameraUniform, d_sum: int, uniform: Uniform | None = None):
         un = uniform if uniform is not None else self.global_uniform

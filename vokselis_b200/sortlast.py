@@ -2,10 +2,12 @@
 px x py x pz axis-aligned bricks, one per rank (one process per GPU). Host-side logic only; the kernels
 and the per-rank API are vkrt_partial_* (include/vokselis_rt.h, vokselis_b200/csrc/sortlast.cu).
 
-Per frame: every rank marches its brick alpha-only -> all-gather of the per-pixel
-transmittances (NCCL) -> each rank derives the alpha entering its brick from the bricks in front of
-it -> colour pass with exact early termination -> the premultiplied partials are SUMMED onto rank 0
-(NCCL reduce; with the alpha pre-pass the composite is commutative) -> rank 0 finalizes the frame.
+Per frame, scheme "two-pass": every rank marches its brick alpha-only -> all-gather of the
+per-pixel transmittances (NCCL) -> each rank derives the alpha entering its brick from the bricks in
+front of it -> colour pass with exact early termination -> the premultiplied partials are SUMMED onto
+rank 0 (NCCL reduce; with absolute weights the composite is commutative) -> rank 0 finalizes the frame.
+Scheme "deferred" (default) marches ONCE from alpha 0, then scales each pixel by the transmittance in
+front of the brick and re-marches only the pixels whose 0.95 crossing can fall inside the brick.
 
 The reference has no counterpart: it is single-device. Its compositing operator,
 shaders/raycast_compute.wgsl:88-91, is what the partial passes split.
@@ -69,12 +71,15 @@ class SortLastGroup:
     """Drives one frame across the ranks. `torch` tensors hold the exchange buffers; collectives run on
     the context's own stream (torch.cuda.ExternalStream), so no host synchronisation is needed."""
 
-    def __init__(self, ctx, rank: int, world: int, gn, dist=None, grid=None):
+    def __init__(self, ctx, rank: int, world: int, gn, dist=None, grid=None, scheme: str = "deferred"):
         import torch
 
         if dist is None:
             import torch.distributed as dist  # noqa: PLC0415
         self.torch, self.dist = torch, dist
+        if scheme not in ("deferred", "two-pass"):
+            raise ValueError(scheme)
+        self.scheme = scheme
         self.ctx, self.rank, self.world, self.gn = ctx, rank, world, tuple(gn)
         self.grid = grid or brick_grid(world)
         self.own_lo, self.own_hi = brick_range(self.gn, self.grid, rank)
@@ -93,13 +98,19 @@ class SortLastGroup:
         order = visibility_order(eye, self.gn, self.grid)
         before = order[: order.index(self.rank)]
         with torch.cuda.stream(self.stream):
-            ctx.partial_alpha(cam, self.T.data_ptr())
+            if self.scheme == "two-pass":  # alpha-only march, then the colour march with the exact incoming alpha
+                ctx.partial_alpha(cam, self.T.data_ptr())
+            else:  # ONE march from alpha 0 (relative partial); early termination is resolved afterwards
+                ctx.partial_relative(cam, self.rgba.data_ptr(), self.T.data_ptr())
             if self.world > 1:
                 dist.all_gather_into_tensor(self.T_all, self.T)
             else:
                 self.T_all.copy_(self.T)
-            ctx.partial_ain(self.T_all.data_ptr(), before, self.ain.data_ptr())
-            ctx.partial_color(cam, self.ain.data_ptr(), self.rgba.data_ptr())
+            if self.scheme == "two-pass":
+                ctx.partial_ain(self.T_all.data_ptr(), before, self.ain.data_ptr())
+            else:
+                ctx.partial_resolve(self.T_all.data_ptr(), before, self.rgba.data_ptr(), self.ain.data_ptr())
+            ctx.partial_color(cam, self.ain.data_ptr(), self.rgba.data_ptr())  # deferred: only the flagged pixels
             if self.world > 1:
                 dist.reduce(self.rgba, dst=0, op=dist.ReduceOp.SUM)
             if self.rank == 0:
