@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
                         const float sy = ((dqy > 0.f ? hiy : loy) - qy) * rqy;
                         const float sz = ((dqz > 0.f ? hiz : loz) - qz) * rqz;
                         const float sm = fminf(fminf(sx, sy), fminf(sz, 4096.0f));
-                        n = max(__float2int_rz(sm - (0.02f + sm * drift_per_step)), 1);
+                        // samples j = 0 .. floor(s - margin) (this one is j = 0) lie inside the region
+                        n = max(__float2int_rz(sm - (0.02f + sm * drift_per_step)) + 1, 1);
                     }
                 }
                 if (n > 0) {
