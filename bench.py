@@ -57,7 +57,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -333,7 +333,6 @@ def run_gpu(args):
     warm_ms, t_wall_warm = timed_pass()
     warm_total_ms = whole_job_ms(warm_ms)
     flushing[0] = True
-    clock_info = clocks.stop() if rank == 0 else None
 
     # ---- e2e through the C ABI with host buffers -----------------------------------------------
     e2e = None
@@ -378,6 +377,8 @@ def run_gpu(args):
         pinned.close()
     else:
         e2e = group.e2e(cams, K, Wm)
+
+    clock_info = clocks.stop() if rank == 0 else None  # sampled across all timed GPU regions above (value, warm, e2e)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------
     cpu = None

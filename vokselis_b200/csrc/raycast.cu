@@ -85,15 +85,23 @@ __device__ __forceinline__ float4 tld4_layer(cudaTextureObject_t tex, int layer,
     return r;
 }
 
+// a + f*(b - a), x then y then z, every operation spelled out (see the determinism note in vkrt_device.cuh)
+__device__ __forceinline__ float lerp1(float a, float b, float f) { return fmaf(f, __fsub_rn(b, a), a); }
+__device__ __forceinline__ float lerp3(float c000, float c100, float c010, float c110, float c001, float c101, float c011, float c111,
+                                       float fx, float fy, float fz) {
+    const float c00 = lerp1(c000, c100, fx), c10 = lerp1(c010, c110, fx), c01 = lerp1(c001, c101, fx), c11 = lerp1(c011, c111, fx);
+    return lerp1(lerp1(c00, c10, fy), lerp1(c01, c11, fy), fz);
+}
+
 // ---- scalar sample, M1 (linear filter, clamp-to-edge) ----------------------------------------
 template <int LAYOUT, int DTYPE>
 __device__ __forceinline__ float m1_sample(const RenderArgs& A, float qx, float qy, float qz) {
     if (LAYOUT == VKRT_LAYOUT_TEXTURE) {
         return tex3D<float>(A.tex_a, qx, qy, qz);  // hardware trilinear, 8-bit weights
     }
-    const float ux = qx - 0.5f, uy = qy - 0.5f, uz = qz - 0.5f;
+    const float ux = __fsub_rn(qx, 0.5f), uy = __fsub_rn(qy, 0.5f), uz = __fsub_rn(qz, 0.5f);
     const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
-    const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+    const float fx = __fsub_rn(ux, flx), fy = __fsub_rn(uy, fly), fz = __fsub_rn(uz, flz);
     if (LAYOUT == VKRT_LAYOUT_GATHER) {
         // (Measured, ncu: in the dense case this path is bound by the texture DATA pipe — l1tex throughput
         // 97 %, data_pipe_tex_wavefronts 83 %, ~35 sectors per warp-level tld4 because the lanes of a warp sit
@@ -106,10 +114,7 @@ __device__ __forceinline__ float m1_sample(const RenderArgs& A, float qx, float 
         const int za = min(max(z0, 0), A.nz - 1), zb = min(max(z0 + 1, 0), A.nz - 1);
         const float4 g0 = tld4_layer(A.tex_a, za, flx + 1.0f, fly + 1.0f);
         const float4 g1 = tld4_layer(A.tex_a, zb, flx + 1.0f, fly + 1.0f);
-        const float c00 = g0.w + fx * (g0.z - g0.w), c10 = g0.x + fx * (g0.y - g0.x);
-        const float c01 = g1.w + fx * (g1.z - g1.w), c11 = g1.x + fx * (g1.y - g1.x);
-        const float c0 = c00 + fy * (c10 - c00), c1 = c01 + fy * (c11 - c01);
-        return c0 + fz * (c1 - c0);
+        return lerp3(g0.w, g0.z, g0.x, g0.y, g1.w, g1.z, g1.x, g1.y, fx, fy, fz);
     }
     const int x0 = (int)flx, y0 = (int)fly, z0 = (int)flz;
     // clamp-to-edge on both taps, like the oracle's scalar_at()
@@ -123,10 +128,7 @@ __device__ __forceinline__ float m1_sample(const RenderArgs& A, float qx, float 
     const float c010 = S::load(A.vol_a, r10 + xa2), c110 = S::load(A.vol_a, r10 + xb2);
     const float c001 = S::load(A.vol_a, r01 + xa2), c101 = S::load(A.vol_a, r01 + xb2);
     const float c011 = S::load(A.vol_a, r11 + xa2), c111 = S::load(A.vol_a, r11 + xb2);
-    const float c00 = c000 + fx * (c100 - c000), c10 = c010 + fx * (c110 - c010);
-    const float c01 = c001 + fx * (c101 - c001), c11 = c011 + fx * (c111 - c011);
-    const float c0 = c00 + fy * (c10 - c00), c1 = c01 + fy * (c11 - c01);
-    return (c0 + fz * (c1 - c0)) * S::kScale;
+    return __fmul_rn(lerp3(c000, c100, c010, c110, c001, c101, c011, c111, fx, fy, fz), S::kScale);
 }
 
 template <int MODE, int LAYOUT, int DTYPE, bool SKIP, bool DBG>

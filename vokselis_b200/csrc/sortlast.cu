@@ -43,9 +43,9 @@ __device__ __forceinline__ size_t part_z(const PartialArgs& A, int lz) {
 
 // trilinear sample of the window array; taps clamp to the GLOBAL grid, then shift by the window origin
 template <int DTYPE> __device__ __forceinline__ float win_sample(const PartialArgs& A, float qx, float qy, float qz) {
-    const float ux = qx - 0.5f, uy = qy - 0.5f, uz = qz - 0.5f;
+    const float ux = __fsub_rn(qx, 0.5f), uy = __fsub_rn(qy, 0.5f), uz = __fsub_rn(qz, 0.5f);
     const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
-    const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+    const float fx = __fsub_rn(ux, flx), fy = __fsub_rn(uy, fly), fz = __fsub_rn(uz, flz);
     const int x0 = (int)flx, y0 = (int)fly, z0 = (int)flz;
     const size_t xa = part_x(A, min(max(x0, 0), A.gnx - 1) - A.wx), xb = part_x(A, min(max(x0 + 1, 0), A.gnx - 1) - A.wx);
     const size_t ya = part_y(A, min(max(y0, 0), A.gny - 1) - A.wy), yb = part_y(A, min(max(y0 + 1, 0), A.gny - 1) - A.wy);
@@ -55,10 +55,10 @@ template <int DTYPE> __device__ __forceinline__ float win_sample(const PartialAr
     const float c010 = win_load<DTYPE>(A.vol_a, r10 + xa), c110 = win_load<DTYPE>(A.vol_a, r10 + xb);
     const float c001 = win_load<DTYPE>(A.vol_a, r01 + xa), c101 = win_load<DTYPE>(A.vol_a, r01 + xb);
     const float c011 = win_load<DTYPE>(A.vol_a, r11 + xa), c111 = win_load<DTYPE>(A.vol_a, r11 + xb);
-    const float c00 = c000 + fx * (c100 - c000), c10 = c010 + fx * (c110 - c010);
-    const float c01 = c001 + fx * (c101 - c001), c11 = c011 + fx * (c111 - c011);
-    const float c0 = c00 + fy * (c10 - c00), c1 = c01 + fy * (c11 - c01);
-    return (c0 + fz * (c1 - c0)) * (DTYPE == VKRT_U8 ? 1.0f / 255.0f : 1.0f);
+    const float c00 = fmaf(fx, __fsub_rn(c100, c000), c000), c10 = fmaf(fx, __fsub_rn(c110, c010), c010);
+    const float c01 = fmaf(fx, __fsub_rn(c101, c001), c001), c11 = fmaf(fx, __fsub_rn(c111, c011), c011);
+    const float c0 = fmaf(fy, __fsub_rn(c10, c00), c00), c1 = fmaf(fy, __fsub_rn(c11, c01), c01);
+    return __fmul_rn(fmaf(fz, __fsub_rn(c1, c0), c0), DTYPE == VKRT_U8 ? 1.0f / 255.0f : 1.0f);
 }
 
 template <int MODE, int DTYPE, int PASS>

@@ -137,9 +137,13 @@ __device__ __forceinline__ float leap_t(float t, float dt, int n) {
 // reciprocal (an IEEE fdiv is ~10 instructions plus a slow path for zero numerators; profiles/).
 // __saturatef maps NaN -> 0 like fmin(fmax(NaN, 0), 1).
 #define VKRT_SMOOTHSTEP(e0, e1, x) vkrt::smoothstep_r((e0), 1.0f / ((e1) - (e0)), (x))
+// NOTE on determinism: the shading below spells out every multiply-add (fmaf / __fmul_rn / __fadd_rn).
+// Left to the compiler, FMA contraction differs between template instantiations of the kernel (SKIP vs
+// not, DBG vs not), which showed up as one pixel in 10^6 differing by one fp16 ulp between the skipping and
+// the non-skipping kernel. With explicit operations all instantiations and layouts produce identical bits.
 __device__ __forceinline__ float smoothstep_r(float e0, float inv_range, float x) {
-    const float t = __saturatef((x - e0) * inv_range);
-    return t * t * (3.0f - 2.0f * t);
+    const float t = __saturatef(__fmul_rn(__fsub_rn(x, e0), inv_range));
+    return __fmul_rn(__fmul_rn(t, t), fmaf(-2.0f, t, 3.0f));
 }
 
 struct Rgba {
@@ -147,11 +151,10 @@ struct Rgba {
 };
 
 // shaders/raycast_compute.wgsl:74-91 — one sample of `get_col2`. c = volume texel, n = normal texel
-// (n.w unused), p = sample position. clear_color.a == 0 is assumed by the fast path (asserted on the
-// host: with a non-zero clear alpha the generic path below is used).
+// (n.w unused), p = sample position.
 __device__ __forceinline__ float m0_alpha(float ca) {
     // pow(a, 3.0) then smoothstep(0, 0.7, .): x*x*x is within 1 ulp of the exact cube (CUDA powf: 4 ulp).
-    const float a3 = ca * ca * ca;
+    const float a3 = __fmul_rn(__fmul_rn(ca, ca), ca);
     return VKRT_SMOOTHSTEP(0.0f, 0.7f, a3);
 }
 
@@ -160,19 +163,19 @@ __device__ __forceinline__ void m0_shade(Rgba& col, float4 c, float4 n, f3 p, co
     const float kP = 0.57735026f;  // normalize(1,1,-1) = (1,1,-1)/sqrt(3)
     const float shade_s = fmaxf(0.0f, -n.y);  // dot((0,-1,0), n); fmaxf drops NaN
     const float vol_alpha = m0_alpha(c.w);
-    const float ndl = fmaxf((-2.0f * kL) * n.x + (-2.0f * kL) * n.y + (-kL) * n.z, 0.0f);
-    const float pd = VKRT_SMOOTHSTEP(0.3f, 1.5f, kP * p.x + kP * p.y - kP * p.z);
-    const float dsc = ndl * pd;
-    const float vr = c.x + 3.0f * dsc, vg = c.y + 0.3f * dsc, vb = c.z + 0.39f * dsc;
-    const float bottom = 0.9f * __saturatef(0.5f - 0.5f * n.y);
-    const float sh_rg = shade_s * 0.8f;                         // mix(shade, 0, 0.2)
-    const float sh_b = shade_s * 0.8f + (bottom * 0.6f) * 0.2f;  // mix(shade, bottom*0.6, 0.2)
-    const float w = (1.0f - col.a) * vol_alpha;
-    const float k = clear[3] * (1.0f - vol_alpha);
-    col.r = col.r + w * vr * sh_rg + clear[0] * k;
-    col.g = col.g + w * vg * sh_rg + clear[1] * k;
-    col.b = col.b + w * vb * sh_b + clear[2] * k;
-    col.a = col.a + w * (1.0f - clear[3]);
+    const float ndl = fmaxf(fmaf(-kL, n.z, fmaf(-2.0f * kL, n.y, __fmul_rn(-2.0f * kL, n.x))), 0.0f);
+    const float pd = VKRT_SMOOTHSTEP(0.3f, 1.5f, fmaf(-kP, p.z, fmaf(kP, p.y, __fmul_rn(kP, p.x))));
+    const float dsc = __fmul_rn(ndl, pd);
+    const float vr = fmaf(3.0f, dsc, c.x), vg = fmaf(0.3f, dsc, c.y), vb = fmaf(0.39f, dsc, c.z);
+    const float bottom = __fmul_rn(0.9f, __saturatef(fmaf(-0.5f, n.y, 0.5f)));
+    const float sh_rg = __fmul_rn(shade_s, 0.8f);                                   // mix(shade, 0, 0.2)
+    const float sh_b = fmaf(__fmul_rn(bottom, 0.6f), 0.2f, __fmul_rn(shade_s, 0.8f));  // mix(shade, bottom*0.6, 0.2)
+    const float w = __fmul_rn(__fsub_rn(1.0f, col.a), vol_alpha);
+    const float k = __fmul_rn(clear[3], __fsub_rn(1.0f, vol_alpha));
+    col.r = fmaf(clear[0], k, fmaf(__fmul_rn(w, vr), sh_rg, col.r));
+    col.g = fmaf(clear[1], k, fmaf(__fmul_rn(w, vg), sh_rg, col.g));
+    col.b = fmaf(clear[2], k, fmaf(__fmul_rn(w, vb), sh_b, col.b));
+    col.a = fmaf(w, __fsub_rn(1.0f, clear[3]), col.a);
 }
 
 // shaders/raycast_naive.wgsl:70-81,106-117 — transfer function + composite of one scalar sample.
@@ -181,14 +184,14 @@ __device__ __forceinline__ float m1_alpha(float s) { return VKRT_SMOOTHSTEP(0.10
 __device__ __forceinline__ void m1_shade(Rgba& col, float s) {
     const float TAU = 6.28318f;
     const float v = m1_alpha(s);
-    const float pr = 0.5f + 0.5f * __cosf(TAU * v);
-    const float pg = 0.5f + 0.5f * __cosf(TAU * (1.7f * v + 0.15f));
-    const float pb = 0.5f + 0.5f * __cosf(TAU * (0.4f * v + 0.20f));
-    const float w = (1.0f - col.a) * v;
-    col.r += w * pr;
-    col.g += w * pg;
-    col.b += w * pb;
-    col.a += w;
+    const float pr = fmaf(0.5f, __cosf(__fmul_rn(TAU, v)), 0.5f);
+    const float pg = fmaf(0.5f, __cosf(__fmul_rn(TAU, fmaf(1.7f, v, 0.15f))), 0.5f);
+    const float pb = fmaf(0.5f, __cosf(__fmul_rn(TAU, fmaf(0.4f, v, 0.20f))), 0.5f);
+    const float w = __fmul_rn(__fsub_rn(1.0f, col.a), v);
+    col.r = fmaf(w, pr, col.r);
+    col.g = fmaf(w, pg, col.g);
+    col.b = fmaf(w, pb, col.b);
+    col.a = __fadd_rn(col.a, w);
 }
 
 // shaders/raycast_naive.wgsl:63-68
