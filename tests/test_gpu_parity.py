@@ -505,3 +505,24 @@ def test_parameters_are_honoured(rt, oracle, noise64, xor_cam):
             ref, ref_aux, _ = oracle.render(p, xor_cam, W, H, color=color, normal=normal)
             assert np.array_equal(ctx.readback_aux() >> 31, ref_aux >> 31), v
             check_images(ctx.readback_rgba8(), oracle.present(ref))
+
+
+def test_tile_with_fractional_offsets(rt, oracle, noise64, xor_cam):
+    """`Offset` is two f32 (examples/xor/main.rs:20-25): the ray uses gid + offset, the store goes to
+    gid + u32(offset) (raycast_compute.wgsl:141-143). Fractional origins must behave like the shader."""
+    W, H, ts = 320, 180, 64
+    color, normal = noise64
+    table = np.array([[x * ts + fx, y * ts + fy] for y in range(H // ts + 1) for x in range(W // ts + 1)
+                      for fx, fy in [((x % 2) * 0.5, (y % 3) * 0.25)]], np.float32)
+    p = abi.default_params(abi.MODE_M0)
+    p.tile_size = ts
+    ref, _, _ = oracle.render(p, xor_cam, W, H, color=color, normal=normal, offsets=table, want_aux=False)
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_rgba16f(color, normal)
+        q = rt.default_params(abi.MODE_M0)
+        q.tile_size, q.skip_empty = ts, 1
+        ctx.set_params(q)
+        ctx.render_tiles(xor_cam, table)
+        ctx.present()
+        got8 = ctx.readback_rgba8()
+    check_images(got8, oracle.present(ref))

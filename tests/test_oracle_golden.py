@@ -75,6 +75,41 @@ def test_oracle_equals_translated_reference_when_present(oracle):
         assert np.array_equal(ref, got)
 
 
+@pytest.mark.parametrize("seed", range(5))
+def test_oracle_equals_translated_reference_randomised(oracle, seed):
+    """Random volumes (NaN / inf / negative texels, non-cubic dims on both sides of the dt floor), random
+    cameras (outside, grazing, inside the box) and random tile tables with FRACTIONAL offsets (the Offset is
+    two f32: the ray uses gid + offset, the store goes to gid + u32(offset)): hand restatement == the
+    reference's translated WGSL, bit for bit."""
+    from oracle import ref_binding as rb
+
+    if not rb.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    rng = np.random.default_rng(100 + seed)
+    nx, ny, nz = (int(v) for v in rng.choice([3, 8, 17, 40, 180, 200], size=3))
+    if nx * ny * nz > 400_000:
+        nz = max(2, 400_000 // (nx * ny))
+    color = rng.uniform(-0.1, 1.0, size=(nz, ny, nx, 4)).astype(np.float16)
+    color[..., 3] = np.where(rng.uniform(size=(nz, ny, nx)) < 0.5, 0, color[..., 3])
+    normal = rng.normal(size=(nz, ny, nx, 4)).astype(np.float16)
+    normal[rng.uniform(size=(nz, ny, nx)) < 0.15] = np.float16(np.nan)
+    normal[0, 0, 0, 1] = np.float16(-np.inf)
+    W, H = int(rng.integers(40, 120)), int(rng.integers(30, 80))
+    cam = oracle.camera_uniform(float(rng.uniform(0.4, 4.0)), float(rng.uniform(-1.2, 1.2)), float(rng.uniform(-3, 3)),
+                                tuple(rng.uniform(-0.3, 0.3, 3)), W / H)
+    p = abi.default_params(abi.MODE_M0)
+    got, _, _ = oracle.render(p, cam, W, H, color=color.view(np.uint16), normal=normal.view(np.uint16))
+    ref = rb.raycast_compute(cam, color.view(np.uint16), normal.view(np.uint16), W, H)
+    assert np.array_equal(got, ref)
+    ts = int(rng.choice([16, 32, 48]))
+    table = np.array([[x * ts + float(rng.choice([0.0, 0.25, 0.5])), y * ts + float(rng.choice([0.0, 0.75]))]
+                      for y in range(H // ts + 1) for x in range(W // ts + 1)], np.float32)
+    p.tile_size = ts
+    got_t, _, _ = oracle.render(p, cam, W, H, color=color.view(np.uint16), normal=normal.view(np.uint16), offsets=table)
+    ref_t = rb.raycast_compute(cam, color.view(np.uint16), normal.view(np.uint16), W, H, entry="tile", offsets=table, tile_size=ts)
+    assert np.array_equal(got_t, ref_t)
+
+
 def test_m1_follows_naive_march_body(oracle):
     """M1 = raycast_naive's march body on the compute boundary's rays. Render a volume with M1, then
     feed the same rays (mapped from the [-1,1] box to the naive shader's [0,1] box) to the literal
