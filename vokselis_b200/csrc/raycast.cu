@@ -5,10 +5,11 @@
 // shading, front-to-back compositing and early ray termination (`get_col2` :62-97). Mode M1 swaps
 // the march body for the scalar/trilinear/transfer-function body of shaders/raycast_naive.wgsl:96-119.
 //
-// B200 mapping: a block is 8x8 pixels = two warps of 8x4 pixels, so the 32 rays of a
-// warp walk through neighbouring voxels and their texel requests coalesce into a handful of 32-B
-// sectors. All tiles of a frame go out in ONE launch (grid.z = tile). Not a contraction: no tensor
-// cores; the limiter is the texel path (TEX/L1 -> L2 -> HBM) and the dependent ALU chain per sample.
+// B200 mapping: a block is 8x16 pixels = four warps of 8x4 pixels, so the 32 rays of a
+// warp walk through neighbouring voxels and their texel requests fall into a handful of 32-B sectors
+// (L1 hit rate 97 % on the 256^3 u8 volume). All tiles of a frame go out in ONE launch (grid.z = tile).
+// Not a contraction: no tensor cores. Measured limiters (profiles/): instruction issue of the traversal
+// when skipping is on (issue active 80 %), the texture data pipe in the dense case (l1tex 97 %).
 #include <cstdio>
 #include <cstdlib>
 
@@ -19,9 +20,7 @@ namespace vkrt {
 
 namespace {
 
-// Value below which the M1 transfer function is exactly transparent (smoothstep(0.1,1.2,min(.9,s)) == 0
-// <=> s <= 0.1f). A brick is marked empty only if every voxel a sample inside it can touch is <= this
-// slightly smaller bound, so fp32 rounding inside any trilinear formula cannot cross 0.1f.
+// Scalar taps of the LINEAR layout, per storage type.
 template <int DTYPE> struct Scalar;
 template <> struct Scalar<VKRT_U8> {
     // R8Unorm: value = b / 255. The byte is turned into a float on the FMA pipe (0x4B000000 | b is

@@ -212,7 +212,7 @@ __device__ __forceinline__ float4 unpack_rgba16f(uint2 v) {
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
-// ---- bricked layout address (DESIGN.md §5) --------------------------------------------------
+// ---- bricked layout address (DESIGN.md §4.1) --------------------------------------------------
 // M0 interleaved texel = 16 B (colour rgba16f + normal rgba16f). 2x2x2 texels fill one 128-B line;
 // 4x4x4 lines (8^3 voxels, 8 KB) form a brick; bricks are x-fastest. nbx, nby = bricks per axis.
 __device__ __host__ __forceinline__ uint32_t bricked_index(int ix, int iy, int iz, int nbx, int nby) {

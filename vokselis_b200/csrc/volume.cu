@@ -1,9 +1,11 @@
 // volume.cu — volume staging kernels: bricked re-layout, occupancy grids, and the procedural generator.
 //
-//  * interleave_bricked: builds the B200 layout of DESIGN.md §5 from the upload layout of
+//  * interleave_bricked: builds the B200 layout of DESIGN.md §4.1 from the upload layout of
 //    examples/xor/xor_compute.rs:93-118 (two rgba16f textures, x fastest).
-//  * occupancy_m0 / occupancy_m1: one bit per 8^3-voxel brick, set when some sample falling in the
-//    brick can change the running colour (exactness argument: DESIGN.md §4.4).
+//  * occupancy_m0 / occupancy_m1 + distance_step: one byte per 8^3-voxel brick — 0 when some sample falling
+//    in the brick can change the running colour, else the Chebyshev distance (in bricks) to the nearest such
+//    brick (exactness argument: DESIGN.md §4.2). The M1 bound 0.0999999 sits just below the transfer
+//    function's 0.1f threshold so that fp32 rounding inside any trilinear formula cannot cross it.
 //  * generate_xor: shaders/xor.wgsl `cs_main` (:69-78) with `noise_volume` (:55-61) or the dead
 //    bit-pattern `volume` (:46-53), writing both rgba16f volumes on the device ("next" row N1).
 #include "raycast.cuh"
