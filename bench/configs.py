@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--granularity", default="tiles")
     ap.add_argument("--layout", type=int, default=abi.LAYOUT_GATHER)
     ap.add_argument("--checks", type=int, default=1)
+    ap.add_argument("--tile", type=int, default=120, help="sort-first tile edge in pixels (N > 1, granularity tiles)")
     args = ap.parse_args()
     W, H = map(int, args.res.split("x"))
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -92,7 +93,7 @@ def main():
         if world > 1:
             from vokselis_b200 import sortfirst
 
-            group = sortfirst.SortFirstGroup(ctx, rank, world, granularity=args.granularity, tile=120)
+            group = sortfirst.SortFirstGroup(ctx, rank, world, granularity=args.granularity, tile=args.tile)
             f = group.submit(cams[0])
             if rank == 0:
                 group.wait(f)
@@ -140,7 +141,7 @@ def main():
             kernel_ms = float(ms.mean())
             line = {
                 "config": cfg["name"], "volume_edge": n, "dtype": np.dtype(cfg["dtype"]).name, "resolution": [W, H], "n_gpus": world,
-                "granularity": args.granularity if world > 1 else None, "layout": args.layout, "frames": args.frames,
+                "granularity": args.granularity if world > 1 else None, "tile": args.tile if world > 1 else None, "layout": args.layout, "frames": args.frames,
                 "frames_per_s": fps, "ms_per_frame": total / args.frames, "wall_ms_per_frame_incl_flush": 1e3 * wall / args.frames,
                 "ray_samples_per_s": st.samples_reference * fps, "fetched_samples_per_s": st.samples_fetched * fps,
                 "samples_frame0": {"reference": st.samples_reference, "fetched": st.samples_fetched, "rays": st.rays_hit},
