@@ -26,4 +26,12 @@ with rt.Context(0, W, H) as ctx:
     ctx.timing_enable(frames)
     for i in range(frames):
         ctx.render(rt.Camera(zoom, pitch, 1.0 + 2 * np.pi * i / 36, (0, 0, 0), W / H).get_proj_view_matrix())
-    print("frame ms:", np.round(ctx.timing_read(frames), 4))
+    ms = ctx.timing_read(frames)
+    print("frame ms:", np.round(ms[:6], 4), "median", round(float(np.median(ms[2:])), 4), "mean", round(float(np.mean(ms[2:])), 4))
+    # one more frame through the counting kernel: reference-semantics iterations vs samples actually fetched
+    p.count_samples = 1
+    ctx.set_params(p)
+    ctx.reset_stats()
+    ctx.render(rt.Camera(zoom, pitch, 1.0, (0, 0, 0), W / H).get_proj_view_matrix())
+    st = ctx.stats()
+    print("stats: rays_hit", st.rays_hit, "reference", st.samples_reference, "fetched", st.samples_fetched)

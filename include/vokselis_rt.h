@@ -185,6 +185,13 @@ VKRT_API int vkrt_render_tiles(VkrtContext* ctx, const VkrtCameraUniform* cam, c
 /* The reference's tile table (examples/xor/main.rs:80-95): (w/ts+1)*(h/ts+1) origins, row-major.
  * Returns the count; writes at most `cap` entries. */
 VKRT_API int vkrt_tile_table(int width, int height, int tile_size, VkrtOffset* out, int cap);
+/* Host-only helper (no GPU): the screen rectangle, in the shader's pixel coordinates gid + offset
+ * (raycast_compute.wgsl:102-105), outside which no ray of `render` (:99-131) can pass the slab test of
+ * `intersect_box` (:42-53), plus the pixel row the box centre projects to (-1 if unknown). The raycast
+ * launch uses it to build no rays for pixels that cannot hit and to issue the expensive block rows first.
+ * rect = {x0, y0, x1, y1}, inclusive; +-3e38 when the projection is not trustworthy (camera plane cuts the
+ * box, singular matrix): then nothing is culled. */
+VKRT_API int vkrt_box_screen_bounds(const VkrtCameraUniform* cam, int width, int height, float rect[4], int* centre_row);
 
 /* Present — replaces the present pass (shaders/present.wgsl:23-35,111-119;
  * src/context/present_pipeline.rs:123-136): ACES + sRGB of the frame into a W x H RGBA8 buffer. */

@@ -45,9 +45,33 @@ def leap_t(t, dt, n):
         M = (db & 0x7FFFFF) | 0x800000
         rem, half = M & ((1 << shift) - 1), 1 << (shift - 1)
         if rem != half:
-            nb = (tb + n * ((M >> shift) + (1 if rem > half else 0))) & 0xFFFFFFFF
+            nb = tb + n * ((M >> shift) + (1 if rem > half else 0))  # 64-bit in the kernel: must not wrap
             if (nb >> 23) == e:
                 return np.uint32(nb).view(np.float32)
+    return advance_t(t, dt, n)
+
+
+def binade_inc(e, dt):
+    db = int(np.float32(dt).view(np.uint32))
+    ed, shift = db >> 23, e - (db >> 23)
+    if shift < 1 or shift > 24 or ed == 0:
+        return 0xFFFFFFFF
+    M = (db & 0x7FFFFF) | 0x800000
+    rem, half = M & ((1 << shift) - 1), 1 << (shift - 1)
+    if rem == half:
+        return 0xFFFFFFFF
+    return (M >> shift) + (1 if rem > half else 0)
+
+
+def leap_cached(t, dt, n, cache):
+    """leap_cached in vkrt_device.cuh: the per-binade increment lives in `cache` = [e, inc] across a ray's leaps."""
+    tb = int(np.float32(t).view(np.uint32))
+    e = tb >> 23
+    if e != cache[0]:
+        cache[0], cache[1] = e, binade_inc(e, dt)
+    nb = tb + n * cache[1]
+    if (nb >> 23) == e:
+        return np.uint32(nb).view(np.float32)
     return advance_t(t, dt, n)
 
 
@@ -68,3 +92,33 @@ def test_closed_form_equals_repeated_addition(seed):
         assert got.view(np.uint32) == ref.view(np.uint32), (t0, dt, n, got, ref)
         got2 = leap_t(t0, dt, n)
         assert got2.view(np.uint32) == ref.view(np.uint32), ("leap_t", t0, dt, n, got2, ref)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_cached_closed_form_along_a_ray(seed):
+    """A ray alternates leaps of random length and single steps; the cache persists across them."""
+    rng = np.random.default_rng(100 + seed)
+    for _ in range(25):
+        t = ref = np.float32(rng.uniform(0, 3) if rng.uniform() < 0.7 else 0.0)
+        dt = np.float32(0.01) if rng.uniform() < 0.5 else np.float32(10 ** rng.uniform(-4, -1.5))
+        cache = [0xFFFFFFFF, 0xFFFFFFFF]
+        for _ in range(12):
+            n = int(rng.integers(1, 400))
+            for _ in range(n):
+                ref = np.float32(ref + dt)
+            t = leap_cached(t, dt, n, cache)
+            assert t.view(np.uint32) == ref.view(np.uint32), (t, ref, dt, n)
+            t = ref = np.float32(ref + dt)  # an ordinary sample step in between
+
+
+def test_long_leap_from_a_small_t_does_not_wrap():
+    """n * inc exceeds 2^32 when t sits one binade above dt and the leap is long (eye inside a 4096^3 box,
+    dt = 1/4096-ish): a 32-bit product could wrap back into t's binade; the kernel multiplies in 64 bits."""
+    dt = np.float32(2.4414062e-4 * 1.37)
+    for t0 in (np.float32(dt * np.float32(1.01)), np.float32(dt * np.float32(1.9))):
+        for n in (511, 512, 1024, 4097):
+            ref = np.float32(t0)
+            for _ in range(n):
+                ref = np.float32(ref + dt)
+            assert leap_t(t0, dt, n).view(np.uint32) == ref.view(np.uint32)
+            assert leap_cached(t0, dt, n, [0xFFFFFFFF, 0xFFFFFFFF]).view(np.uint32) == ref.view(np.uint32)

@@ -117,3 +117,56 @@ def test_synthetic_volumes_are_deterministic():
     assert np.array_equal(b, volumes.bonsai_standin_u8(32, seed=1, blobs=8)) and b.max() == 255
     h = volumes.hash_noise(16, 3)
     assert h.dtype == np.float16 and 0.3 < float(h.astype(np.float32).mean()) < 0.7
+
+
+def _as_rt_cam(rt, ocam):
+    cam = abi.CameraUniform()
+    C.memmove(C.byref(cam), C.byref(ocam), C.sizeof(cam))
+    return cam
+
+
+def test_box_screen_bounds_contain_every_hit_pixel(rt, oracle):
+    """The launch builds no ray for pixels outside vkrt_box_screen_bounds: every pixel the oracle's slab test
+    (raycast_compute.wgsl:42-53,117-118) accepts must lie inside it — orbit cameras far, near, grazing and
+    inside the box, odd frame shapes, fractional tile offsets, and the identity (orthographic) matrices the
+    reference's camera buffer starts with (src/camera.rs:13-21)."""
+    rng = np.random.default_rng(7)
+    cases = [(3.0, -0.5, 1.0, (0, 0, 0)), (2.0, 0.5, 1.0, (0, 0, 0)), (1.45, 0.1, 0.3, (0, 0, 0)), (0.6, 0.2, 2.0, (0, 0, 0)),
+             (5.0, 1.5, -2.0, (0.5, -0.5, 0.2)), (3.0, 0.0, 0.0, (4.0, 0.0, 0.0)), (50.0, -1.0, 4.0, (0, 0, 0))]
+    cases += [(float(rng.uniform(0.3, 8)), float(rng.uniform(-1.5, 1.5)), float(rng.uniform(-6, 6)),
+               tuple(rng.uniform(-1.5, 1.5, 3))) for _ in range(40)]
+    culled_some = 0
+    for k, (zoom, pitch, yaw, tgt) in enumerate(cases):
+        W, H = [(160, 90), (128, 128), (97, 211)][k % 3]
+        ocam = oracle.camera_uniform(zoom, pitch, yaw, tgt, W / H)
+        offx, offy = [(0.0, 0.0), (0.5, 0.25), (37.0, 11.75)][k % 3]
+        r = oracle.rays(ocam, W, H, offx, offy)
+        hit = r[..., 6] < r[..., 7]
+        (x0, y0, x1, y1), row = rt.box_screen_bounds(_as_rt_cam(rt, ocam), W, H)
+        ys, xs = np.nonzero(hit)
+        if len(xs):
+            cx, cy = xs + offx, ys + offy
+            assert cx.min() >= x0 and cx.max() <= x1 and cy.min() >= y0 and cy.max() <= y1, (zoom, pitch, yaw, tgt)
+        if x0 > -1e30:
+            # not grossly loose either: the margin is two pixels around the box's projected extent
+            inside = (np.arange(W)[None, :] + offx >= x0) & (np.arange(W)[None, :] + offx <= x1) & \
+                     (np.arange(H)[:, None] + offy >= y0) & (np.arange(H)[:, None] + offy <= y1)
+            if len(xs) and xs.min() > 4 and xs.max() < W - 5 and ys.min() > 4 and ys.max() < H - 5:
+                assert x0 >= cx.min() - 4 and x1 <= cx.max() + 4 and y0 >= cy.min() - 4 and y1 <= cy.max() + 4
+            culled_some += int((~inside).any())
+            assert row == -1 or 0 <= row < H
+    assert culled_some >= 10
+    # identity matrices: orthographic rays along +z through (sx, sy, 0); the box covers |sx| <= 1 and |sy| <= 1
+    ident = abi.CameraUniform()
+    for i in range(4):
+        ident.inv_proj[5 * i] = 1.0
+        ident.proj_view[5 * i] = 1.0
+    r = oracle.rays(ident, 64, 36)
+    hit = r[..., 6] < r[..., 7]
+    (x0, y0, x1, y1), _ = rt.box_screen_bounds(ident, 64, 36)
+    ys, xs = np.nonzero(hit)
+    assert len(xs) and xs.min() >= x0 and xs.max() <= x1 and ys.min() >= y0 and ys.max() <= y1
+    # a singular matrix disables culling
+    sing = abi.CameraUniform()
+    (x0, y0, x1, y1), row = rt.box_screen_bounds(sing, 64, 36)
+    assert x0 < -1e30 and y1 > 1e30 and row == -1

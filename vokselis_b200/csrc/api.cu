@@ -7,6 +7,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -277,6 +279,60 @@ bool params_ok(const VkrtParams* p, std::string& why) {
     return true;
 }
 
+// Screen rectangle (in the shader's pixel coordinates, gid + offset) that contains every pixel whose ray
+// can hit the box [-1,1]^3, plus `margin` pixels, and the pixel row of the box centre.
+//
+// A pixel's ray is the world line through inv*(sx,sy,0,1) and inv*(sx,sy,1,1) (raycast_compute.wgsl:107-116);
+// the slab test decides `hit` for the whole line (t0 < t1 is tested before t0 is clamped to 0). With
+// M = inv^-1, a world point X lies on that line iff (MX).xy / (MX).w == (sx, sy). If all eight corners have
+// (MX).w > 0 the box does not cross the plane w = 0, its image is the convex hull of the corner images, and
+// the line hits the box iff (sx, sy) lies inside it; the bounding rectangle of the corner images is
+// therefore conservative. Anything else (singular or non-finite matrix, a corner with w <= 0, i.e. the
+// camera plane cuts the box) disables culling: the rectangle becomes the whole plane. The kernel's own
+// rounding moves the silhouette by ~1e-6 of the frame; the margin is two pixels.
+void cull_rect(const float inv[16], int W, int H, float cull[4], int* centre_row) {
+    const float big = 3.0e38f;
+    cull[0] = cull[1] = -big; cull[2] = cull[3] = big;
+    *centre_row = -1;
+    double a[4][8];
+    for (int r = 0; r < 4; ++r)
+        for (int k = 0; k < 4; ++k) { a[r][k] = (double)inv[4 * k + r]; a[r][4 + k] = r == k ? 1.0 : 0.0; }  // column-major in
+    for (int r = 0; r < 4; ++r)
+        for (int k = 0; k < 4; ++k) if (!std::isfinite(a[r][k])) return;
+    for (int i = 0; i < 4; ++i) {  // Gauss-Jordan, partial pivoting
+        int piv = i;
+        for (int r = i + 1; r < 4; ++r) if (fabs(a[r][i]) > fabs(a[piv][i])) piv = r;
+        if (!(fabs(a[piv][i]) > 1e-30)) return;
+        if (piv != i) for (int k = 0; k < 8; ++k) std::swap(a[i][k], a[piv][k]);
+        const double d = 1.0 / a[i][i];
+        for (int k = 0; k < 8; ++k) a[i][k] *= d;
+        for (int r = 0; r < 4; ++r) if (r != i) { const double f = a[r][i]; if (f != 0.0) for (int k = 0; k < 8; ++k) a[r][k] -= f * a[i][k]; }
+    }
+    // M = a[:, 4:8]. Its overall sign is arbitrary (inv is used projectively): orient it so the box centre has w > 0.
+    double sgn = a[3][7] >= 0.0 ? 1.0 : -1.0;
+    double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300, wmax = 0.0, wmin = 1e300;
+    for (int cidx = 0; cidx < 8; ++cidx) {
+        const double X[4] = {cidx & 1 ? 1.0 : -1.0, cidx & 2 ? 1.0 : -1.0, cidx & 4 ? 1.0 : -1.0, 1.0};
+        double h[4];
+        for (int r = 0; r < 4; ++r) h[r] = sgn * (a[r][4] * X[0] + a[r][5] * X[1] + a[r][6] * X[2] + a[r][7] * X[3]);
+        if (!std::isfinite(h[0]) || !std::isfinite(h[1]) || !std::isfinite(h[3])) return;
+        wmax = std::max(wmax, h[3]); wmin = std::min(wmin, h[3]);
+        if (!(h[3] > 0.0)) return;
+        const double sx = h[0] / h[3], sy = h[1] / h[3];
+        // sx = 2*cx/W - 1 ; sy = (2*cy/H - 1) * (-H/W)     (raycast_compute.wgsl:103-105)
+        const double cx = (sx + 1.0) * 0.5 * W, cy = (1.0 - sy * (double)W / (double)H) * 0.5 * H;
+        x0 = std::min(x0, cx); x1 = std::max(x1, cx); y0 = std::min(y0, cy); y1 = std::max(y1, cy);
+    }
+    if (!(wmin > 1e-6 * wmax)) return;  // a corner (almost) on the camera plane: its image is unreliable
+    if (!std::isfinite(x0) || !std::isfinite(x1) || !std::isfinite(y0) || !std::isfinite(y1)) return;
+    const double margin = 2.0;
+    const double lim = 1.0e9;
+    cull[0] = (float)std::max(-lim, floor(x0 - margin)); cull[1] = (float)std::max(-lim, floor(y0 - margin));
+    cull[2] = (float)std::min(lim, ceil(x1 + margin));   cull[3] = (float)std::min(lim, ceil(y1 + margin));
+    const double cyc = 0.5 * (std::max(y0, 0.0) + std::min(y1, (double)H - 1.0));
+    if (cyc >= 0.0 && cyc <= (double)H - 1.0) *centre_row = (int)cyc;
+}
+
 int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, const VkrtOffset* offsets, int n, bool bracket = true) {
     if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
     if (!cam || !un) return fail(VKRT_ERR_INVALID, "camera/uniform is NULL");
@@ -295,6 +351,13 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     RenderArgs A{};
     memcpy(A.inv, cam->inv_proj, sizeof A.inv);
     A.W = c->W; A.H = c->H;
+    {
+        static int use_cull = -1;  // VKRT_CULL=0 switches it off (A/B only)
+        if (use_cull < 0) { const char* e = getenv("VKRT_CULL"); use_cull = e ? atoi(e) != 0 : 1; }
+        int centre_row;
+        cull_rect(A.inv, A.W, A.H, A.cull, &centre_row);
+        if (!use_cull) { A.cull[0] = A.cull[1] = -3.0e38f; A.cull[2] = A.cull[3] = 3.0e38f; }
+    }
     A.n_tiles = 0; A.tile_size = P.tile_size; A.offsets = nullptr;
     if (offsets && n > 0) {
         if (n > c->offsets_cap) {
@@ -331,6 +394,7 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     }
     // shrink leap regions by ~16 ulp of the largest voxel coordinate (rounding of p and q)
     A.leap_eps = 16.0f * 1.1920929e-07f * (float)(c->nx > c->ny ? (c->nx > c->nz ? c->nx : c->nz) : (c->ny > c->nz ? c->ny : c->nz));
+    A.leap_lim[0] = A.fx - A.leap_eps; A.leap_lim[1] = A.fy - A.leap_eps; A.leap_lim[2] = A.fz - A.leap_eps;
     A.dt_scale = P.dt_scale; A.dt_floor = P.dt_floor; A.alpha_threshold = P.alpha_threshold; A.initial_alpha = P.initial_alpha;
     memcpy(A.clear, P.clear_color, sizeof A.clear);
     A.m1_srgb = P.m1_srgb;
@@ -591,6 +655,14 @@ int vkrt_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform*
 int vkrt_render_tiles(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, const VkrtOffset* offsets, int n) {
     if (!offsets || n <= 0) return fail(VKRT_ERR_INVALID, "vkrt_render_tiles needs at least one offset");
     return do_render(c, cam, un, offsets, n);
+}
+
+int vkrt_box_screen_bounds(const VkrtCameraUniform* cam, int width, int height, float rect[4], int* centre_row) {
+    if (!cam || !rect || width <= 0 || height <= 0) return fail(VKRT_ERR_INVALID, "bad box_screen_bounds arguments");
+    int row = -1;
+    cull_rect(cam->inv_proj, width, height, rect, &row);
+    if (centre_row) *centre_row = row;
+    return VKRT_OK;
 }
 
 int vkrt_tile_table(int width, int height, int tile_size, VkrtOffset* out, int cap) {

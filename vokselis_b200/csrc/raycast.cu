@@ -130,6 +130,42 @@ __device__ __forceinline__ float m1_sample(const RenderArgs& A, float qx, float 
     return __fmul_rn(lerp3(c000, c100, c010, c110, c001, c101, c011, c111, fx, fy, fz), S::kScale);
 }
 
+// Per-ray constants of the leap length model: reciprocal of the voxel-space advance per step on each axis
+// (sign = direction of travel; 1e30 for an axis the ray does not move along) and the drift allowance.
+struct LeapRay {
+    float rqx, rqy, rqz, drift_per_step;
+};
+
+// How many consecutive samples, this one included, provably stay inside the empty region around the sample's
+// brick (d >= 1 from the distance field). Region = bricks [c-(d-1), c+d) per axis, shrunk by A.leap_eps voxels
+// (covers the rounding of p and q). s = steps until the ray leaves it (approximate line model); the margin
+// covers the drift of the replayed additions: each rounds by <= ulp(t)/2, i.e. <= drift_per_step of a step,
+// so after n <= s steps the model is off by at most s * drift_per_step steps (+ a fixed 0.02). The result is
+// >= 1: the current sample's emptiness was read from its exact index.
+//
+// Written around the brick centre m = 8*(i>>3) + 4: the exit plane on an axis is m +- r with
+// r = 4 + 8(d-1) - eps, the sign being the ray's direction on that axis (copied from rq with one LOP3), so
+// there is no per-axis select. In M1 the region is also clipped to the grid (clamp-to-edge sampling: outside
+// is NOT empty; the distance field's border is "occupied", so only a partial last brick can stick out):
+// min(., dims - eps), which never binds for the low plane.
+template <int MODE>
+__device__ __forceinline__ int leap_count(const RenderArgs& A, const LeapRay& L, uint32_t d, int ix, int iy, int iz,
+                                          float qx, float qy, float qz) {
+    const float r = (float)((int)d * 8 - 4) - A.leap_eps;
+    const uint32_t rb = __float_as_uint(r);  // r > 0
+    const float mx = (float)((ix >> 3) * 8 + 4), my = (float)((iy >> 3) * 8 + 4), mz = (float)((iz >> 3) * 8 + 4);
+    float ex = mx + __uint_as_float(rb | (__float_as_uint(L.rqx) & 0x80000000u));
+    float ey = my + __uint_as_float(rb | (__float_as_uint(L.rqy) & 0x80000000u));
+    float ez = mz + __uint_as_float(rb | (__float_as_uint(L.rqz) & 0x80000000u));
+    if (MODE == VKRT_MODE_M1) {
+        ex = fminf(ex, A.leap_lim[0]); ey = fminf(ey, A.leap_lim[1]); ez = fminf(ez, A.leap_lim[2]);
+    }
+    const float sx = (ex - qx) * L.rqx, sy = (ey - qy) * L.rqy, sz = (ez - qz) * L.rqz;
+    const float sm = fminf(fminf(sx, sy), fminf(sz, 4096.0f));
+    // samples j = 0 .. floor(s - margin) (this one is j = 0) lie inside the region
+    return max(__float2int_rz(sm - fmaf(sm, L.drift_per_step, 0.02f)) + 1, 1);
+}
+
 template <int MODE, int LAYOUT, int DTYPE, bool SKIP, bool DBG>
 __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ RenderArgs A) {
     // ---- which pixel -------------------------------------------------------------------------
@@ -148,10 +184,17 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
     valid = valid && px < (uint32_t)A.W && py < (uint32_t)A.H;  // out-of-range textureStore is dropped
 
     // ---- ray ---------------------------------------------------------------------------------
-    f3 eye, dir;
-    gen_ray(A.inv, (float)gx, (float)gy, offx, offy, (float)A.W, (float)A.H, eye, dir);
-    float t0, t1;
-    intersect_box(eye, dir, t0, t1);
+    // Pixels outside A.cull (the screen rectangle around the projected box, computed on the host with a
+    // margin of pixels; the whole plane when the projection is not trustworthy) cannot hit: no ray is built.
+    f3 eye = {0.f, 0.f, 0.f}, dir = {0.f, 0.f, 1.f};
+    float t0 = 0.0f, t1 = -1.0f;
+    {
+        const float cx = (float)gx + offx, cy = (float)gy + offy;
+        if (valid && cx >= A.cull[0] && cy >= A.cull[1] && cx <= A.cull[2] && cy <= A.cull[3]) {
+            gen_ray(A.inv, (float)gx, (float)gy, offx, offy, (float)A.W, (float)A.H, eye, dir);
+            intersect_box(eye, dir, t0, t1);
+        }
+    }
     const bool hit = valid && (t0 < t1);
     t0 = fmaxf(t0, 0.0f);
 
@@ -164,20 +207,22 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
 
     if (hit) {
         const float dt = step_dt(dir, A.fx, A.fy, A.fz, A.dt_scale, A.dt_floor);
-        // Leap geometry (SKIP only; approximate on purpose, see the margins below): voxel-space advance
-        // per step and its reciprocal, per axis.
-        float dqx = 0.f, dqy = 0.f, dqz = 0.f, rqx = 0.f, rqy = 0.f, rqz = 0.f;
+        // Leap geometry (SKIP only; approximate on purpose, see leap_count).
+        LeapRay L = {};
+        LeapCache lc = {0xffffffffu, 0xffffffffu};
         if (SKIP) {
-            dqx = dir.x * A.hx * dt; dqy = dir.y * A.hy * dt; dqz = dir.z * A.hz * dt;
-            rqx = fabsf(dqx) > 1e-12f ? 1.0f / dqx : 1e30f;
-            rqy = fabsf(dqy) > 1e-12f ? 1.0f / dqy : 1e30f;
-            rqz = fabsf(dqz) > 1e-12f ? 1.0f / dqz : 1e30f;
+            const float dqx = dir.x * A.hx * dt, dqy = dir.y * A.hy * dt, dqz = dir.z * A.hz * dt;  // voxels per step
+            L.rqx = fabsf(dqx) > 1e-12f ? 1.0f / dqx : 1e30f;
+            L.rqy = fabsf(dqy) > 1e-12f ? 1.0f / dqy : 1e30f;
+            L.rqz = fabsf(dqz) > 1e-12f ? 1.0f / dqz : 1e30f;
+            // one replayed addition moves t off the exact line by <= ulp(t)/2 <= t1 * 2^-24; in units of a step:
+            L.drift_per_step = (t1 * 5.9604645e-08f) / dt * 2.0f;  // x2 safety
         }
-        // one replayed addition moves t off the exact line by <= ulp(t)/2 <= t1 * 2^-24; in units of a step:
-        const float drift_per_step = SKIP ? (t1 * 5.9604645e-08f) / dt * 2.0f : 0.0f;  // x2 safety
-        // (A while-while traversal — every lane first advances to its next non-empty sample, then the warp
-        // votes and shades together — was measured 1.9x SLOWER on B200: the skip phase costs about as much
-        // as a sample here, and it ran at lower lane utilisation. profiles/r01_whilewhile_ab.md)
+        // (Two traversal restructurings were measured and rejected on B200. While-while — every lane first
+        // advances to its next non-empty sample on its own, then the warp shades together: 1.9x slower,
+        // profiles/r01_whilewhile_ab.md. Warp-uniform leaps — leap only when every live lane sits in empty
+        // space, all by the warp minimum: 13 % slower, the 20 % extra samples taken by lanes that could have
+        // leapt outweigh the leaps saved, profiles/r01_uniform_ab.md.)
         float t = t0;
         while (t < t1) {
             // p = eye + t*dir ; q = (p + 1) * (N/2) — exact, decides the texel
@@ -186,37 +231,16 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
             const int ix = __float2int_rz(qx), iy = __float2int_rz(qy), iz = __float2int_rz(qz);
             const bool inb = (unsigned)ix < (unsigned)A.nx && (unsigned)iy < (unsigned)A.ny && (unsigned)iz < (unsigned)A.nz;
             if (SKIP) {
-                // Exact empty-space skipping (DESIGN.md §4.4). A sample in an empty brick (or, in M0,
+                // Exact empty-space skipping (DESIGN.md §4.2). A sample in an empty brick (or, in M0,
                 // outside the grid) leaves colour and alpha bit-identical, so only the t sequence
-                // advances — by repeated addition, exactly like the reference loop. n = how many
-                // consecutive samples (this one included) provably stay inside the empty region.
+                // advances — landing on exactly the floats the reference's `t = t + dt` visits. n = how
+                // many consecutive samples (this one included) provably stay inside the empty region.
                 int n = 0;
                 if (!inb) {
                     n = MODE == VKRT_MODE_M0 ? 1 : 0;
                 } else {
                     const uint32_t d = brick_distance(A, ix, iy, iz);
-                    if (d != 0u) {
-                        n = 1;
-                        // Region = bricks [c-(d-1), c+d) per axis, shrunk by A.leap_eps voxels (covers the
-                        // rounding of p and q). s = steps until the ray leaves it (approximate line model);
-                        // the margin covers the drift of the replayed additions: each rounds by <= ulp(t)/2,
-                        // i.e. <= drift_per_step of a step, so after n <= s steps the model is off by at most
-                        // s * drift_per_step steps (+ a fixed 0.02).
-                        const float w = (float)((int)d * 8 - 8);  // (d-1) bricks on either side
-                        const float bx0 = (float)(ix & ~7), by0 = (float)(iy & ~7), bz0 = (float)(iz & ~7);
-                        const float lox = bx0 - w + A.leap_eps, loy = by0 - w + A.leap_eps, loz = bz0 - w + A.leap_eps;
-                        float hix = bx0 + 8.0f + w, hiy = by0 + 8.0f + w, hiz = bz0 + 8.0f + w;
-                        if (MODE == VKRT_MODE_M1) {  // clamp-to-edge sampling: outside the grid is NOT empty
-                            hix = fminf(hix, A.fx); hiy = fminf(hiy, A.fy); hiz = fminf(hiz, A.fz);
-                        }
-                        hix -= A.leap_eps; hiy -= A.leap_eps; hiz -= A.leap_eps;
-                        const float sx = ((dqx > 0.f ? hix : lox) - qx) * rqx;
-                        const float sy = ((dqy > 0.f ? hiy : loy) - qy) * rqy;
-                        const float sz = ((dqz > 0.f ? hiz : loz) - qz) * rqz;
-                        const float sm = fminf(fminf(sx, sy), fminf(sz, 4096.0f));
-                        // samples j = 0 .. floor(s - margin) (this one is j = 0) lie inside the region
-                        n = max(__float2int_rz(sm - (0.02f + sm * drift_per_step)) + 1, 1);
-                    }
+                    if (d != 0u) n = leap_count<MODE>(A, L, d, ix, iy, iz, qx, qy, qz);
                 }
                 if (n > 0) {
                     if (DBG) {
@@ -225,7 +249,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
                             t = xadd(t, dt);
                         }
                     } else if (n >= A.leap_closed_min) {
-                        t = leap_t(t, dt, n);  // closed form, bit-identical to n additions
+                        t = leap_cached(t, dt, n, lc);  // closed form, bit-identical to n additions
                     } else {
 #pragma unroll 4
                         for (int j = 0; j < n; ++j) t = xadd(t, dt);
@@ -247,6 +271,8 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
             if (col.a >= A.alpha_threshold) break;
             t = xadd(t, dt);
         }
+    }
+    if (hit) {
         if (MODE == VKRT_MODE_M1 && A.m1_srgb) {
             col.r = linear_to_srgb_naive(col.r);
             col.g = linear_to_srgb_naive(col.g);

@@ -12,6 +12,7 @@ namespace vkrt {
 struct RenderArgs {
     float inv[16];  // CameraUniform.inv_proj, column-major (src/camera.rs:10)
     int W, H;
+    float cull[4];  // x0, y0, x1, y1 (ray coordinates = gid + offset): pixels outside cannot hit the box
     // tiles: n_tiles == 0 -> `single`; else grid.z indexes `offsets` (device memory)
     const VkrtOffset* offsets;
     int n_tiles, tile_size;
@@ -25,6 +26,7 @@ struct RenderArgs {
     int nbx, nby, nbz;  // 8^3-voxel bricks per axis (occupancy grid and bricked layout)
     const uint8_t* dist;  // per brick: 0 = occupied, d = bricks within Chebyshev radius d-1 are all empty
     float leap_eps;       // safety shrink of leap regions, in voxels
+    float leap_lim[3];    // M1: dims - leap_eps (leap regions are clipped to the grid)
     int leap_closed_min;  // leaps of at least this many samples use the closed-form advance (leap_t)
     // parameters (VkrtParams)
     float dt_scale, dt_floor, alpha_threshold, initial_alpha;

@@ -125,10 +125,38 @@ __device__ __forceinline__ float leap_t(float t, float dt, int n) {
         const uint32_t M = (db & 0x7fffffu) | 0x800000u;
         const uint32_t rem = M & ((1u << shift) - 1u), half = 1u << (shift - 1);
         if (rem != half) {
-            const uint32_t nb = tb + (uint32_t)n * ((M >> shift) + (rem > half ? 1u : 0u));
-            if ((int)(nb >> 23) == e) return __uint_as_float(nb);
+            // 64-bit: n * inc can exceed 2^32 (n up to thousands, inc up to 2^23) and must not wrap into the binade
+            const unsigned long long nb = (unsigned long long)tb + (unsigned long long)(uint32_t)n * ((M >> shift) + (rem > half ? 1u : 0u));
+            if ((nb >> 23) == (unsigned long long)e) return __uint_as_float((uint32_t)nb);
         }
     }
+    return advance_t(t, dt, n);
+}
+
+// The same fast path with the per-binade increment kept in registers across the leaps of one ray (a ray
+// crosses one or two binades of t): shift, compare, one wide multiply-add, compare. inc == 0xffffffff marks
+// "no closed form in this binade" (t below dt's binade, dt < ulp(t)/2, an exact tie, subnormals): with it the
+// binade check below always fails and advance_t takes over.
+struct LeapCache {
+    uint32_t e, inc;  // biased exponent the increment was derived for (0xffffffff = none yet)
+};
+__device__ __forceinline__ uint32_t binade_inc(uint32_t e, float dt) {
+    const uint32_t db = __float_as_uint(dt), ed = db >> 23;
+    const int shift = (int)e - (int)ed;
+    if (shift < 1 || shift > 24 || ed == 0u) return 0xffffffffu;
+    const uint32_t M = (db & 0x7fffffu) | 0x800000u;
+    const uint32_t rem = M & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    if (rem == half) return 0xffffffffu;
+    return (M >> shift) + (rem > half ? 1u : 0u);  // >= 1 for shift <= 24
+}
+__device__ __forceinline__ float leap_cached(float t, float dt, int n, LeapCache& c) {
+    const uint32_t tb = __float_as_uint(t), e = tb >> 23;  // t >= 0
+    if (e != c.e) {
+        c.e = e;
+        c.inc = binade_inc(e, dt);
+    }
+    const unsigned long long nb = (unsigned long long)tb + (unsigned long long)(uint32_t)n * c.inc;
+    if ((nb >> 23) == (unsigned long long)e) return __uint_as_float((uint32_t)nb);
     return advance_t(t, dt, n);
 }
 
@@ -184,6 +212,9 @@ __device__ __forceinline__ float m1_alpha(float s) { return VKRT_SMOOTHSTEP(0.10
 __device__ __forceinline__ void m1_shade(Rgba& col, float s) {
     const float TAU = 6.28318f;
     const float v = m1_alpha(s);
+    // v == 0 (s <= 0.1, most of a sparse volume): w = 0 and the palette is finite, so the sample leaves colour
+    // and alpha bit-identical — skip the three cosines. v is never NaN (__saturatef).
+    if (!(v > 0.0f)) return;
     const float pr = fmaf(0.5f, __cosf(__fmul_rn(TAU, v)), 0.5f);
     const float pg = fmaf(0.5f, __cosf(__fmul_rn(TAU, fmaf(1.7f, v, 0.15f))), 0.5f);
     const float pb = fmaf(0.5f, __cosf(__fmul_rn(TAU, fmaf(0.4f, v, 0.20f))), 0.5f);

@@ -25,7 +25,7 @@ _SO = Path(os.environ.get("VKRT_LIB") or (Path(__file__).resolve().parent / "lib
 EXPORTS = [
     "vkrt_create", "vkrt_destroy", "vkrt_resize", "vkrt_last_error", "vkrt_default_params", "vkrt_set_params",
     "vkrt_get_params", "vkrt_upload_rgba16f", "vkrt_upload_scalar", "vkrt_generate_xor", "vkrt_download_rgba16f",
-    "vkrt_render", "vkrt_render_tiles", "vkrt_tile_table", "vkrt_present", "vkrt_readback", "vkrt_readback_rgba8",
+    "vkrt_render", "vkrt_render_tiles", "vkrt_tile_table", "vkrt_box_screen_bounds", "vkrt_present", "vkrt_readback", "vkrt_readback_rgba8",
     "vkrt_readback_aux", "vkrt_sync", "vkrt_frame_host", "vkrt_frame_host_async", "vkrt_frame_host_wait",
     "vkrt_frame_host_slot_ptr", "vkrt_frame_device_ptr", "vkrt_frame_rgba8_device_ptr", "vkrt_stream", "vkrt_stats",
     "vkrt_reset_stats", "vkrt_timing_enable", "vkrt_timing_read", "vkrt_flush_l2", "vkrt_volume_info", "vkrt_camera_uniform", "vkrt_dispatch_optimal",
@@ -71,6 +71,7 @@ def lib() -> C.CDLL:
         "vkrt_render": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), C.POINTER(Offset)]),
         "vkrt_render_tiles": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp, ci]),
         "vkrt_tile_table": (ci, [ci, ci, ci, vp, ci]),
+        "vkrt_box_screen_bounds": (ci, [C.POINTER(CameraUniform), ci, ci, C.POINTER(C.c_float * 4), C.POINTER(ci)]),
         "vkrt_present": (ci, [vp]),
         "vkrt_readback": (ci, [vp, vp]),
         "vkrt_readback_rgba8": (ci, [vp, vp]),
@@ -152,6 +153,14 @@ def tile_table(width: int, height: int, tile_size: int = 256) -> np.ndarray:
     out = np.zeros((n, 2), np.float32)
     lib().vkrt_tile_table(width, height, tile_size, _vp(out), n)
     return out
+
+
+def box_screen_bounds(cam: CameraUniform, width: int, height: int):
+    """(x0, y0, x1, y1), centre_row: the pixel rectangle outside which no ray can hit the box (host-only)."""
+    rect = (C.c_float * 4)()
+    row = C.c_int(-1)
+    _check(lib().vkrt_box_screen_bounds(C.byref(cam), width, height, C.byref(rect), C.byref(row)))
+    return tuple(float(v) for v in rect), int(row.value)
 
 
 class Camera:
