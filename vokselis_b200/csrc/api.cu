@@ -81,6 +81,7 @@ struct VkrtContext {
     cudaArray_t arr_a = nullptr, arr_b = nullptr, arr_g = nullptr;
     cudaTextureObject_t tex_a = 0, tex_b = 0, tex_g = 0;  // tex_g: layered + gather (LAYOUT_GATHER)
     uint8_t* dist = nullptr;  // brick distance field (0 = occupied)
+    int occ_lo[3] = {0, 0, 0}, occ_hi[3] = {-1, -1, -1};  // bounding box of the occupied bricks (inclusive); hi < lo = none
     // brick-partitioned (sort-last) state: the resident volume is a window of a larger global grid
     bool windowed = false;
     bool win_bricked = false;  // scalar windows are stored as 8^3 bricks (sortlast.cu)
@@ -256,15 +257,20 @@ int build_occupancy(VkrtContext* c) {
     const size_t cells = (size_t)c->nbx * c->nby * c->nbz;
     uint8_t* scratch = nullptr;
     CK(cudaMalloc(&c->dist, cells));
-    CK(cudaMalloc(&scratch, cells));
+    CK(cudaMalloc(&scratch, cells < 64 ? 64 : cells));
     cudaError_t e;
     if (c->kind == VOL_RGBA16F) e = launch_occupancy_m0((const uint2*)c->lin_a, c->nx, c->ny, c->nz, c->nbx, c->nby, c->nbz, c->dist, c->stream);
     else e = launch_occupancy_m1(c->lin_a, c->dtype, c->nx, c->ny, c->nz, c->nbx, c->nby, c->nbz, c->dist, c->stream);
     // bricks outside the grid: empty for M0 (out-of-range texels read 0), occupied for M1 (clamp-to-edge)
     if (e == cudaSuccess) e = launch_distance_transform(c->dist, scratch, c->nbx, c->nby, c->nbz, c->kind == VOL_RGBA16F ? 255 : 0, kMaxLeapBricks, c->stream);
+    // bounding box of the occupied bricks (the raycast clips every ray to it); reuses the scratch buffer
+    int bounds[6] = {0, 0, 0, -1, -1, -1};
+    if (e == cudaSuccess) e = launch_occupied_bounds(c->dist, c->nbx, c->nby, c->nbz, (int*)scratch, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bounds, scratch, sizeof bounds, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(scratch);
     if (e != cudaSuccess) return cuda_fail(e, "build_occupancy");
+    for (int k = 0; k < 3; ++k) { c->occ_lo[k] = bounds[k]; c->occ_hi[k] = bounds[3 + k]; }
     return VKRT_OK;
 }
 
@@ -394,6 +400,19 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     }
     // shrink leap regions by ~16 ulp of the largest voxel coordinate (rounding of p and q)
     A.leap_eps = 16.0f * 1.1920929e-07f * (float)(c->nx > c->ny ? (c->nx > c->nz ? c->nx : c->nz) : (c->ny > c->nz ? c->ny : c->nz));
+    {
+        static int use_bb = -1;  // VKRT_BBOX=0 switches the clip off (A/B only)
+        if (use_bb < 0) { const char* e = getenv("VKRT_BBOX"); use_bb = e ? atoi(e) != 0 : 1; }
+        const int n3[3] = {c->nx, c->ny, c->nz};
+        for (int k = 0; k < 3; ++k) {
+            if (!use_bb) { A.bb_lo[k] = -3.0e38f; A.bb_hi[k] = 3.0e38f; continue; }
+            if (c->occ_hi[0] < c->occ_lo[0]) { A.bb_lo[k] = 1.0f; A.bb_hi[k] = -1.0f; continue; }
+            // voxel q = (p + 1) * n/2  ->  p = 2q/n - 1; one voxel of margin (float rounding is ~1e-4 of that)
+            const double lo = (double)c->occ_lo[k] * 8.0 - 1.0, hi = std::min((double)(c->occ_hi[k] + 1) * 8.0, (double)n3[k]) + 1.0;
+            A.bb_lo[k] = (float)(2.0 * lo / n3[k] - 1.0);
+            A.bb_hi[k] = (float)(2.0 * hi / n3[k] - 1.0);
+        }
+    }
     A.leap_lim[0] = A.fx - A.leap_eps; A.leap_lim[1] = A.fy - A.leap_eps; A.leap_lim[2] = A.fz - A.leap_eps;
     A.dt_scale = P.dt_scale; A.dt_floor = P.dt_floor; A.alpha_threshold = P.alpha_threshold; A.initial_alpha = P.initial_alpha;
     memcpy(A.clear, P.clear_color, sizeof A.clear);

@@ -186,13 +186,13 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
     // ---- ray ---------------------------------------------------------------------------------
     // Pixels outside A.cull (the screen rectangle around the projected box, computed on the host with a
     // margin of pixels; the whole plane when the projection is not trustworthy) cannot hit: no ray is built.
-    f3 eye = {0.f, 0.f, 0.f}, dir = {0.f, 0.f, 1.f};
+    f3 eye = {0.f, 0.f, 0.f}, dir = {0.f, 0.f, 1.f}, inv_dir = {0.f, 0.f, 1.f};
     float t0 = 0.0f, t1 = -1.0f;
     {
         const float cx = (float)gx + offx, cy = (float)gy + offy;
         if (valid && cx >= A.cull[0] && cy >= A.cull[1] && cx <= A.cull[2] && cy <= A.cull[3]) {
             gen_ray(A.inv, (float)gx, (float)gy, offx, offy, (float)A.W, (float)A.H, eye, dir);
-            intersect_box(eye, dir, t0, t1);
+            intersect_box(eye, dir, t0, t1, inv_dir);
         }
     }
     const bool hit = valid && (t0 < t1);
@@ -223,8 +223,41 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
         // profiles/r01_whilewhile_ab.md. Warp-uniform leaps — leap only when every live lane sits in empty
         // space, all by the warp minimum: 13 % slower, the 20 % extra samples taken by lanes that could have
         // leapt outweigh the leaps saved, profiles/r01_uniform_ab.md.)
-        float t = t0;
-        while (t < t1) {
+        float t = t0, t_end = t1;
+        bool terminated = false;  // (DBG bookkeeping only)
+        if (SKIP) {
+            // Clip the march to the bounding box of the occupied bricks (grown by one voxel, A.bb_*): every
+            // sample outside it lies in an empty brick, i.e. is a bit-exact no-op, so the loop may stop at the
+            // box's exit (no trailing leaps to the far face), does not run at all for rays that miss it, and
+            // reaches its entry with ONE leap — landing on the floats the reference's t = t + dt visits, like
+            // every leap. The exit test is on the sample's own t, so drift does not matter there; the entry
+            // leap keeps the margin of leap_count (2 steps + the drift of the replayed additions), on top of
+            // the voxel of margin in the box.
+            float tb0, tb1;
+            slab_box(eye, inv_dir, A.bb_lo, A.bb_hi, tb0, tb1);
+            // a ray that misses the box (or an empty volume) does not march at all; otherwise tb0 < t_end <= t1,
+            // which also bounds the entry leap (a ray almost parallel to a face it passes outside of has an
+            // "entry" thousands of steps away)
+            t_end = (tb0 < tb1 && A.bb_lo[0] <= A.bb_hi[0]) ? fminf(t1, tb1) : -1.0f;
+            if (tb0 > t0 && tb0 < t_end) {
+                const float s = fminf((tb0 - t0) * __frcp_rn(dt), 1.0e6f);
+                const int n0 = __float2int_rz(s - fmaf(s, L.drift_per_step, 2.0f));
+                if (n0 >= 1) {
+                    if (DBG) {
+                        for (int j = 0; j < n0 && t < t1; ++j) {
+                            ++iters;
+                            t = xadd(t, dt);
+                        }
+                    } else if (n0 >= A.leap_closed_min) {
+                        t = leap_cached(t, dt, n0, lc);
+                    } else {  // measured faster than the closed form at these lengths (profiles/r01_bounds_clip.md)
+#pragma unroll 4
+                        for (int j = 0; j < n0; ++j) t = xadd(t, dt);
+                    }
+                }
+            }
+        }
+        while (t < t_end) {
             // p = eye + t*dir ; q = (p + 1) * (N/2) — exact, decides the texel
             f3 p = {xadd(eye.x, xmul(t, dir.x)), xadd(eye.y, xmul(t, dir.y)), xadd(eye.z, xmul(t, dir.z))};
             const float qx = xmul(xadd(p.x, 1.0f), A.hx), qy = xmul(xadd(p.y, 1.0f), A.hy), qz = xmul(xadd(p.z, 1.0f), A.hz);
@@ -268,8 +301,17 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
             } else {
                 m1_shade(col, m1_sample<LAYOUT, DTYPE>(A, qx, qy, qz));
             }
-            if (col.a >= A.alpha_threshold) break;
+            if (col.a >= A.alpha_threshold) {
+                terminated = true;
+                break;
+            }
             t = xadd(t, dt);
+        }
+        if (DBG && SKIP && !terminated) {  // the reference's loop runs on to the far face: count those iterations
+            while (t < t1) {
+                ++iters;
+                t = xadd(t, dt);
+            }
         }
     }
     if (hit) {

@@ -52,10 +52,25 @@ __device__ __forceinline__ void gen_ray(const float* inv, float gx, float gy, fl
 }
 
 // shaders/raycast_compute.wgsl:42-53 — slab test against [-1,1]^3 (fminf/fmaxf = WGSL min/max on NVIDIA).
-__device__ __forceinline__ void intersect_box(f3 o, f3 d, float& t0, float& t1) {
+__device__ __forceinline__ void intersect_box(f3 o, f3 d, float& t0, float& t1, f3& inv) {
     const float ix = xdiv(1.0f, d.x), iy = xdiv(1.0f, d.y), iz = xdiv(1.0f, d.z);
+    inv.x = ix; inv.y = iy; inv.z = iz;
     const float ax = xmul(xsub(-1.0f, o.x), ix), ay = xmul(xsub(-1.0f, o.y), iy), az = xmul(xsub(-1.0f, o.z), iz);
     const float bx = xmul(xsub(1.0f, o.x), ix), by = xmul(xsub(1.0f, o.y), iy), bz = xmul(xsub(1.0f, o.z), iz);
+    t0 = fmaxf(fminf(ax, bx), fmaxf(fminf(ay, by), fminf(az, bz)));
+    t1 = fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz)));
+}
+
+__device__ __forceinline__ void intersect_box(f3 o, f3 d, float& t0, float& t1) {
+    f3 inv;
+    intersect_box(o, d, t0, t1, inv);
+}
+
+// The same slab test against an arbitrary box (used to clip rays to the occupied bounds; approximate
+// arithmetic is fine there, the box carries a margin).
+__device__ __forceinline__ void slab_box(f3 o, f3 inv, const float* lo, const float* hi, float& t0, float& t1) {
+    const float ax = (lo[0] - o.x) * inv.x, ay = (lo[1] - o.y) * inv.y, az = (lo[2] - o.z) * inv.z;
+    const float bx = (hi[0] - o.x) * inv.x, by = (hi[1] - o.y) * inv.y, bz = (hi[2] - o.z) * inv.z;
     t0 = fmaxf(fminf(ax, bx), fmaxf(fminf(ay, by), fminf(az, bz)));
     t1 = fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz)));
 }

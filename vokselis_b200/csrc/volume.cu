@@ -113,6 +113,23 @@ __global__ void __launch_bounds__(256) distance_step_kernel(const uint8_t* __res
     out[c] = (uint8_t)d;
 }
 
+// Bounding box, in bricks, of the occupied cells (dist == 0) of the finished distance field:
+// out = {min x, min y, min z, max x, max y, max z}, initialised to {INT_MAX x3, -1 x3} by the launcher.
+__global__ void __launch_bounds__(256) occupied_bounds_kernel(const uint8_t* __restrict__ dist, int nbx, int nby, int nbz, int* __restrict__ out) {
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool occ = c < (size_t)nbx * nby * nbz && dist[c] == 0;
+    const int bx = (int)(c % (size_t)nbx), by = (int)((c / (size_t)nbx) % (size_t)nby), bz = (int)(c / ((size_t)nbx * nby));
+    const int big = 0x7fffffff;
+    const int lx = __reduce_min_sync(0xffffffffu, occ ? bx : big), ly = __reduce_min_sync(0xffffffffu, occ ? by : big);
+    const int lz = __reduce_min_sync(0xffffffffu, occ ? bz : big);
+    const int hx = __reduce_max_sync(0xffffffffu, occ ? bx : -1), hy = __reduce_max_sync(0xffffffffu, occ ? by : -1);
+    const int hz = __reduce_max_sync(0xffffffffu, occ ? bz : -1);
+    if ((threadIdx.x & 31u) == 0u && hx >= 0) {
+        atomicMin(out + 0, lx); atomicMin(out + 1, ly); atomicMin(out + 2, lz);
+        atomicMax(out + 3, hx); atomicMax(out + 4, hy); atomicMax(out + 5, hz);
+    }
+}
+
 // ---- shaders/xor.wgsl -------------------------------------------------------------------------
 __device__ __forceinline__ float fractf(float x) { return x - floorf(x); }
 // :18-20. The product is rounded before the floor is subtracted (no FMA contraction): the hash amplifies
@@ -422,6 +439,15 @@ cudaError_t launch_distance_transform(uint8_t* dist, uint8_t* scratch, int nbx, 
         cudaError_t e = cudaMemcpyAsync(dist, a, cells, cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return e;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_occupied_bounds(const uint8_t* dist, int nbx, int nby, int nbz, int* d_out6, cudaStream_t s) {
+    static const int init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1};
+    cudaError_t e = cudaMemcpyAsync(d_out6, init, sizeof init, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+    const size_t cells = (size_t)nbx * nby * nbz;
+    occupied_bounds_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(dist, nbx, nby, nbz, d_out6);
     return cudaGetLastError();
 }
 
