@@ -526,3 +526,99 @@ def test_tile_with_fractional_offsets(rt, oracle, noise64, xor_cam):
         ctx.present()
         got8 = ctx.readback_rgba8()
     check_images(got8, oracle.present(ref))
+
+
+def _corner_content(nx, ny, nz, seed=11):
+    """Content confined to a small off-centre region of a grid whose dims are not multiples of 8: the
+    occupied-bounds box is far from the faces on one side and cuts a partial brick on the other."""
+    rng = np.random.default_rng(seed)
+    scalar = np.zeros((nz, ny, nx), np.uint8)
+    zs, ys, xs = slice(nz * 5 // 8, nz - 2), slice(3, ny // 3), slice(nx * 2 // 3, nx)
+    scalar[zs, ys, xs] = rng.integers(0, 256, size=scalar[zs, ys, xs].shape) * (rng.uniform(size=scalar[zs, ys, xs].shape) < 0.5)
+    color = np.zeros((nz, ny, nx, 4), np.float16)
+    color[..., :3] = rng.uniform(0, 1, size=(nz, ny, nx, 3))
+    color[zs, ys, xs, 3] = rng.uniform(0, 0.9, size=scalar[zs, ys, xs].shape) * (rng.uniform(size=scalar[zs, ys, xs].shape) < 0.5)
+    normal = rng.normal(size=(nz, ny, nx, 4)).astype(np.float16)
+    return scalar, color, normal
+
+
+@pytest.mark.parametrize("mode", [abi.MODE_M0, abi.MODE_M1])
+def test_cull_rectangle_and_bounds_clip_are_bit_exact(rt, oracle, mode):
+    """The PRODUCTION kernel (no counters) with skipping on — cull rectangle, clip to the occupied bounds, the
+    entry leap in both its forms (replayed for short gaps, closed form from 64 steps up), closed-form leaps
+    inside — against the same kernel with skipping off: identical bits; and the counting kernel's hit masks and
+    iteration counts against the oracle. Cameras: far, behind the content (long entry gap), inside the box but
+    outside the occupied bounds, inside the bounds, grazing a face, and one whose near plane cuts the box."""
+    W, H = 384, 216
+    nx, ny, nz = 100, 60, 77
+    scalar, color, normal = _corner_content(nx, ny, nz)
+    cams = [(3.0, -0.5, 1.0, (0, 0, 0)), (2.6, 0.4, 4.0, (0, 0, 0)), (0.5, 0.2, 2.5, (-0.4, 0.3, -0.3)), (0.3, -0.1, 0.7, (0.6, -0.7, 0.5)),
+            (1.45, 0.0, 0.0, (0, 0.99, 0)), (1.1, 0.3, -1.0, (0.2, 0.1, 0.0))]
+    with rt.Context(0, W, H) as ctx:
+        if mode == abi.MODE_M0:
+            ctx.upload_rgba16f(color.view(np.uint16), normal.view(np.uint16))
+            layouts = LAYOUTS_M0
+        else:
+            ctx.upload_scalar(scalar)
+            layouts = [abi.LAYOUT_LINEAR, abi.LAYOUT_GATHER]
+        info = ctx.volume_info()
+        assert 0 < info["bricks_occupied"] < info["bricks_total"] // 4
+        long_gap = False
+        for zoom, pitch, yaw, tgt in cams:
+            cam = rt.Camera(zoom, pitch, yaw, tgt, W / H).get_proj_view_matrix()
+            if mode == abi.MODE_M0:
+                ref, aux, st = oracle.render(abi.default_params(mode), cam, W, H, color=color.view(np.uint16), normal=normal.view(np.uint16))
+            else:
+                ref, aux, st = oracle.render(abi.default_params(mode), cam, W, H, scalar=scalar)
+            for layout in layouts:
+                frames = []
+                for skip in (0, 1):
+                    q = rt.default_params(mode)
+                    q.skip_empty, q.count_samples, q.layout = skip, 0, layout
+                    ctx.set_params(q)
+                    ctx.render(cam)
+                    frames.append(ctx.readback())
+                assert np.array_equal(frames[0], frames[1]), (zoom, pitch, yaw, layout)
+                q.count_samples = 1
+                ctx.set_params(q)
+                ctx.reset_stats()
+                ctx.render(cam)
+                assert np.array_equal(ctx.readback(), frames[1])
+                got_aux = ctx.readback_aux()
+                assert np.array_equal(got_aux >> 31, aux >> 31), (zoom, pitch, yaw, layout)
+                # counts: the documented allowance against the oracle (last-ulp alpha differences can move the
+                # 0.95 crossing by one sample on a rare ray); exact between the kernel's own skip settings
+                diff = got_aux.astype(np.int64) - aux.astype(np.int64)
+                assert (diff != 0).mean() <= 1e-3 and np.abs(diff).max() <= 1, (zoom, pitch, yaw, layout)
+                s = ctx.stats()
+                assert abs(int(s.samples_reference) - int(st.samples_reference)) <= 1e-4 * max(st.samples_reference, 1) + 2
+                assert s.samples_fetched <= s.samples_reference
+                q.skip_empty = 0
+                ctx.set_params(q)
+                ctx.render(cam)
+                assert np.array_equal(ctx.readback_aux(), got_aux), (zoom, pitch, yaw, layout)
+            ctx.present()
+            check_images(ctx.readback_rgba8(), oracle.present(ref))
+            long_gap = long_gap or int((aux & 0x7FFFFFFF).max()) > 200
+        assert long_gap  # some rays march > 200 reference steps, so entry gaps beyond 64 steps occur
+
+
+def test_all_empty_volume_with_skipping(rt, oracle, xor_cam):
+    """Nothing occupied: no ray marches; every hit pixel keeps the initial colour, like the full march."""
+    W, H = 256, 144
+    scalar = np.full((24, 40, 32), 20, np.uint8)  # below the transfer function's 0.1 threshold everywhere
+    ref, aux, _ = oracle.render(abi.default_params(1), xor_cam, W, H, scalar=scalar)
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_scalar(scalar)
+        assert ctx.volume_info()["bricks_occupied"] == 0
+        out = []
+        for skip, count in ((0, 0), (1, 0), (1, 1)):
+            q = rt.default_params(abi.MODE_M1)
+            q.skip_empty, q.count_samples, q.layout = skip, count, abi.LAYOUT_GATHER
+            ctx.set_params(q)
+            ctx.render(xor_cam)
+            out.append(ctx.readback())
+        assert np.array_equal(out[0], out[1]) and np.array_equal(out[1], out[2])
+        assert np.array_equal(ctx.readback_aux(), aux)
+        check_images_hdr = np.abs(out[0].view(np.float16).astype(np.float32) - ref.view(np.float16).astype(np.float32)).max()
+        assert check_images_hdr == 0.0
