@@ -29,10 +29,23 @@ template <> __device__ __forceinline__ float win_load<VKRT_F16>(const void* p, s
 }
 template <> __device__ __forceinline__ float win_load<VKRT_F32>(const void* p, size_t i) { return __ldg((const float*)p + i); }
 
-// Element index of window-local voxel (lx, ly, lz). Bricked windows (scalar data) store 8^3-voxel bricks
-// contiguously — 2 KB for fp32 — so the 8 taps of a sample fall into one or two bricks instead of 8 cache
-// lines that are 16 KB (a row) and 64 MB (a slice) apart at 4096^3: far fewer sectors, DRAM pages and TLB
-// entries per sample. The index is a sum of three per-axis parts, computed once per axis value.
+// Raw taps of one sample: all eight loads are issued before anything consumes them (volatile keeps ptxas from
+// sinking the first interpolation between the loads, which cut the loads in flight per thread from 8 to 2-3 and
+// cost 13 % at 32 GiB per rank, where the march waits on HBM).
+template <int DTYPE> __device__ __forceinline__ uint32_t win_raw(const void* p) {
+    uint32_t v;
+    if (DTYPE == VKRT_U8) asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    else if (DTYPE == VKRT_F16) asm("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
+    else asm("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+template <int DTYPE> __device__ __forceinline__ float win_cvt(uint32_t v) {
+    if (DTYPE == VKRT_U8) return __uint_as_float(0x4B000000u | v) - 8388608.0f;
+    if (DTYPE == VKRT_F16) return __half2float(__ushort_as_half((unsigned short)v));
+    return __uint_as_float(v);
+}
+
+// Element index of window-local voxel (lx, ly, lz) as a sum of three per-axis parts (occupancy pass).
 __device__ __forceinline__ size_t part_x(const PartialArgs& A, int lx) { return A.bricked ? (size_t)(lx >> 3) * 512 + (lx & 7) : (size_t)lx; }
 __device__ __forceinline__ size_t part_y(const PartialArgs& A, int ly) {
     return A.bricked ? (size_t)(ly >> 3) * A.bnx * 512 + (size_t)(ly & 7) * 8 : (size_t)ly * A.nx;
@@ -41,20 +54,54 @@ __device__ __forceinline__ size_t part_z(const PartialArgs& A, int lz) {
     return A.bricked ? (size_t)(lz >> 3) * A.bny * A.bnx * 512 + (size_t)(lz & 7) * 64 : (size_t)lz * A.nx * A.ny;
 }
 
-// trilinear sample of the window array; taps clamp to the GLOBAL grid, then shift by the window origin
+template <int DTYPE> struct WinElem;
+template <> struct WinElem<VKRT_U8> { typedef uint8_t type; };
+template <> struct WinElem<VKRT_F16> { typedef unsigned short type; };
+template <> struct WinElem<VKRT_F32> { typedef float type; };
+
+// Trilinear sample of the window array; taps clamp to the GLOBAL grid, then shift by the window origin.
+//
+// Bricked windows (scalar data) store 8^3-voxel bricks contiguously — 2 KB for fp32 — so the 8 taps of a
+// sample fall into one or two bricks instead of 8 cache lines that are 16 KB (a row) and 64 MB (a slice)
+// apart at 4096^3: far fewer sectors, DRAM pages and TLB entries per sample.
+//
+// Addressing: ONE 64-bit element index for the low corner (xa, ya, za), plus three 32-bit strides to the
+// high tap of each axis (1 / 8 / 64 inside a brick, the jump to the neighbouring brick when the low tap sits
+// on the brick's last plane, 0 where the global clamp folds both taps onto one voxel). The other seven
+// addresses are 32-bit sums of those strides added to the corner pointer (one IMAD.WIDE each). The first
+// version built six 64-bit per-axis parts and four 64-bit row sums per sample; ncu showed that address
+// arithmetic as 29 % of the kernel's instructions on an ALU-bound kernel (profiles/r01_v3_prof_final_partial.md).
 template <int DTYPE> __device__ __forceinline__ float win_sample(const PartialArgs& A, float qx, float qy, float qz) {
     const float ux = __fsub_rn(qx, 0.5f), uy = __fsub_rn(qy, 0.5f), uz = __fsub_rn(qz, 0.5f);
     const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
     const float fx = __fsub_rn(ux, flx), fy = __fsub_rn(uy, fly), fz = __fsub_rn(uz, flz);
     const int x0 = (int)flx, y0 = (int)fly, z0 = (int)flz;
-    const size_t xa = part_x(A, min(max(x0, 0), A.gnx - 1) - A.wx), xb = part_x(A, min(max(x0 + 1, 0), A.gnx - 1) - A.wx);
-    const size_t ya = part_y(A, min(max(y0, 0), A.gny - 1) - A.wy), yb = part_y(A, min(max(y0 + 1, 0), A.gny - 1) - A.wy);
-    const size_t za = part_z(A, min(max(z0, 0), A.gnz - 1) - A.wz), zb = part_z(A, min(max(z0 + 1, 0), A.gnz - 1) - A.wz);
-    const size_t r00 = za + ya, r10 = za + yb, r01 = zb + ya, r11 = zb + yb;
-    const float c000 = win_load<DTYPE>(A.vol_a, r00 + xa), c100 = win_load<DTYPE>(A.vol_a, r00 + xb);
-    const float c010 = win_load<DTYPE>(A.vol_a, r10 + xa), c110 = win_load<DTYPE>(A.vol_a, r10 + xb);
-    const float c001 = win_load<DTYPE>(A.vol_a, r01 + xa), c101 = win_load<DTYPE>(A.vol_a, r01 + xb);
-    const float c011 = win_load<DTYPE>(A.vol_a, r11 + xa), c111 = win_load<DTYPE>(A.vol_a, r11 + xb);
+    const int xa = min(max(x0, 0), A.gnx - 1), ya = min(max(y0, 0), A.gny - 1), za = min(max(z0, 0), A.gnz - 1);
+    const bool mx = xa != min(max(x0 + 1, 0), A.gnx - 1), my = ya != min(max(y0 + 1, 0), A.gny - 1), mz = za != min(max(z0 + 1, 0), A.gnz - 1);
+    const uint32_t lx = (uint32_t)(xa - A.wx), ly = (uint32_t)(ya - A.wy), lz = (uint32_t)(za - A.wz);
+    size_t base;
+    uint32_t dx, dy, dz;
+    if (A.bricked) {
+        const uint32_t rowb = (uint32_t)A.bnx * 512u, slabb = (uint32_t)A.bny * rowb;  // elements per row / slab of bricks
+        const uint32_t brick = ((lz >> 3) * (uint32_t)A.bny + (ly >> 3)) * (uint32_t)A.bnx + (lx >> 3);
+        base = ((size_t)brick << 9) + (((lz & 7u) << 6) | ((ly & 7u) << 3) | (lx & 7u));
+        dx = mx ? ((lx & 7u) == 7u ? 512u - 7u : 1u) : 0u;
+        dy = my ? ((ly & 7u) == 7u ? rowb - 56u : 8u) : 0u;
+        dz = mz ? ((lz & 7u) == 7u ? slabb - 448u : 64u) : 0u;
+    } else {
+        base = ((size_t)lz * (uint32_t)A.ny + ly) * (uint32_t)A.nx + lx;
+        dx = mx ? 1u : 0u;
+        dy = my ? (uint32_t)A.nx : 0u;
+        dz = mz ? (uint32_t)A.nx * (uint32_t)A.ny : 0u;
+    }
+    const typename WinElem<DTYPE>::type* c = (const typename WinElem<DTYPE>::type*)A.vol_a + base;
+    const uint32_t dxy = dx + dy;
+    const typename WinElem<DTYPE>::type *p100 = c + dx, *p010 = c + dy, *p110 = c + dxy, *p001 = c + dz, *p101 = c + (dz + dx),
+                                        *p011 = c + (dz + dy), *p111 = c + (dz + dxy);
+    const uint32_t r000 = win_raw<DTYPE>(c), r100 = win_raw<DTYPE>(p100), r010 = win_raw<DTYPE>(p010), r110 = win_raw<DTYPE>(p110);
+    const uint32_t r001 = win_raw<DTYPE>(p001), r101 = win_raw<DTYPE>(p101), r011 = win_raw<DTYPE>(p011), r111 = win_raw<DTYPE>(p111);
+    const float c000 = win_cvt<DTYPE>(r000), c100 = win_cvt<DTYPE>(r100), c010 = win_cvt<DTYPE>(r010), c110 = win_cvt<DTYPE>(r110);
+    const float c001 = win_cvt<DTYPE>(r001), c101 = win_cvt<DTYPE>(r101), c011 = win_cvt<DTYPE>(r011), c111 = win_cvt<DTYPE>(r111);
     const float c00 = fmaf(fx, __fsub_rn(c100, c000), c000), c10 = fmaf(fx, __fsub_rn(c110, c010), c010);
     const float c01 = fmaf(fx, __fsub_rn(c101, c001), c001), c11 = fmaf(fx, __fsub_rn(c111, c011), c011);
     const float c0 = fmaf(fy, __fsub_rn(c10, c00), c00), c1 = fmaf(fy, __fsub_rn(c11, c01), c01);
@@ -106,7 +153,12 @@ __global__ void __launch_bounds__(256) partial_kernel(const __grid_constant__ Pa
         }
         float t = t0;
         if (te - 2.0f * dt <= tx + 2.0f * dt) {
-            const int n_pre = (int)fminf((te - t0) / dt - 2.0f, 1.0e9f);
+            // Each replayed addition rounds by <= ulp(t)/2 <= t1 * 2^-24, always the same way inside a binade, so
+            // after s steps the t sequence may run ahead of t0 + s*dt by s * drift steps (several steps at
+            // 4096^3, where a ray takes ~10^4 of them): keep that, doubled, plus 2 samples, in hand.
+            const float s_pre = (te - t0) / dt;
+            const float drift_per_step = (t1 * 5.9604645e-08f) / dt * 2.0f;
+            const int n_pre = (int)fminf(s_pre - fmaf(s_pre, drift_per_step, 2.0f), 1.0e9f);
             if (n_pre > 0) t = advance_t(t, dt, n_pre);
             const float t_stop = fminf(t1, tx + 2.0f * dt);
             const float dqx = dir.x * A.hx * dt, dqy = dir.y * A.hy * dt, dqz = dir.z * A.hz * dt;
