@@ -193,6 +193,23 @@ VKRT_API int vkrt_tile_table(int width, int height, int tile_size, VkrtOffset* o
  * box, singular matrix): then nothing is culled. */
 VKRT_API int vkrt_box_screen_bounds(const VkrtCameraUniform* cam, int width, int height, float rect[4], int* centre_row);
 
+/* Batched `single`: the cameras of n consecutive frames of a sweep (n consecutive `Demo::render` calls of the
+ * event loop, src/lib.rs:178-200; the recorder's frame sequence, src/lib.rs:132-140) rendered by ONE launch,
+ * grid.z = frame. One 1080p frame with a fifth of its pixels on the box cannot fill a B200 and its duration is
+ * bounded by the dependent march of its longest rays; a few frames per launch do fill it. Every frame is
+ * bit-identical to what vkrt_render produces for its camera. Frames land in context-owned batch buffers
+ * (vkrt_batch_frame_device_ptr / vkrt_readback_batch, valid until the next batch call). */
+#define VKRT_MAX_BATCH 8
+VKRT_API int vkrt_render_batch(VkrtContext* ctx, const VkrtCameraUniform* cams, int n, const VkrtUniform* un);
+VKRT_API void* vkrt_batch_frame_device_ptr(VkrtContext* ctx, int i); /* W*H rgba16f, frame i of the last vkrt_render_batch */
+VKRT_API int vkrt_readback_batch(VkrtContext* ctx, int i, uint16_t* rgba16f /* W*H*4 halfs */);
+/* n frames (any n) for a host consumer — the screenshot/recorder path (src/context/screenshot.rs:37-77,
+ * src/utils/recorder.rs:79-127) for a whole sweep: cameras in, presented RGBA8 frames out into host memory
+ * (n * W*H*4 bytes, frame i at offset i*W*H*4; page-locked memory keeps the copies asynchronous). Internally
+ * groups of `group` frames (<= VKRT_MAX_BATCH; 0 = default 4) go out as one launch each, and the raycast of a
+ * group overlaps present + D2H of the previous one. Blocks until every frame is in `rgba8`. */
+VKRT_API int vkrt_frames_host(VkrtContext* ctx, const VkrtCameraUniform* cams, int n, const VkrtUniform* un, uint8_t* rgba8, int group);
+
 /* Present — replaces the present pass (shaders/present.wgsl:23-35,111-119;
  * src/context/present_pipeline.rs:123-136): ACES + sRGB of the frame into a W x H RGBA8 buffer. */
 VKRT_API int vkrt_present(VkrtContext* ctx);

@@ -622,3 +622,47 @@ def test_all_empty_volume_with_skipping(rt, oracle, xor_cam):
         assert np.array_equal(ctx.readback_aux(), aux)
         check_images_hdr = np.abs(out[0].view(np.float16).astype(np.float32) - ref.view(np.float16).astype(np.float32)).max()
         assert check_images_hdr == 0.0
+
+
+@pytest.mark.parametrize("mode", [abi.MODE_M0, abi.MODE_M1])
+def test_batched_launch_equals_single_frames(rt, oracle, noise64, mode):
+    """vkrt_render_batch (grid.z = frame) and vkrt_frames_host (groups pipelined against present + D2H): every
+    frame bit-identical to the one vkrt_render / vkrt_frame_host produces for its camera; odd group sizes,
+    a last partial group, pageable and page-locked destinations."""
+    from vokselis_b200 import volumes
+
+    W, H = 320, 180
+    cams = [rt.Camera(3.0 - 0.2 * i, -0.5 + 0.1 * i, 1.0 + 0.7 * i, (0, 0, 0), W / H).get_proj_view_matrix() for i in range(11)]
+    with rt.Context(0, W, H) as ctx:
+        if mode == abi.MODE_M0:
+            ctx.upload_rgba16f(*noise64)
+            layout = abi.LAYOUT_TEXTURE
+        else:
+            ctx.upload_scalar(volumes.bonsai_standin_u8(64, seed=3, blobs=9))
+            layout = abi.LAYOUT_GATHER
+        q = rt.default_params(mode)
+        q.skip_empty, q.layout = 1, layout
+        ctx.set_params(q)
+        singles, singles8 = [], []
+        for cam in cams:
+            ctx.render(cam)
+            singles.append(ctx.readback())
+            singles8.append(ctx.frame_host(cam).copy())
+        assert len({s.tobytes() for s in singles}) == len(cams)  # the cameras really differ
+        for n in (1, 3, rt.MAX_BATCH):
+            ctx.render_batch(cams[:n])
+            for i in range(n):
+                assert np.array_equal(ctx.readback_batch(i), singles[i]), (n, i)
+        with pytest.raises(rt.VokselisError):
+            ctx.render_batch(cams[:rt.MAX_BATCH + 1])
+        for group in (0, 1, 3, 8):
+            got = ctx.frames_host(cams, group=group)
+            for i in range(len(cams)):
+                assert np.array_equal(got[i], singles8[i]), (group, i)
+        pin = rt.PinnedArray((len(cams), H, W, 4), np.uint8)
+        ctx.frames_host(cams, pin.array, group=4)
+        assert all(np.array_equal(pin.array[i], singles8[i]) for i in range(len(cams)))
+        pin.close()
+        # the single-frame API is untouched by the batch buffers
+        ctx.render(cams[2])
+        assert np.array_equal(ctx.readback(), singles[2])

@@ -57,6 +57,13 @@ struct VkrtContext {
     uint2* frame = nullptr;
     uint32_t* rgba8 = nullptr;
     uint32_t* rgba8_slot[2] = {nullptr, nullptr};  // device copies for the async host path
+    // batches (vkrt_render_batch / vkrt_frames_host): two groups of up to VKRT_MAX_BATCH frames each, so the copy
+    // stream can present + copy group j while the raycast of group j+1 runs
+    uint2* batch_frames[2] = {nullptr, nullptr};
+    uint32_t* batch_rgba8[2] = {nullptr, nullptr};
+    int batch_cap = 0;  // frames per group currently allocated
+    int batch_last_n = 0;
+    cudaEvent_t ev_group_ready[2] = {nullptr, nullptr}, ev_group_copied[2] = {nullptr, nullptr};
     uint8_t* host_slot[2] = {nullptr, nullptr};    // pinned
     uint32_t* aux = nullptr;
     unsigned long long* counters = nullptr;
@@ -141,9 +148,35 @@ void free_frame(VkrtContext* c) {
         c->rgba8_slot[i] = nullptr;
         c->host_slot[i] = nullptr;
     }
+    for (int i = 0; i < 2; ++i) {
+        if (c->batch_frames[i]) cudaFree(c->batch_frames[i]);
+        if (c->batch_rgba8[i]) cudaFree(c->batch_rgba8[i]);
+        c->batch_frames[i] = nullptr;
+        c->batch_rgba8[i] = nullptr;
+    }
+    c->batch_cap = 0;
+    c->batch_last_n = 0;
     c->frame = nullptr;
     c->rgba8 = nullptr;
     c->aux = nullptr;
+}
+// batch frame groups, allocated on first use (2 x frames x W x H x (8 + 4) bytes)
+int ensure_batch(VkrtContext* c, int frames) {
+    if (frames <= c->batch_cap) return VKRT_OK;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->copy_stream));
+    const size_t n = (size_t)c->W * c->H * frames;
+    for (int i = 0; i < 2; ++i) {
+        if (c->batch_frames[i]) cudaFree(c->batch_frames[i]);
+        if (c->batch_rgba8[i]) cudaFree(c->batch_rgba8[i]);
+        c->batch_frames[i] = nullptr;
+        c->batch_rgba8[i] = nullptr;
+        c->batch_cap = 0;
+        CK(cudaMalloc(&c->batch_frames[i], n * sizeof(uint2)));
+        CK(cudaMalloc(&c->batch_rgba8[i], n * 4));
+    }
+    c->batch_cap = frames;
+    return VKRT_OK;
 }
 int alloc_frame(VkrtContext* c, int W, int H) {
     free_frame(c);
@@ -339,9 +372,14 @@ void cull_rect(const float inv[16], int W, int H, float cull[4], int* centre_row
     if (cyc >= 0.0 && cyc <= (double)H - 1.0) *centre_row = (int)cyc;
 }
 
-int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, const VkrtOffset* offsets, int n, bool bracket = true) {
+// n_frames > 1 (with frames_out): the `single` entry for n_frames cameras in ONE launch, frame f stored at
+// frames_out + f*W*H (vkrt_render_batch / vkrt_frames_host); otherwise one camera into the context's frame.
+// rgba8_out: also store the presented RGBA8 pixels (fused present pass), n_frames * W*H.
+int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, const VkrtOffset* offsets, int n, bool bracket = true,
+              int n_frames = 1, uint2* frames_out = nullptr, uint32_t* rgba8_out = nullptr) {
     if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
     if (!cam || !un) return fail(VKRT_ERR_INVALID, "camera/uniform is NULL");
+    if (n_frames < 1 || n_frames > kMaxBatch) return fail(VKRT_ERR_INVALID, "batch size out of range");
     CK(cudaSetDevice(c->device));
     if (c->kind == VOL_NONE) return fail(VKRT_ERR_NO_VOLUME, "render before any volume upload/generate");
     if (c->windowed) return fail(VKRT_ERR_INVALID, "the resident volume is one brick of a partitioned grid: use vkrt_partial_*");
@@ -355,14 +393,17 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     const bool skip = P.skip_empty && !(P.mode == VKRT_MODE_M0 && P.clear_color[3] != 0.0f);
 
     RenderArgs A{};
-    memcpy(A.inv, cam->inv_proj, sizeof A.inv);
     A.W = c->W; A.H = c->H;
+    A.n_frames = n_frames;
     {
         static int use_cull = -1;  // VKRT_CULL=0 switches it off (A/B only)
         if (use_cull < 0) { const char* e = getenv("VKRT_CULL"); use_cull = e ? atoi(e) != 0 : 1; }
-        int centre_row;
-        cull_rect(A.inv, A.W, A.H, A.cull, &centre_row);
-        if (!use_cull) { A.cull[0] = A.cull[1] = -3.0e38f; A.cull[2] = A.cull[3] = 3.0e38f; }
+        for (int f = 0; f < n_frames; ++f) {
+            memcpy(A.inv[f], cam[f].inv_proj, sizeof A.inv[f]);
+            int centre_row;
+            cull_rect(A.inv[f], A.W, A.H, A.cull[f], &centre_row);
+            if (!use_cull) { A.cull[f][0] = A.cull[f][1] = -3.0e38f; A.cull[f][2] = A.cull[f][3] = 3.0e38f; }
+        }
     }
     A.n_tiles = 0; A.tile_size = P.tile_size; A.offsets = nullptr;
     if (offsets && n > 0) {
@@ -417,8 +458,11 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     A.dt_scale = P.dt_scale; A.dt_floor = P.dt_floor; A.alpha_threshold = P.alpha_threshold; A.initial_alpha = P.initial_alpha;
     memcpy(A.clear, P.clear_color, sizeof A.clear);
     A.m1_srgb = P.m1_srgb;
-    A.frame = c->frame;
+    A.frame = frames_out ? frames_out : c->frame;
+    A.rgba8 = rgba8_out;
     const bool dbg = P.count_samples != 0;
+    if (dbg && n_frames > 1) return fail(VKRT_ERR_INVALID, "params.count_samples needs single-frame renders (the counters are per frame)");
+    if (n_frames > 1 && (offsets && n > 0)) return fail(VKRT_ERR_INVALID, "a batch renders whole frames (`single`), not tiles");
     if (dbg && !c->aux) {
         CK(cudaMalloc(&c->aux, (size_t)c->W * c->H * 4));
         CK(cudaMemsetAsync(c->aux, 0, (size_t)c->W * c->H * 4, c->stream));
@@ -487,6 +531,8 @@ int vkrt_create(int device, int width, int height, VkrtContext** out_ctx) {
         for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
             e = cudaEventCreateWithFlags(&c->ev_slot_ready[i], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_slot_copied[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_group_ready[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_group_copied[i], cudaEventDisableTiming);
         }
         if (e != cudaSuccess) break;
         if ((e = cudaMalloc(&c->counters, 3 * sizeof(unsigned long long))) != cudaSuccess) break;
@@ -521,6 +567,8 @@ int vkrt_destroy(VkrtContext* c) {
     for (int i = 0; i < 2; ++i) {
         if (c->ev_slot_ready[i]) cudaEventDestroy(c->ev_slot_ready[i]);
         if (c->ev_slot_copied[i]) cudaEventDestroy(c->ev_slot_copied[i]);
+        if (c->ev_group_ready[i]) cudaEventDestroy(c->ev_group_ready[i]);
+        if (c->ev_group_copied[i]) cudaEventDestroy(c->ev_group_copied[i]);
     }
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -749,9 +797,8 @@ int vkrt_frame_host_async(VkrtContext* c, const VkrtCameraUniform* cam, const Vk
     }
     // the previous D2H out of this slot's device buffer must be done before we overwrite it
     CK(cudaStreamWaitEvent(c->stream, c->ev_slot_copied[slot], 0));
-    int rc = do_render(c, cam, un, nullptr, 0);
+    int rc = do_render(c, cam, un, nullptr, 0, true, 1, nullptr, c->rgba8_slot[slot]);  // present fused into the raycast epilogue
     if (rc) return rc;
-    CK(launch_present(c->frame, c->rgba8_slot[slot], c->W, c->H, c->stream));
     CK(cudaEventRecord(c->ev_slot_ready[slot], c->stream));
     CK(cudaStreamWaitEvent(c->copy_stream, c->ev_slot_ready[slot], 0));
     CK(cudaMemcpyAsync(c->host_slot[slot], c->rgba8_slot[slot], bytes, cudaMemcpyDeviceToHost, c->copy_stream));
@@ -801,9 +848,8 @@ int vkrt_frame_host(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUnif
     if (is_pinned_host(rgba8)) {
         // caller's buffer is page-locked (vkrt_alloc_host / cudaHostAlloc): DMA straight into it
         CK(cudaSetDevice(c->device));
-        int rc = do_render(c, cam, un, nullptr, 0);
+        int rc = do_render(c, cam, un, nullptr, 0, true, 1, nullptr, c->rgba8);  // present fused into the raycast epilogue
         if (rc) return rc;
-        CK(launch_present(c->frame, c->rgba8, c->W, c->H, c->stream));
         CK(cudaMemcpyAsync(rgba8, c->rgba8, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         return VKRT_OK;
@@ -811,6 +857,68 @@ int vkrt_frame_host(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUnif
     int rc = vkrt_frame_host_async(c, cam, un, 0);
     if (rc) return rc;
     return vkrt_frame_host_wait(c, 0, rgba8);
+}
+
+int vkrt_render_batch(VkrtContext* c, const VkrtCameraUniform* cams, int n, const VkrtUniform* un) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    if (!cams || n < 1 || n > VKRT_MAX_BATCH) return fail(VKRT_ERR_INVALID, "batch needs 1..VKRT_MAX_BATCH cameras");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_batch(c, n);
+    if (rc) return rc;
+    // group 0 may still be read by the copy stream of an earlier vkrt_frames_host
+    CK(cudaStreamWaitEvent(c->stream, c->ev_group_copied[0], 0));
+    rc = do_render(c, cams, un, nullptr, 0, true, n, c->batch_frames[0]);
+    if (rc) return rc;
+    c->batch_last_n = n;
+    return VKRT_OK;
+}
+
+void* vkrt_batch_frame_device_ptr(VkrtContext* c, int i) {
+    if (!c || i < 0 || i >= c->batch_last_n || !c->batch_frames[0]) return nullptr;
+    return c->batch_frames[0] + (size_t)i * c->W * c->H;
+}
+
+int vkrt_readback_batch(VkrtContext* c, int i, uint16_t* out) {
+    if (!c || !out) return fail(VKRT_ERR_INVALID, "NULL argument");
+    if (i < 0 || i >= c->batch_last_n || !c->batch_frames[0]) return fail(VKRT_ERR_INVALID, "no such frame in the last batch");
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->W * c->H;
+    CK(cudaMemcpyAsync(out, c->batch_frames[0] + (size_t)i * n, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_frames_host(VkrtContext* c, const VkrtCameraUniform* cams, int n, const VkrtUniform* un, uint8_t* rgba8, int group) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    if (!cams || !rgba8 || n < 1) return fail(VKRT_ERR_INVALID, "bad frames_host arguments");
+    if (group <= 0) group = 4;  // frames per launch: 3-4 fill a B200 at 1080p (profiles/r01_batch.md)
+    if (group > VKRT_MAX_BATCH) group = VKRT_MAX_BATCH;
+    CK(cudaSetDevice(c->device));
+    if (c->params.count_samples) {  // the counting kernel is per frame: no batching
+        for (int i = 0; i < n; ++i) {
+            int rc = vkrt_frame_host(c, cams + i, un, rgba8 + (size_t)i * c->W * c->H * 4);
+            if (rc) return rc;
+        }
+        return VKRT_OK;
+    }
+    int rc = ensure_batch(c, group);
+    if (rc) return rc;
+    const size_t px = (size_t)c->W * c->H;
+    // Software pipeline over groups of `group` frames, two device buffers: the raycast of group j+1 (context
+    // stream, ONE launch, present fused into its epilogue) overlaps the D2H of group j (copy stream).
+    for (int first = 0, j = 0; first < n; first += group, ++j) {
+        const int g = std::min(group, n - first), b = j & 1;
+        CK(cudaStreamWaitEvent(c->stream, c->ev_group_copied[b], 0));  // buffer b has left the device (group j-2)
+        rc = do_render(c, cams + first, un, nullptr, 0, false, g, c->batch_frames[b], c->batch_rgba8[b]);  // present fused
+        if (rc) return rc;
+        CK(cudaEventRecord(c->ev_group_ready[b], c->stream));
+        CK(cudaStreamWaitEvent(c->copy_stream, c->ev_group_ready[b], 0));
+        CK(cudaMemcpyAsync(rgba8 + (size_t)first * px * 4, c->batch_rgba8[b], (size_t)g * px * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        CK(cudaEventRecord(c->ev_group_copied[b], c->copy_stream));
+    }
+    c->batch_last_n = 0;  // the group buffers were recycled: nothing to read back through vkrt_readback_batch
+    CK(cudaStreamSynchronize(c->copy_stream));
+    return VKRT_OK;
 }
 
 void* vkrt_frame_device_ptr(VkrtContext* c) { return c ? c->frame : nullptr; }

@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
     float offx = 0.0f, offy = 0.0f;
     uint32_t px = gx, py = gy;
     bool valid = true;
+    const uint32_t fr = A.n_tiles > 0 ? 0u : blockIdx.z;  // `single`: grid.z = frame of the batch
     if (A.n_tiles > 0) {  // `tile` entry: coord = gid + offset; store at gid + u32(offset)
         const VkrtOffset o = A.offsets[blockIdx.z];
         offx = o.x;
@@ -190,8 +191,9 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
     float t0 = 0.0f, t1 = -1.0f;
     {
         const float cx = (float)gx + offx, cy = (float)gy + offy;
-        if (valid && cx >= A.cull[0] && cy >= A.cull[1] && cx <= A.cull[2] && cy <= A.cull[3]) {
-            gen_ray(A.inv, (float)gx, (float)gy, offx, offy, (float)A.W, (float)A.H, eye, dir);
+        const float* cull = A.cull[fr];
+        if (valid && cx >= cull[0] && cy >= cull[1] && cx <= cull[2] && cy <= cull[3]) {
+            gen_ray(A.inv[fr], (float)gx, (float)gy, offx, offy, (float)A.W, (float)A.H, eye, dir);
             intersect_box(eye, dir, t0, t1, inv_dir);
         }
     }
@@ -327,8 +329,10 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
     }
 
     if (valid) {
-        const size_t o = (size_t)py * A.W + px;
-        A.frame[o] = pack_rgba16f(col.r, col.g, col.b, 1.0f);
+        const size_t o = ((size_t)fr * A.H + py) * A.W + px;
+        const uint2 texel = pack_rgba16f(col.r, col.g, col.b, 1.0f);
+        A.frame[o] = texel;
+        if (A.rgba8) A.rgba8[o] = present_pixel(texel);  // fused present pass (host-frame paths): no second kernel, no re-read
         if (DBG && A.aux) A.aux[o] = hit ? (0x80000000u | iters) : 0u;
     }
     if (DBG && A.counters) {
@@ -373,7 +377,7 @@ cudaError_t launch_raycast(const RenderArgs& A, int mode, int layout, int dtype,
     if (A.n_tiles > 0) {
         grid = dim3((unsigned)((A.tile_size + bw - 1) / bw), (unsigned)((A.tile_size + bh - 1) / bh), (unsigned)A.n_tiles);
     } else {
-        grid = dim3((unsigned)((A.W + bw - 1) / bw), (unsigned)((A.H + bh - 1) / bh), 1);
+        grid = dim3((unsigned)((A.W + bw - 1) / bw), (unsigned)((A.H + bh - 1) / bh), (unsigned)(A.n_frames > 0 ? A.n_frames : 1));
     }
     if (mode == VKRT_MODE_M0) {
         switch (layout) {

@@ -9,10 +9,15 @@ namespace vkrt {
 
 // Everything one raycast launch reads; passed by value as a __grid_constant__ kernel parameter
 // (lives in the constant bank, no global loads for the camera or the parameters).
+constexpr int kMaxBatch = VKRT_MAX_BATCH;
 struct RenderArgs {
-    float inv[16];  // CameraUniform.inv_proj, column-major (src/camera.rs:10)
+    // One launch renders n_frames cameras (`single` entry: grid.z = frame; frame f is stored at frame + f*W*H).
+    // A 1080p frame with a fifth of its pixels on the box cannot fill 148 SMs, and its duration is bounded by
+    // the dependent march of its longest rays; several frames of a sweep in one grid do (measured 1.85x).
+    float inv[kMaxBatch][16];  // per frame: CameraUniform.inv_proj, column-major (src/camera.rs:10)
+    float cull[kMaxBatch][4];  // per frame: x0, y0, x1, y1 (ray coordinates = gid + offset): pixels outside cannot hit the box
+    int n_frames;
     int W, H;
-    float cull[4];  // x0, y0, x1, y1 (ray coordinates = gid + offset): pixels outside cannot hit the box
     // tiles: n_tiles == 0 -> `single`; else grid.z indexes `offsets` (device memory)
     const VkrtOffset* offsets;
     int n_tiles, tile_size;
@@ -36,7 +41,8 @@ struct RenderArgs {
     float clear[4];
     int m1_srgb;
     // outputs
-    uint2* frame;                  // W*H rgba16f
+    uint2* frame;                  // n_frames * W*H rgba16f
+    uint32_t* rgba8;               // optional, n_frames * W*H: the presented pixel (ACES + sRGB, present.wgsl) from the same thread
     uint32_t* aux;                 // optional W*H: bit31 hit, low bits iterations
     unsigned long long* counters;  // optional [3]: rays_hit, samples_reference, samples_fetched
 };

@@ -258,6 +258,27 @@ __device__ __forceinline__ float4 unpack_rgba16f(uint2 v) {
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// ---- present (shaders/present.wgsl:23-35,111-119): ACESFilm + linear_to_srgb + unorm8 pack --------------
+// Every multiply-add is spelled out so that the stand-alone present pass (present.cu) and the raycast kernel's
+// fused epilogue produce identical bytes.
+__device__ __forceinline__ float present_channel(float x) {
+    // ACESFilm; clamp via fminf/fmaxf so NaN -> 0 like the oracle
+    const float num = __fmul_rn(x, fmaf(2.51f, x, 0.03f)), den = fmaf(x, fmaf(2.43f, x, 0.59f), 0.14f);
+    const float v = fminf(fmaxf(__fdiv_rn(num, den), 0.0f), 1.0f);
+    // linear_to_srgb: selector = ceil(v - 0.0031308) in {0,1}; mix(under, over, selector)
+    const float sel = ceilf(__fsub_rn(v, 0.0031308f));
+    const float under = __fmul_rn(12.92f, v);
+    const float over = fmaf(1.055f, powf(v, 0.41666f), -0.055f);
+    return fmaf(over, sel, __fmul_rn(under, __fsub_rn(1.0f, sel)));
+}
+__device__ __forceinline__ uint32_t unorm8(float x) { return (uint32_t)__float2int_rn(__fmul_rn(__saturatef(x), 255.0f)); }
+// packed = one rgba16f texel of the frame (what textureStore wrote; the present pass samples that, not the fp32 colour)
+__device__ __forceinline__ uint32_t present_pixel(uint2 packed) {
+    const __half2 lo = *reinterpret_cast<const __half2*>(&packed.x), hi = *reinterpret_cast<const __half2*>(&packed.y);
+    const float2 a = __half22float2(lo), b = __half22float2(hi);
+    return unorm8(present_channel(a.x)) | unorm8(present_channel(a.y)) << 8 | unorm8(present_channel(b.x)) << 16 | unorm8(b.y) << 24;
+}
+
 // ---- bricked layout address --------------------------------------------------
 // M0 interleaved texel = 16 B (colour rgba16f + normal rgba16f). 2x2x2 texels fill one 128-B line;
 // 4x4x4 lines (8^3 voxels, 8 KB) form a brick; bricks are x-fastest. nbx, nby = bricks per axis.

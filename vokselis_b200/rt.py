@@ -25,7 +25,8 @@ _SO = Path(os.environ.get("VKRT_LIB") or (Path(__file__).resolve().parent / "lib
 EXPORTS = [
     "vkrt_create", "vkrt_destroy", "vkrt_resize", "vkrt_last_error", "vkrt_default_params", "vkrt_set_params",
     "vkrt_get_params", "vkrt_upload_rgba16f", "vkrt_upload_scalar", "vkrt_generate_xor", "vkrt_download_rgba16f",
-    "vkrt_render", "vkrt_render_tiles", "vkrt_tile_table", "vkrt_box_screen_bounds", "vkrt_present", "vkrt_readback", "vkrt_readback_rgba8",
+    "vkrt_render", "vkrt_render_tiles", "vkrt_tile_table", "vkrt_box_screen_bounds",
+    "vkrt_render_batch", "vkrt_batch_frame_device_ptr", "vkrt_readback_batch", "vkrt_frames_host", "vkrt_present", "vkrt_readback", "vkrt_readback_rgba8",
     "vkrt_readback_aux", "vkrt_sync", "vkrt_frame_host", "vkrt_frame_host_async", "vkrt_frame_host_wait",
     "vkrt_frame_host_slot_ptr", "vkrt_frame_device_ptr", "vkrt_frame_rgba8_device_ptr", "vkrt_stream", "vkrt_stats",
     "vkrt_reset_stats", "vkrt_timing_enable", "vkrt_timing_read", "vkrt_flush_l2", "vkrt_volume_info", "vkrt_camera_uniform", "vkrt_dispatch_optimal",
@@ -72,6 +73,10 @@ def lib() -> C.CDLL:
         "vkrt_render_tiles": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp, ci]),
         "vkrt_tile_table": (ci, [ci, ci, ci, vp, ci]),
         "vkrt_box_screen_bounds": (ci, [C.POINTER(CameraUniform), ci, ci, C.POINTER(C.c_float * 4), C.POINTER(ci)]),
+        "vkrt_render_batch": (ci, [vp, vp, ci, C.POINTER(Uniform)]),
+        "vkrt_batch_frame_device_ptr": (vp, [vp, ci]),
+        "vkrt_readback_batch": (ci, [vp, ci, vp]),
+        "vkrt_frames_host": (ci, [vp, vp, ci, C.POINTER(Uniform), vp, ci]),
         "vkrt_present": (ci, [vp]),
         "vkrt_readback": (ci, [vp, vp]),
         "vkrt_readback_rgba8": (ci, [vp, vp]),
@@ -137,6 +142,9 @@ def _vp(a):
 def dispatch_optimal(length: int, subgroup_size: int) -> int:
     """src/utils/mod.rs:15-18"""
     return int(lib().vkrt_dispatch_optimal(length, subgroup_size))
+
+
+MAX_BATCH = 8  # VKRT_MAX_BATCH
 
 
 def default_params(mode: int = abi.MODE_M0) -> Params:
@@ -339,6 +347,34 @@ class Context:
         if out is None:
             out = np.empty((self.height, self.width, 4), np.uint8)
         _check(lib().vkrt_frame_host(self._h, C.byref(cam), C.byref(un), _vp(out)))
+        return out
+
+    # -- batches: several cameras of a sweep in ONE launch (grid.z = frame) ---------------------------
+    @staticmethod
+    def _cam_array(cams):
+        arr = (CameraUniform * len(cams))()
+        for i, cam in enumerate(cams):
+            C.memmove(C.byref(arr, i * C.sizeof(CameraUniform)), C.byref(cam), C.sizeof(CameraUniform))
+        return arr
+
+    def render_batch(self, cams, uniform: Uniform | None = None):
+        """vkrt_render_batch: len(cams) <= MAX_BATCH frames into the context's batch buffers, one launch."""
+        un = uniform if uniform is not None else self.global_uniform
+        arr = self._cam_array(cams)
+        _check(lib().vkrt_render_batch(self._h, C.cast(arr, C.c_void_p), len(cams), C.byref(un)))
+
+    def readback_batch(self, i: int) -> np.ndarray:
+        out = np.empty((self.height, self.width, 4), np.uint16)
+        _check(lib().vkrt_readback_batch(self._h, i, _vp(out)))
+        return out
+
+    def frames_host(self, cams, out: np.ndarray | None = None, group: int = 0, uniform: Uniform | None = None) -> np.ndarray:
+        """vkrt_frames_host: len(cams) presented RGBA8 frames into host memory [n, H, W, 4], pipelined in groups."""
+        un = uniform if uniform is not None else self.global_uniform
+        if out is None:
+            out = np.empty((len(cams), self.height, self.width, 4), np.uint8)
+        arr = self._cam_array(cams)
+        _check(lib().vkrt_frames_host(self._h, C.cast(arr, C.c_void_p), len(cams), C.byref(un), _vp(out), group))
         return out
 
     def frame_host_async(self, cam: CameraUniform, slot: int, uniform: Uniform | None = None):
