@@ -5,9 +5,12 @@ Workload (BASELINE.json configs[1]): the `xor` procedural volume, 256^3 uint8, r
 over an orbit camera sweep of 360 frames (yaw_i = 1 + 2*pi*i/360, pitch -0.5, zoom 3, the xor
 example's camera, examples/xor/main.rs:273-279) in mode M1 (scalar volume, trilinear, `vertigo`
 transfer function, early ray termination, exact empty-space skipping). One STEP = one frame of the
-orbit. `value` = frames/s with the volume resident in HBM, timed per frame with CUDA events on the
-context's own stream, L2 flushed (a 256 MiB write) between timed frames. `e2e` = the same metric
-through the C ABI with HOST buffers (camera in, presented RGBA8 frame out into pinned host memory).
+orbit; a LAUNCH renders --batch (default 8) consecutive frames of the sweep (grid.z = frame), because one
+1080p frame with a fifth of its pixels on the box cannot fill a B200 (the one-frame-per-launch figure is
+reported beside it as `single_frame_per_launch`). `value` = frames/s with the volume resident in HBM,
+timed per launch with CUDA events on the context's own stream, L2 flushed (a 256 MiB write) between
+timed launches. `e2e` = the same metric through the C ABI with HOST buffers (vkrt_frames_host: cameras in,
+presented RGBA8 frames out into pinned host memory).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
@@ -274,107 +277,135 @@ def run_gpu(args):
         samples_fetched = st.samples_fetched / len(probe)
         ctx.set_params(p)
 
+    B = max(1, min(args.batch, rt.MAX_BATCH))  # frames per launch (grid.z = frame)
+    L = (K + B - 1) // B                        # launches per timed pass
+
+    def chunk(i0):  # cameras of the launch that starts at step i0 (the orbit wraps)
+        return [cams[(Wm + i0 + k) % ORBIT] for k in range(min(B, K - i0))]
+
     if world > 1:
         from vokselis_b200 import sortfirst
 
-        # 1080p frames take a fraction of a millisecond on one GPU: deal whole frames round-robin
-        # ("frames" granularity); every frame still lands in rank 0's ring by peer stores.
-        group = sortfirst.SortFirstGroup(ctx, rank, world, granularity=args.granularity, tile=120)
+        # 1080p frames take a fraction of a millisecond on one GPU: deal whole frames — groups of B consecutive
+        # frames, one launch per group — round-robin; every frame still lands in rank 0's ring by peer stores.
+        group = sortfirst.SortFirstGroup(ctx, rank, world, granularity=args.granularity, tile=120, batch=B if args.granularity == "frames" else 1)
+        GB = group.batch
 
-        def render(cam):
+        def launch(i0, flush):
             f = group.frame
-            if group.granularity == "tiles" or sortfirst.frame_owner(f, world) == rank:
-                if flushing[0]:
-                    ctx.flush_l2()
-            group.render(cam)
+            mine = group.granularity == "tiles" or sortfirst.frame_owner(f, world, GB) == rank
+            if flush and mine:
+                ctx.flush_l2()
+            if group.granularity == "tiles":
+                group.render(cams[(Wm + i0) % ORBIT])
+            else:
+                group.render_batch(chunk(i0) if GB > 1 else [cams[(Wm + i0) % ORBIT]])
+        step_stride = GB if group.granularity == "frames" else 1
     else:
         group = None
 
-        def render(cam):
-            if flushing[0]:
+        def launch(i0, flush):
+            if flush:
                 ctx.flush_l2()
-            ctx.render(cam)
-    flushing = [True]
+            ctx.render_batch(chunk(i0))
+        step_stride = B
 
-    # ---- timed: device time per frame, L2 flushed between frames -------------------------------
+    # ---- timed: device time per launch (CUDA events on the context's stream), L2 flushed between launches -----
     ctx.timing_enable(max(K, 1))
-    for i in range(Wm):
-        render(cams[i % ORBIT])
+    for i in range(0, max(Wm, step_stride), step_stride):
+        launch(i % max(K, 1), True)
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
 
-    def timed_pass():
-        """K steps between barriers; returns (per-frame device ms of the frames THIS rank rendered, wall s)."""
+    def timed_pass(flush):
+        """K steps (frames) between barriers; returns (device ms of the launches THIS rank issued, wall s)."""
         first = group.frame if group is not None else 0
         barrier()
         t0 = time.perf_counter()
-        for i in range(K):
-            render(cams[(Wm + i) % ORBIT])
+        for i0 in range(0, K, step_stride):
+            launch(i0, flush)
         barrier()
         wall = time.perf_counter() - t0
-        mine = K if group is None else group.my_frames(first, K)
+        if group is None:
+            mine = len(range(0, K, step_stride))
+        elif group.granularity == "tiles":
+            mine = K
+        else:
+            mine = group.my_launches(first, group.frame - first)
         return (ctx.timing_read(mine).astype(np.float64) if mine > 0 else np.zeros(0)), wall
 
     def whole_job_ms(ms):
-        total = float(ms.sum())  # this rank's busy device time (its frames: kernel + peer stores + arrival signal)
+        total = float(ms.sum())  # this rank's busy device time (its launches: kernel + peer stores + arrival signals)
         if world > 1:
             t = torch.tensor([total], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             total = float(t.item())
         return total
 
-    frame_ms, t_wall = timed_pass()
-    total_ms = whole_job_ms(frame_ms)
+    launch_ms, t_wall = timed_pass(True)
+    total_ms = whole_job_ms(launch_ms)
     fps = K / (total_ms * 1e-3)
     # warm-L2 variant (steady-state orbit, no flush), device-timed the same way
-    flushing[0] = False
-    warm_ms, t_wall_warm = timed_pass()
+    warm_ms, t_wall_warm = timed_pass(False)
     warm_total_ms = whole_job_ms(warm_ms)
-    flushing[0] = True
+
+    # ---- one frame per launch (latency of a single frame), N = 1 only ---------------------------------------
+    single = None
+    if world == 1:
+        n1 = min(K, 120)
+        ctx.timing_enable(n1)
+        for i in range(n1):
+            ctx.flush_l2()
+            ctx.render(cams[(Wm + i) % ORBIT])
+        s_ms = ctx.timing_read(n1).astype(np.float64)
+        single = {"ms_per_frame": float(s_ms.mean()), "frames_per_s": 1e3 / float(s_ms.mean()),
+                  "p10_p50_p90_ms": [float(np.percentile(s_ms, q)) for q in (10, 50, 90)],
+                  "note": "vkrt_render, one frame per launch, L2 flushed between frames: a 1080p frame with a fifth of its pixels on the box "
+                          "does not fill 148 SMs and is bounded by the dependent march of its longest rays"}
 
     # ---- e2e through the C ABI with host buffers -----------------------------------------------
     e2e = None
     if world == 1:
-        pinned = rt.PinnedArray((H, W, 4), np.uint8)  # result buffer in page-locked host memory
+        # the call a user of a sweep makes: vkrt_frames_host — cameras in, presented RGBA8 frames out in page-locked host memory;
+        # groups of B frames per launch, present fused into the raycast epilogue, D2H of a group overlapping the next raycast
+        PER_CALL = 24
+        pinned = rt.PinnedArray((PER_CALL, H, W, 4), np.uint8)
         out = pinned.array
-        for i in range(min(Wm, 5)):
-            ctx.frame_host(cams[i], out)
-        tot = 0.0
-        for i in range(K):
+        ctx.frames_host([cams[i % ORBIT] for i in range(PER_CALL)], out, group=min(B, 4))
+        tot, done = 0.0, 0
+        while done < K:
+            n = min(PER_CALL, K - done)
+            cs = [cams[(Wm + done + k) % ORBIT] for k in range(n)]
             ctx.flush_l2()
             ctx.sync()
             t0 = time.perf_counter()
-            ctx.frame_host(cams[(Wm + i) % ORBIT], out)  # camera H2D (kernel args) -> raycast -> present -> RGBA8 D2H, blocking
+            ctx.frames_host(cs, out[:n], group=min(B, 4))  # blocking: returns when the n frames are in host memory
             tot += time.perf_counter() - t0
-        e2e_blocking = K / tot
-
-        def pipelined(flush: bool) -> float:
-            """Two pinned slots: the D2H of frame i overlaps the raycast of frame i+1. Wall clock over K frames."""
+            done += n
+        e2e_frames = K / tot
+        pinned.close()
+        # one frame per call (vkrt_frame_host, blocking), for comparison
+        pinned1 = rt.PinnedArray((H, W, 4), np.uint8)
+        n1 = min(K, 120)
+        for i in range(3):
+            ctx.frame_host(cams[i], pinned1.array)
+        tot1 = 0.0
+        for i in range(n1):
+            ctx.flush_l2()
             ctx.sync()
             t0 = time.perf_counter()
-            for i in range(K):
-                s = i & 1
-                if i >= 2:
-                    ctx.frame_host_wait(s, None)  # pixels are in the context's pinned slot (vkrt_frame_host_slot_ptr)
-                if flush:
-                    ctx.flush_l2()
-                ctx.frame_host_async(cams[(Wm + i) % ORBIT], s)
-            for i in range(max(K - 2, 0), K):
-                ctx.frame_host_wait(i & 1, None)
-            return K / (time.perf_counter() - t0)
-
-        e2e_pipe_flush = pipelined(True)
-        e2e_pipe_warm = pipelined(False)
-        e2e = {"value": e2e_blocking, "unit": "frames/s", "h2d_bytes_per_step": 144 + 48, "d2h_bytes_per_step": W * H * 4,
-               "how": "vkrt_frame_host per frame, blocking: camera in (kernel arguments), raycast, present, RGBA8 D2H into a pinned host "
-                      "buffer; wall clock per frame, L2 flushed before each frame (flush untimed)",
-               "pipelined_two_slots_flush_timed": e2e_pipe_flush, "pipelined_two_slots_warm_l2": e2e_pipe_warm,
-               "note": "pipelined = vkrt_frame_host_async/_wait, the D2H of frame i overlaps the raycast of frame i+1; with the 256 MiB flush "
-                       "inside the loop the flush competes with the copy engine, so the blocking figure is the headline"}
-        out = None
-        pinned.close()
+            ctx.frame_host(cams[(Wm + i) % ORBIT], pinned1.array)
+            tot1 += time.perf_counter() - t0
+        pinned1.close()
+        e2e = {"value": e2e_frames, "unit": "frames/s", "h2d_bytes_per_step": 144 + 48, "d2h_bytes_per_step": W * H * 4,
+               "how": f"vkrt_frames_host, {PER_CALL} frames per blocking call into page-locked host memory: cameras in (kernel arguments), "
+                      f"groups of {min(B, 4)} frames per launch with the present pass fused into the raycast epilogue, RGBA8 D2H of a group overlapping "
+                      "the raycast of the next; wall clock per call, L2 flushed before each call (flush untimed)",
+               "single_frame_blocking": n1 / tot1,
+               "note": "single_frame_blocking = vkrt_frame_host, one frame per call (raycast + fused present + D2H, nothing overlapped). "
+                       "The PCIe floor for 8.3 MB of RGBA8 per frame is ~0.154 ms (54 GB/s measured) = 6,500 frames/s"}
     else:
         e2e = group.e2e(cams, K, Wm)
 
@@ -398,13 +429,14 @@ def run_gpu(args):
         group.close()
     if rank == 0:
         ms = total_ms / K
+        frames_per_launch = step_stride
         # Roofline of the dominant kernel, raycast_kernel<M1, GATHER, SKIP>.
         # Algorithmic bytes per ray-sample: 8 taps x 1 B; units per launch = the samples the
         # kernel actually fetches for one frame. The 16 MiB volume is L1/L2-resident, so the texture path
         # (two tld4 gathers per sample) is the binding memory resource, not HBM; both are reported.
-        kernel_ms = float(frame_ms.mean())
+        kernel_ms = float(launch_ms.mean())  # average launch duration of the dominant kernel (CUDA events, context stream)
         micro = peaks.get("micro", {})
-        alg_bytes = samples_fetched * 8.0
+        alg_bytes = samples_fetched * 8.0 * frames_per_launch
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         tld4_peak = micro.get("tld4_a2d_u8_F16_ginstr_s")  # G tld4/s; 4 B of texels each -> GB/s of texel bytes = 4x
         l1_peak = 4.0 * tld4_peak if tld4_peak else None
@@ -415,7 +447,7 @@ def run_gpu(args):
                 traffic = json.loads(tfile.read_text()).get("raycast_m1_gather_u8_skip_dram_bytes_per_launch")
             except Exception:
                 pass
-        hbm_bytes = min(NVOL ** 3, alg_bytes) + W * H * 8.0
+        hbm_bytes = min(NVOL ** 3, alg_bytes) + frames_per_launch * W * H * 8.0
         roofline = {
             "kernel": "raycast_kernel<M1, GATHER, SKIP>", "bound": "tex",
             "achieved": achieved, "peak": l1_peak, "unit": "GB/s", "frac": (achieved / l1_peak) if l1_peak else None, "traffic": traffic,
@@ -424,23 +456,26 @@ def run_gpu(args):
             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
             "hbm": {"bound": "hbm", "achieved": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["hbm_source"],
-                    "compulsory_bytes_per_launch": hbm_bytes, "note": "volume (16 MiB) + frame (W*H*8 B); far below HBM peak by construction"},
-            "note": "with exact empty-space skipping most of the kernel's time is traversal, not fetching; see DESIGN.md §7 for the "
-                    "no-skip figures",
+                    "compulsory_bytes_per_launch": hbm_bytes, "note": "volume (16 MiB, read once per launch) + frames (W*H*8 B each); far below HBM peak by construction"},
+            "frames_per_launch": frames_per_launch,
+            "note": "achieved = samples actually fetched x 8 B of taps / launch time; with exact empty-space skipping a large share of the kernel's "
+                    "time is traversal (instruction issue), not fetching; see DESIGN.md §7 for the no-skip figures",
         }
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "volume": "xor bit pattern (shaders/xor.wgsl:46-53) quantised to u8, 16 MiB", "resolution": [W, H],
-                       "l2": "flushed between timed frames (write of a 256 MiB buffer, untimed)", "layout": "GATHER (two tld4 per sample on a layered texture, fp32 weights: parity path)",
+                       "l2": "flushed between timed launches (write of a 256 MiB buffer, untimed)", "layout": "GATHER (two tld4 per sample on a layered texture, fp32 weights: parity path)",
+                       "frames_per_launch": frames_per_launch, "step": "one frame of the orbit; a launch renders frames_per_launch consecutive frames (grid.z = frame), every frame bit-identical to a single-frame launch",
                        "parallelism": "single GPU" if world == 1 else
-                       f"sort-first over {world} GPUs ({args.granularity} dealt round-robin), volume replicated, kernels store pixels into rank 0's frame ring over NVLink"},
+                       f"sort-first over {world} GPUs ({args.granularity} dealt round-robin in groups of {frames_per_launch}), volume replicated, kernels store pixels into rank 0's frame ring over NVLink"},
             "ray_samples_per_s": samples_ref * fps, "fetched_samples_per_s": samples_fetched * fps,
             "samples_per_frame": {"reference": samples_ref, "fetched": samples_fetched},
             "ms_per_step_warm_l2": warm_total_ms / K, "fps_warm_l2": K / (warm_total_ms * 1e-3),
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / K, "wall_ms_per_step_warm_l2": 1e3 * t_wall_warm / K,
-            "frame_ms_p10_p50_p90": [float(np.percentile(frame_ms, q)) for q in (10, 50, 90)],
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K, "clocks": clock_info,
+            "launch_ms_p10_p50_p90": [float(np.percentile(launch_ms, q)) for q in (10, 50, 90)] if len(launch_ms) else None,
+            "single_frame_per_launch": single,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": len(range(0, K, step_stride)), "clocks": clock_info,
             "sortfirst_wait_timeouts": (timeouts if group is not None else None),
             "m0_reference_exact": m0,
         }
@@ -459,6 +494,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
     ap.add_argument("--granularity", default="frames", choices=["frames", "tiles"], help="sort-first granularity for N > 1")
+    ap.add_argument("--batch", type=int, default=8, help="frames per launch (grid.z = frame), 1..8")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -52,6 +52,29 @@ def main():
                 ok = ok and to == 0
                 print(f"mode {mode} {gran}/{slots}: device-side wait timeouts = {to}", flush=True)
             group.close()
+        # batched groups of 3 frames dealt round-robin, one launch per group, straight into consecutive ring slots
+        group = sortfirst.SortFirstGroup(ctx, rank, world, granularity="frames", batch=3)
+        seq = cams * 4  # 20 frames: six full groups and a padded one, slots reused several times
+        done = 0
+        for g in range(0, len(seq), 3):
+            chunk = seq[g:g + 3]
+            f = group.submit_batch(chunk)
+            if rank == 0:
+                for k in range(3):
+                    group.wait(f + k)
+                    got = ctx.readback()
+                    group.consume(f + k)
+                    if k < len(chunk):
+                        same = np.array_equal(got, refs[(g + k) % len(cams)])
+                        ok = ok and same
+                        done += 1
+                        if not same:
+                            print(f"mode {mode} frames/batch3 frame {g + k}: MISMATCH", flush=True)
+        if rank == 0:
+            to = ctx.sortfirst_timeouts()
+            ok = ok and to == 0
+            print(f"mode {mode} frames/batch3: {done} frames {'bit-exact' if ok else 'FAILED'}, device-side wait timeouts = {to}", flush=True)
+        group.close()
         ctx.close()
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)

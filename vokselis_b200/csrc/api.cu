@@ -1103,6 +1103,32 @@ int vkrt_sortfirst_render(VkrtContext* c, const VkrtCameraUniform* cam, const Vk
     return VKRT_OK;
 }
 
+int vkrt_sortfirst_render_batch(VkrtContext* c, const VkrtCameraUniform* cams, int n_frames, const VkrtUniform* un, uint64_t first_frame) {
+    if (!c || !c->sf_base) return fail(VKRT_ERR_INVALID, "context is not in a sort-first group");
+    if (!cams || n_frames < 1 || n_frames > VKRT_MAX_BATCH) return fail(VKRT_ERR_INVALID, "batch needs 1..VKRT_MAX_BATCH cameras");
+    const int slot0 = (int)(first_frame % (uint64_t)c->sf_slots);
+    if (slot0 + n_frames > c->sf_slots) return fail(VKRT_ERR_INVALID, "a batch must occupy consecutive ring slots (slots % batch == 0, first_frame % batch == 0)");
+    CK(cudaSetDevice(c->device));
+    cudaEvent_t eb = nullptr, ee = nullptr;
+    if (!c->ring_begin.empty()) {
+        eb = c->ring_begin[c->ring_next];
+        ee = c->ring_end[c->ring_next];
+        c->ring_next = (c->ring_next + 1) % c->ring_begin.size();
+        if (c->ring_count < c->ring_begin.size()) ++c->ring_count;
+    }
+    // slot reuse: the frame that used the LAST of these slots before must have been consumed (frames are consumed in order)
+    const uint64_t last = first_frame + (uint64_t)n_frames - 1;
+    if (last >= (uint64_t)c->sf_slots)
+        CK(launch_flag_wait(sf_consumed(c), last - (uint64_t)c->sf_slots + 1, sf_timeouts(c), c->stream));
+    if (eb) CK(cudaEventRecord(eb, c->stream));
+    // ONE launch, grid.z = frame: frame f of the batch is stored at slot0 + f (root: local memory; peers: rank 0's, over NVLink)
+    int rc = do_render(c, cams, un, nullptr, 0, false, n_frames, sf_slot(c, slot0));
+    if (rc) return rc;
+    for (int f = 0; f < n_frames; ++f) CK(launch_flag_add(sf_arrive(c, slot0 + f), 1ull, c->stream));
+    if (ee) CK(cudaEventRecord(ee, c->stream));
+    return VKRT_OK;
+}
+
 int vkrt_sortfirst_wait(VkrtContext* c, uint64_t frame_index, uint64_t arrivals_target) {
     if (!c || !c->sf_base || c->sf_rank != 0) return fail(VKRT_ERR_INVALID, "only the root waits for frames");
     CK(cudaSetDevice(c->device));

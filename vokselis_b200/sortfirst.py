@@ -12,6 +12,9 @@ Two granularities of the same scheme:
   * "frames" — whole frames are dealt round-robin (tile = the frame). For frames that one GPU
                renders in a fraction of a millisecond, splitting them only adds tail effects; dealing
                frames keeps every GPU busy and rank 0 still receives every frame, in order.
+               With batch > 1, GROUPS of `batch` consecutive frames are dealt round-robin and a rank renders
+               its group in ONE launch (grid.z = frame) into consecutive ring slots: one 1080p frame does not
+               fill a B200 (profiles/r01_batch.md), a few do.
 """
 from __future__ import annotations
 
@@ -26,20 +29,25 @@ def partition_tiles(width: int, height: int, tile: int, rank: int, world: int) -
     return rt.sortfirst_partition(width, height, tile, rank, world)
 
 
-def frame_owner(frame_index: int, world: int) -> int:
-    """'frames' granularity: which rank renders frame f."""
-    return frame_index % world
+def frame_owner(frame_index: int, world: int, batch: int = 1) -> int:
+    """'frames' granularity: which rank renders frame f (groups of `batch` consecutive frames, round-robin)."""
+    return (frame_index // batch) % world
 
 
 class SortFirstGroup:
     def __init__(self, ctx: rt.Context, rank: int, world: int, granularity: str = "tiles", tile: int = 120, slots: int | None = None,
-                 dist=None):
+                 dist=None, batch: int = 1):
         if dist is None:
             import torch.distributed as dist  # noqa: PLC0415
         if granularity not in ("tiles", "frames"):
             raise ValueError(granularity)
         self.ctx, self.rank, self.world, self.dist, self.granularity = ctx, rank, world, dist, granularity
-        self.slots = slots if slots is not None else (2 if granularity == "tiles" else 2 * world)
+        self.batch = batch if granularity == "frames" else 1
+        if not 1 <= self.batch <= rt.MAX_BATCH:
+            raise ValueError(f"batch must be 1..{rt.MAX_BATCH}")
+        self.slots = slots if slots is not None else (2 if granularity == "tiles" else 2 * world * self.batch)
+        if self.slots % self.batch:
+            raise ValueError("slots must be a multiple of batch")
         self.tiles = None
         if granularity == "tiles":
             p = ctx.get_params()
@@ -67,8 +75,31 @@ class SortFirstGroup:
         self.frame += 1
         if self.granularity == "tiles":
             self.ctx.sortfirst_render(cam, self.tiles, f)
+        elif self.batch > 1:
+            raise RuntimeError("with batch > 1 use submit_batch")
         elif frame_owner(f, self.world) == self.rank:
             self.ctx.sortfirst_render(cam, None, f)
+        return f
+
+    def submit_batch(self, cams) -> int:
+        """'frames' granularity with batch > 1: every rank calls this once per group of len(cams) <= batch
+        consecutive frames, in the same order; the owning rank renders the group in one launch. Returns the
+        index of the group's first frame."""
+        assert self.granularity == "frames" and 1 <= len(cams) <= self.batch and self.frame % self.batch == 0
+        cams = list(cams) + [cams[-1]] * (self.batch - len(cams))  # a short last group is padded: every slot gets its arrival
+        f = self.frame
+        self.frame += self.batch
+        if frame_owner(f, self.world, self.batch) == self.rank:
+            self.ctx.sortfirst_render_batch(cams, f)
+        return f
+
+    def render_batch(self, cams, present: bool = False) -> int:
+        """submit_batch + (root) wait + consume of every frame of the group, in order. Asynchronous."""
+        f = self.submit_batch(cams)
+        if self.rank == 0:
+            for k in range(self.batch):
+                self.wait(f + k)
+                self.consume(f + k, present)
         return f
 
     def wait(self, f: int):
@@ -99,7 +130,11 @@ class SortFirstGroup:
     def my_frames(self, first: int, count: int) -> int:
         if self.granularity == "tiles":
             return count
-        return sum(1 for f in range(first, first + count) if frame_owner(f, self.world) == self.rank)
+        return sum(1 for f in range(first, first + count) if frame_owner(f, self.world, self.batch) == self.rank)
+
+    def my_launches(self, first: int, count: int) -> int:
+        """Launches this rank issues for frames [first, first+count) ('frames' granularity, groups of `batch`)."""
+        return sum(1 for f in range(first, first + count, self.batch) if frame_owner(f, self.world, self.batch) == self.rank)
 
     def e2e(self, cams, K: int, warmup: int) -> dict:
         """End to end on the root, pipelined: every rank submits its share; the root waits for each frame
@@ -112,16 +147,21 @@ class SortFirstGroup:
         ctx.sync()
         dist.barrier()
         t0 = time.perf_counter()
-        for i in range(K):
+        B = self.batch
+        for i in range(0, K, B):
             f_next = self.frame
-            if self.granularity == "tiles" or frame_owner(f_next, self.world) == self.rank:
+            if self.granularity == "tiles" or frame_owner(f_next, self.world, B) == self.rank:
                 ctx.flush_l2()
-            f = self.submit(cams[(warmup + i) % len(cams)])
+            if B > 1:
+                f = self.submit_batch([cams[(warmup + i + k) % len(cams)] for k in range(min(B, K - i))])
+            else:
+                f = self.submit(cams[(warmup + i) % len(cams)])
             if self.rank == 0:
-                self.wait(f)
-                ctx.present()
-                ctx.readback_rgba8(out)
-                self.consume(f)
+                for k in range(B):
+                    self.wait(f + k)
+                    ctx.present()
+                    ctx.readback_rgba8(out)
+                    self.consume(f + k)
         ctx.sync()
         tot = time.perf_counter() - t0
         dist.barrier()
