@@ -444,7 +444,8 @@ def run_gpu(args):
         tfile = ROOT / "profiles" / "traffic_r01.json"
         if tfile.exists():
             try:
-                traffic = json.loads(tfile.read_text()).get("raycast_m1_gather_u8_skip_dram_bytes_per_launch")
+                tj = json.loads(tfile.read_text())
+                traffic = tj.get("raycast_m1_gather_u8_skip_batch8_dram_bytes_per_launch") if frames_per_launch == 8 else None
             except Exception:
                 pass
         hbm_bytes = min(NVOL ** 3, alg_bytes) + frames_per_launch * W * H * 8.0

@@ -218,6 +218,9 @@ VKRT_API int vkrt_present(VkrtContext* ctx);
  * Both block until the stream is idle. Rows are top-first, tightly packed. */
 VKRT_API int vkrt_readback(VkrtContext* ctx, uint16_t* rgba16f /* W*H*4 halfs */);
 VKRT_API int vkrt_readback_rgba8(VkrtContext* ctx, uint8_t* rgba8 /* W*H*4 bytes */);
+/* Enqueue only (page-locked destination); the pixels are there after vkrt_sync. Lets a consumer loop keep the
+ * stream busy instead of blocking once per frame. */
+VKRT_API int vkrt_readback_rgba8_async(VkrtContext* ctx, uint8_t* rgba8 /* W*H*4 bytes, page-locked */);
 VKRT_API int vkrt_sync(VkrtContext* ctx);
 /* Validation output (no reference counterpart; the reference cannot report it): after a render with
  * params.count_samples = 1, one u32 per pixel: bit 31 = the ray entered the box (t0 < t1,

@@ -768,6 +768,13 @@ int vkrt_readback_rgba8(VkrtContext* c, uint8_t* out) {
     return VKRT_OK;
 }
 
+int vkrt_readback_rgba8_async(VkrtContext* c, uint8_t* out) {
+    if (!c || !out) return fail(VKRT_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, c->rgba8, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream));
+    return VKRT_OK;
+}
+
 int vkrt_readback_aux(VkrtContext* c, uint32_t* out) {
     if (!c || !out) return fail(VKRT_ERR_INVALID, "NULL argument");
     if (!c->aux) return fail(VKRT_ERR_INVALID, "no aux buffer: render with params.count_samples = 1 first");

@@ -26,7 +26,7 @@ EXPORTS = [
     "vkrt_create", "vkrt_destroy", "vkrt_resize", "vkrt_last_error", "vkrt_default_params", "vkrt_set_params",
     "vkrt_get_params", "vkrt_upload_rgba16f", "vkrt_upload_scalar", "vkrt_generate_xor", "vkrt_download_rgba16f",
     "vkrt_render", "vkrt_render_tiles", "vkrt_tile_table", "vkrt_box_screen_bounds",
-    "vkrt_render_batch", "vkrt_batch_frame_device_ptr", "vkrt_readback_batch", "vkrt_frames_host", "vkrt_present", "vkrt_readback", "vkrt_readback_rgba8",
+    "vkrt_render_batch", "vkrt_batch_frame_device_ptr", "vkrt_readback_batch", "vkrt_frames_host", "vkrt_present", "vkrt_readback", "vkrt_readback_rgba8", "vkrt_readback_rgba8_async",
     "vkrt_readback_aux", "vkrt_sync", "vkrt_frame_host", "vkrt_frame_host_async", "vkrt_frame_host_wait",
     "vkrt_frame_host_slot_ptr", "vkrt_frame_device_ptr", "vkrt_frame_rgba8_device_ptr", "vkrt_stream", "vkrt_stats",
     "vkrt_reset_stats", "vkrt_timing_enable", "vkrt_timing_read", "vkrt_flush_l2", "vkrt_volume_info", "vkrt_camera_uniform", "vkrt_dispatch_optimal",
@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
         "vkrt_present": (ci, [vp]),
         "vkrt_readback": (ci, [vp, vp]),
         "vkrt_readback_rgba8": (ci, [vp, vp]),
+        "vkrt_readback_rgba8_async": (ci, [vp, vp]),
         "vkrt_readback_aux": (ci, [vp, vp]),
         "vkrt_sync": (ci, [vp]),
         "vkrt_frame_host": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp]),
@@ -342,6 +343,10 @@ class Context:
         out = np.empty((self.height, self.width), np.uint32)
         _check(lib().vkrt_readback_aux(self._h, _vp(out)))
         return out
+
+    def readback_rgba8_async(self, out: np.ndarray):
+        """Enqueue the D2H of the presented frame into page-locked `out`; valid after sync()."""
+        _check(lib().vkrt_readback_rgba8_async(self._h, _vp(out)))
 
     def frame_host(self, cam: CameraUniform, out: np.ndarray | None = None, uniform: Uniform | None = None) -> np.ndarray:
         un = uniform if uniform is not None else self.global_uniform

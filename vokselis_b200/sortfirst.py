@@ -142,8 +142,10 @@ class SortFirstGroup:
         clock on the root from the first submit to the last frame's pixels on the host. The L2 flush
         before each rendered frame is INSIDE the timed region here (conservative)."""
         ctx, dist = self.ctx, self.dist
-        pinned = rt.PinnedArray((ctx.height, ctx.width, 4), np.uint8) if self.rank == 0 else None
+        R = 8  # host frames in flight on the root: the D2H copies are enqueued, the host blocks once per R frames
+        pinned = rt.PinnedArray((R, ctx.height, ctx.width, 4), np.uint8) if self.rank == 0 else None
         out = pinned.array if pinned is not None else None
+        done = 0
         ctx.sync()
         dist.barrier()
         t0 = time.perf_counter()
@@ -160,8 +162,11 @@ class SortFirstGroup:
                 for k in range(B):
                     self.wait(f + k)
                     ctx.present()
-                    ctx.readback_rgba8(out)
+                    ctx.readback_rgba8_async(out[done % R])
                     self.consume(f + k)
+                    done += 1
+                    if done % R == 0:
+                        ctx.sync()  # a consumer would use the R host frames here
         ctx.sync()
         tot = time.perf_counter() - t0
         dist.barrier()
@@ -169,4 +174,5 @@ class SortFirstGroup:
         return {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": (144 + 48) * self.participants(0),
                 "d2h_bytes_per_step": ctx.width * ctx.height * 4,
                 "how": f"pipelined sort-first ({self.granularity}): ranks render into rank 0's ring by peer stores; rank 0 waits for each frame "
-                       "in order, presents, copies RGBA8 to host (blocking); wall clock on rank 0 over all K frames, L2 flushes included"}
+                       "in order, presents, enqueues the RGBA8 D2H into a ring of 8 page-locked host frames and blocks once per 8 frames; wall clock on rank 0 "
+                       "over all K frames, L2 flushes included. Every frame leaves through rank 0's PCIe link (~0.154 ms per 1080p RGBA8 frame)"}
