@@ -27,6 +27,10 @@ extern "C" {
     fn vkrt_readback(ctx: *mut VkrtContext, rgba16f: *mut u16) -> c_int;
     fn vkrt_readback_rgba8(ctx: *mut VkrtContext, rgba8: *mut u8) -> c_int;
     fn vkrt_sync(ctx: *mut VkrtContext) -> c_int;
+    // a sweep: n cameras -> n presented RGBA8 frames in host memory, groups of `group` frames per launch
+    fn vkrt_frames_host(ctx: *mut VkrtContext, cams: *const CameraUniform, n: c_int, un: *const Uniform, rgba8: *mut u8, group: c_int) -> c_int;
+    fn vkrt_alloc_host(bytes: usize, out: *mut *mut c_void) -> c_int;   // page-locked memory: keeps the D2H copies asynchronous
+    fn vkrt_free_host(ptr: *mut c_void) -> c_int;
 }
 
 pub struct CudaRaycast { ctx: *mut VkrtContext, pub width: u32, pub height: u32 }
@@ -58,6 +62,14 @@ impl CudaRaycast {
         check(unsafe { vkrt_present(self.ctx) })?;
         check(unsafe { vkrt_readback_rgba8(self.ctx, px.as_mut_ptr()) })?;
         Ok(px)
+    }
+}
+impl CudaRaycast {
+    /// The recorder path (src/lib.rs:132-140, src/utils/recorder.rs:79-127) for a whole camera sweep: one call,
+    /// frames come back presented (ACES + sRGB) as tightly packed RGBA8, frame i at i * width * height * 4.
+    pub fn capture_sweep(&self, cams: &[CameraUniform], un: &Uniform, out: &mut [u8]) -> color_eyre::eyre::Result<()> {
+        assert!(out.len() >= cams.len() * (self.width * self.height * 4) as usize);
+        check(unsafe { vkrt_frames_host(self.ctx, cams.as_ptr(), cams.len() as _, un, out.as_mut_ptr(), 0) })
     }
 }
 impl Drop for CudaRaycast { fn drop(&mut self) { unsafe { vkrt_destroy(self.ctx); } } }
