@@ -170,13 +170,23 @@ def m0_section(rt, abi, device, K, Wm, no_cpu):
             c.flush_l2()
             c.render(cams[(Wm + i) % ORBIT])
         ms = c.timing_read(n).astype(np.float64)
-        out[f"gpu_fps_{w}x{h}"] = 1e3 / float(ms.mean())
-        out[f"gpu_ms_{w}x{h}"] = float(ms.mean())
+        out[f"gpu_fps_{w}x{h}_one_frame_per_launch"] = 1e3 / float(ms.mean())
+        out[f"gpu_ms_{w}x{h}_one_frame_per_launch"] = float(ms.mean())
+        # 8 frames of the sweep per launch (grid.z = frame), like the headline
+        nb = max(n // 8, 1)
+        c.timing_enable(nb)
+        c.render_batch(cams[:8])
+        for j in range(nb):
+            c.flush_l2()
+            c.render_batch([cams[(Wm + 8 * j + k) % ORBIT] for k in range(8)])
+        msb = c.timing_read(nb).astype(np.float64)
+        out[f"gpu_fps_{w}x{h}"] = 8e3 / float(msb.mean())
+        out[f"gpu_ms_{w}x{h}"] = float(msb.mean()) / 8
         if (w, h) == (1280, 720) and not no_cpu:
             color, normal = c.download_rgba16f()
             cam0 = cams[0]
         c.close()
-    out["layout"] = "TEXTURE (tex3D point fetches), exact empty-space skipping"
+    out["layout"] = "TEXTURE (tex3D point fetches), exact empty-space skipping; gpu_fps_* = 8 frames per launch, L2 flushed between launches"
     if color is not None:
         try:
             from oracle import ref_binding as rb
@@ -277,7 +287,16 @@ def run_gpu(args):
         samples_fetched = st.samples_fetched / len(probe)
         ctx.set_params(p)
 
-    B = max(1, min(args.batch, rt.MAX_BATCH))  # frames per launch (grid.z = frame)
+    # frames per launch (grid.z = frame). --batch 0 = choose: 8 on one GPU; for N ranks the group size that minimises the
+    # busiest rank's time (groups are dealt round-robin: K = 360 in groups of 8 gives 4 ranks 12/11/11/11 groups, groups of
+    # 6 give 15 each), with the measured per-frame cost of a launch of b frames (profiles/r01_batch.md)
+    if args.batch > 0:
+        B = max(1, min(args.batch, rt.MAX_BATCH))
+    elif world == 1:
+        B = rt.MAX_BATCH
+    else:
+        cost = {1: 0.215, 2: 0.165, 3: 0.149, 4: 0.141, 5: 0.137, 6: 0.133, 7: 0.131, 8: 0.129}
+        B = min(cost, key=lambda b: (-(-(-(-K // b)) // world)) * b * cost[b])
     L = (K + B - 1) // B                        # launches per timed pass
 
     def chunk(i0):  # cameras of the launch that starts at step i0 (the orbit wraps)
@@ -292,14 +311,12 @@ def run_gpu(args):
         GB = group.batch
 
         def launch(i0, flush):
-            f = group.frame
-            mine = group.granularity == "tiles" or sortfirst.frame_owner(f, world, GB) == rank
-            if flush and mine:
-                ctx.flush_l2()
             if group.granularity == "tiles":
+                if flush:
+                    ctx.flush_l2()
                 group.render(cams[(Wm + i0) % ORBIT])
-            else:
-                group.render_batch(chunk(i0) if GB > 1 else [cams[(Wm + i0) % ORBIT]])
+            else:  # the owner flushes on the stream its launch uses (the root renders on its second stream)
+                group.render_batch(chunk(i0) if GB > 1 else [cams[(Wm + i0) % ORBIT]], flush_l2=flush)
         step_stride = GB if group.granularity == "frames" else 1
     else:
         group = None
@@ -495,7 +512,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
     ap.add_argument("--granularity", default="frames", choices=["frames", "tiles"], help="sort-first granularity for N > 1")
-    ap.add_argument("--batch", type=int, default=8, help="frames per launch (grid.z = frame), 1..8")
+    ap.add_argument("--batch", type=int, default=0, help="frames per launch (grid.z = frame), 1..8; 0 = choose (8 on one GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

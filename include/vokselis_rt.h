@@ -283,8 +283,12 @@ VKRT_API int vkrt_sortfirst_render(VkrtContext* ctx, const VkrtCameraUniform* ca
                                    const VkrtOffset* offsets, int n, uint64_t frame_index);
 /* `frames` granularity with batched launches: this rank renders n consecutive frames of the sweep
  * (first_frame .. first_frame+n-1, n <= VKRT_MAX_BATCH) in ONE launch into n consecutive ring slots; needs
- * slots % n == 0 and first_frame % n == 0. Each frame counts one arrival on its own slot. */
-VKRT_API int vkrt_sortfirst_render_batch(VkrtContext* ctx, const VkrtCameraUniform* cams, int n, const VkrtUniform* un, uint64_t first_frame);
+ * slots % n == 0 and first_frame % n == 0. Each frame counts one arrival on its own slot. Peers render into a local
+ * buffer and ship the group with one copy-engine transfer over NVLink (overlapping their next launch); the root
+ * renders on its second stream so that its in-order waits never hold back its own launches. */
+#define VKRT_SF_FLUSH_L2 1 /* flags: write an L2-sized buffer before the launch, on the stream the launch uses (benchmarks) */
+VKRT_API int vkrt_sortfirst_render_batch(VkrtContext* ctx, const VkrtCameraUniform* cams, int n, const VkrtUniform* un, uint64_t first_frame,
+                                         int flags);
 VKRT_API int vkrt_sortfirst_wait(VkrtContext* ctx, uint64_t frame_index, uint64_t arrivals_target);
 VKRT_API int vkrt_sortfirst_consume(VkrtContext* ctx, uint64_t frame_index, int do_present);
 /* Number of device-side waits that gave up after 10 s (a peer died); 0 on a healthy group. Synchronises. */

@@ -121,7 +121,7 @@ def lib() -> C.CDLL:
         "vkrt_sortfirst_leave": (ci, [vp]),
         "vkrt_sortfirst_partition": (ci, [ci, ci, ci, ci, ci, vp, ci]),
         "vkrt_sortfirst_render": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp, ci, C.c_uint64]),
-        "vkrt_sortfirst_render_batch": (ci, [vp, vp, ci, C.POINTER(Uniform), C.c_uint64]),
+        "vkrt_sortfirst_render_batch": (ci, [vp, vp, ci, C.POINTER(Uniform), C.c_uint64, ci]),
         "vkrt_sortfirst_consume": (ci, [vp, C.c_uint64, ci]),
         "vkrt_sortfirst_timeouts": (ci, [vp, C.POINTER(C.c_uint64)]),
     }
@@ -435,10 +435,10 @@ class Context:
         n = 0 if offsets is None else offsets.shape[0]
         _check(lib().vkrt_sortfirst_render(self._h, C.byref(cam), C.byref(un), _vp(offsets), n, frame_index))
 
-    def sortfirst_render_batch(self, cams, first_frame: int, uniform: Uniform | None = None):
+    def sortfirst_render_batch(self, cams, first_frame: int, uniform: Uniform | None = None, flush_l2: bool = False):
         un = uniform if uniform is not None else self.global_uniform
         arr = self._cam_array(cams)
-        _check(lib().vkrt_sortfirst_render_batch(self._h, C.cast(arr, C.c_void_p), len(cams), C.byref(un), first_frame))
+        _check(lib().vkrt_sortfirst_render_batch(self._h, C.cast(arr, C.c_void_p), len(cams), C.byref(un), first_frame, 1 if flush_l2 else 0))
 
     def sortfirst_consume(self, frame_index: int, present: bool = False):
         _check(lib().vkrt_sortfirst_consume(self._h, frame_index, 1 if present else 0))

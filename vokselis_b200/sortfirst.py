@@ -81,7 +81,7 @@ class SortFirstGroup:
             self.ctx.sortfirst_render(cam, None, f)
         return f
 
-    def submit_batch(self, cams) -> int:
+    def submit_batch(self, cams, flush_l2: bool = False) -> int:
         """'frames' granularity with batch > 1: every rank calls this once per group of len(cams) <= batch
         consecutive frames, in the same order; the owning rank renders the group in one launch. Returns the
         index of the group's first frame."""
@@ -90,12 +90,13 @@ class SortFirstGroup:
         f = self.frame
         self.frame += self.batch
         if frame_owner(f, self.world, self.batch) == self.rank:
-            self.ctx.sortfirst_render_batch(cams, f)
+            self.ctx.sortfirst_render_batch(cams, f, flush_l2=flush_l2)
         return f
 
-    def render_batch(self, cams, present: bool = False) -> int:
-        """submit_batch + (root) wait + consume of every frame of the group, in order. Asynchronous."""
-        f = self.submit_batch(cams)
+    def render_batch(self, cams, present: bool = False, flush_l2: bool = False) -> int:
+        """submit_batch + (root) wait + consume of every frame of the group, in order. Asynchronous.
+        flush_l2: write an L2-sized buffer before the owner's launch (benchmarks)."""
+        f = self.submit_batch(cams, flush_l2)
         if self.rank == 0:
             for k in range(self.batch):
                 self.wait(f + k)
@@ -152,10 +153,10 @@ class SortFirstGroup:
         B = self.batch
         for i in range(0, K, B):
             f_next = self.frame
-            if self.granularity == "tiles" or frame_owner(f_next, self.world, B) == self.rank:
+            if B == 1 and (self.granularity == "tiles" or frame_owner(f_next, self.world, B) == self.rank):
                 ctx.flush_l2()
             if B > 1:
-                f = self.submit_batch([cams[(warmup + i + k) % len(cams)] for k in range(min(B, K - i))])
+                f = self.submit_batch([cams[(warmup + i + k) % len(cams)] for k in range(min(B, K - i))], flush_l2=True)
             else:
                 f = self.submit(cams[(warmup + i) % len(cams)])
             if self.rank == 0:
