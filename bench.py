@@ -295,8 +295,9 @@ def run_gpu(args):
     elif world == 1:
         B = rt.MAX_BATCH
     else:
-        cost = {1: 0.215, 2: 0.165, 3: 0.149, 4: 0.141, 5: 0.137, 6: 0.133, 7: 0.131, 8: 0.129}
-        B = min(cost, key=lambda b: (-(-(-(-K // b)) // world)) * b * cost[b])
+        from vokselis_b200.sortfirst import choose_batch
+
+        B = choose_batch(K, world)
     L = (K + B - 1) // B                        # launches per timed pass
 
     def chunk(i0):  # cameras of the launch that starts at step i0 (the orbit wraps)
@@ -329,8 +330,12 @@ def run_gpu(args):
 
     # ---- timed: device time per launch (CUDA events on the context's stream), L2 flushed between launches -----
     ctx.timing_enable(max(K, 1))
-    for i in range(0, max(Wm, step_stride), step_stride):
-        launch(i % max(K, 1), True)
+    # warm-up: at least Wm steps, and with N ranks at least two launches on EVERY rank (buffers, module load, clocks)
+    n_warm = max(-(-Wm // step_stride), 1)
+    if group is not None and group.granularity == "frames":
+        n_warm = max(n_warm, 2 * world)
+    for j in range(n_warm):
+        launch((j * step_stride) % max(K - step_stride + 1, 1), True)
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:

@@ -52,29 +52,32 @@ def main():
                 ok = ok and to == 0
                 print(f"mode {mode} {gran}/{slots}: device-side wait timeouts = {to}", flush=True)
             group.close()
-        # batched groups of 3 frames dealt round-robin, one launch per group, straight into consecutive ring slots
-        group = sortfirst.SortFirstGroup(ctx, rank, world, granularity="frames", batch=3)
-        seq = cams * 4  # 20 frames: six full groups and a padded one, slots reused several times
-        done = 0
-        for g in range(0, len(seq), 3):
-            chunk = seq[g:g + 3]
-            f = group.submit_batch(chunk)
+        # batched groups dealt round-robin, one launch per group, peers shipping a group with one copy-engine transfer:
+        # groups of 3 (default ring), and groups of 5 in an 80-slot ring (what 8 ranks use) long enough to wrap it
+        for batch, slots, total in ((3, None, 20), (5, 80, 103)):
+            group = sortfirst.SortFirstGroup(ctx, rank, world, granularity="frames", batch=batch, slots=slots)
+            seq = (cams * (total // len(cams) + 1))[:total]
+            done, good = 0, True
+            for g in range(0, len(seq), batch):
+                chunk = seq[g:g + batch]
+                f = group.submit_batch(chunk, flush_l2=(g % 2 == 0))
+                if rank == 0:
+                    for k in range(batch):
+                        group.wait(f + k)
+                        got = ctx.readback()
+                        group.consume(f + k)
+                        if k < len(chunk):
+                            same = np.array_equal(got, refs[(g + k) % len(cams)])
+                            good = good and same
+                            done += 1
+                            if not same:
+                                print(f"mode {mode} frames/batch{batch} frame {g + k}: MISMATCH", flush=True)
             if rank == 0:
-                for k in range(3):
-                    group.wait(f + k)
-                    got = ctx.readback()
-                    group.consume(f + k)
-                    if k < len(chunk):
-                        same = np.array_equal(got, refs[(g + k) % len(cams)])
-                        ok = ok and same
-                        done += 1
-                        if not same:
-                            print(f"mode {mode} frames/batch3 frame {g + k}: MISMATCH", flush=True)
-        if rank == 0:
-            to = ctx.sortfirst_timeouts()
-            ok = ok and to == 0
-            print(f"mode {mode} frames/batch3: {done} frames {'bit-exact' if ok else 'FAILED'}, device-side wait timeouts = {to}", flush=True)
-        group.close()
+                to = ctx.sortfirst_timeouts()
+                good = good and to == 0
+                ok = ok and good
+                print(f"mode {mode} frames/batch{batch}/slots{group.slots}: {done} frames {'bit-exact' if good else 'FAILED'}, device-side wait timeouts = {to}", flush=True)
+            group.close()
         ctx.close()
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)

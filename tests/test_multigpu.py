@@ -110,3 +110,24 @@ def test_visibility_order_is_front_to_back_for_every_ray(oracle):
                             break
                 assert len(seq) == len(set(seq)), "a ray re-entered a brick"
                 assert [pos[r] for r in seq] == sorted(pos[r] for r in seq), (eye, seq, order)
+
+
+def test_group_dealing_covers_every_frame_once_and_fits_the_ring():
+    """'frames' granularity with batched launches (host logic only): for the world sizes and step counts the bench
+    is run with, the chosen group size keeps the ring within the library's slot limit, every frame has exactly
+    one owner, a group never straddles the ring's end, and ranks differ by at most one group."""
+    from vokselis_b200 import sortfirst
+
+    for world in (2, 4, 8):
+        for steps in (360, 100, 50, 16, 8, 3, 1):
+            b = sortfirst.choose_batch(steps, world)
+            slots = 2 * world * b
+            assert 1 <= b <= 8 and slots <= sortfirst.MAX_SLOTS and slots % b == 0
+            groups = -(-steps // b)
+            owners = [sortfirst.frame_owner(g * b, world, b) for g in range(groups)]
+            for g in range(groups):
+                first = g * b
+                assert all(sortfirst.frame_owner(f, world, b) == owners[g] for f in range(first, first + b))
+                assert first % slots + b <= slots
+            per_rank = [owners.count(r) for r in range(world)]
+            assert max(per_rank) - min(per_rank) <= 1

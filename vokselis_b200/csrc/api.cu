@@ -1010,7 +1010,7 @@ int vkrt_flush_l2(VkrtContext* c) {
 // Shared block in rank 0's memory: [mailbox 4 KiB: u64 consumed, u64 timeouts, u64 arrive[slots]][slot 0]...[slot S-1]
 namespace {
 constexpr size_t kSfMailbox = 4096;
-constexpr int kSfMaxSlots = 64;
+constexpr int kSfMaxSlots = 256;  // arrival flags live in the 4 KiB mailbox: 2 + slots u64 words
 inline size_t sf_frame_bytes(const VkrtContext* c) { return (size_t)c->W * c->H * sizeof(uint2); }
 inline unsigned long long* sf_consumed(VkrtContext* c) { return reinterpret_cast<unsigned long long*>(c->sf_base); }
 inline unsigned long long* sf_timeouts(VkrtContext* c) { return reinterpret_cast<unsigned long long*>(c->sf_base) + 1; }
@@ -1019,7 +1019,7 @@ inline uint2* sf_slot(VkrtContext* c, int slot) { return reinterpret_cast<uint2*
 }  // namespace
 
 int vkrt_sortfirst_create_root(VkrtContext* c, int world, int slots, VkrtSortFirstHandle* out) {
-    if (!c || !out || world < 1 || slots < 2 || slots > kSfMaxSlots) return fail(VKRT_ERR_INVALID, "bad argument (2 <= slots <= 64)");
+    if (!c || !out || world < 1 || slots < 2 || slots > kSfMaxSlots) return fail(VKRT_ERR_INVALID, "bad argument (2 <= slots <= 256)");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     sf_release(c);

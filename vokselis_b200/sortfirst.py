@@ -25,6 +25,23 @@ import numpy as np
 from . import rt
 
 
+MAX_SLOTS = 256  # kSfMaxSlots in csrc/api.cu
+
+
+# measured device ms per frame of a launch of b frames (bench workload, profiles/r01_batch.md)
+_MS_PER_FRAME = {1: 0.215, 2: 0.165, 3: 0.149, 4: 0.141, 5: 0.137, 6: 0.133, 7: 0.131, 8: 0.129}
+
+
+def choose_batch(steps: int, world: int) -> int:
+    """Frames per launch for `steps` frames dealt to `world` ranks in groups, round-robin: the group size that
+    minimises the busiest rank's time (360 frames in groups of 8 give 4 ranks 12/11/11/11 groups; groups of 6 give
+    15 each). A short last group is padded to a full one, hence the ceilings."""
+    def busiest_ms(b):
+        groups = -(-steps // b)
+        return -(-groups // world) * b * _MS_PER_FRAME[b]
+    return min((b for b in _MS_PER_FRAME if 2 * world * b <= MAX_SLOTS), key=busiest_ms)
+
+
 def partition_tiles(width: int, height: int, tile: int, rank: int, world: int) -> np.ndarray:
     return rt.sortfirst_partition(width, height, tile, rank, world)
 
@@ -46,8 +63,8 @@ class SortFirstGroup:
         if not 1 <= self.batch <= rt.MAX_BATCH:
             raise ValueError(f"batch must be 1..{rt.MAX_BATCH}")
         self.slots = slots if slots is not None else (2 if granularity == "tiles" else 2 * world * self.batch)
-        if self.slots % self.batch:
-            raise ValueError("slots must be a multiple of batch")
+        if self.slots % self.batch or not 2 <= self.slots <= MAX_SLOTS:
+            raise ValueError(f"slots must be a multiple of batch in 2..{MAX_SLOTS}")
         self.tiles = None
         if granularity == "tiles":
             p = ctx.get_params()
