@@ -38,7 +38,7 @@ def advance_t(t: np.float32, dt: np.float32, n: int) -> np.float32:
 
 
 def leap_t(t, dt, n):
-    """Fast path (leap_t in vkrt_device.cuh): stays inside the binade and no tie -> one integer multiply-add."""
+    """The uncached form of leap_cached's fast path: stays inside the binade and no tie -> one integer multiply-add."""
     db, tb = int(np.float32(dt).view(np.uint32)), int(np.float32(t).view(np.uint32))
     e, shift = tb >> 23, (tb >> 23) - (db >> 23)
     if 1 <= shift <= 24 and (db >> 23) != 0:

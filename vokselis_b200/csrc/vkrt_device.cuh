@@ -130,26 +130,10 @@ __device__ __forceinline__ float advance_t(float t, float dt, int n) {
     return t;
 }
 
-// Fast path of advance_t for the common case — the whole run stays inside t's binade and dt is not an exact
-// tie there: one shift, one compare, one integer multiply-add on the bit pattern; anything else (binade
-// crossing, tie, tiny t) goes through advance_t. Bit-identical to n repeated additions either way.
-__device__ __forceinline__ float leap_t(float t, float dt, int n) {
-    const uint32_t db = __float_as_uint(dt), tb = __float_as_uint(t);
-    const int e = (int)(tb >> 23), shift = e - (int)(db >> 23);
-    if (shift >= 1 && shift <= 24 && (db >> 23) != 0u) {
-        const uint32_t M = (db & 0x7fffffu) | 0x800000u;
-        const uint32_t rem = M & ((1u << shift) - 1u), half = 1u << (shift - 1);
-        if (rem != half) {
-            // 64-bit: n * inc can exceed 2^32 (n up to thousands, inc up to 2^23) and must not wrap into the binade
-            const unsigned long long nb = (unsigned long long)tb + (unsigned long long)(uint32_t)n * ((M >> shift) + (rem > half ? 1u : 0u));
-            if ((nb >> 23) == (unsigned long long)e) return __uint_as_float((uint32_t)nb);
-        }
-    }
-    return advance_t(t, dt, n);
-}
-
-// The same fast path with the per-binade increment kept in registers across the leaps of one ray (a ray
-// crosses one or two binades of t): shift, compare, one wide multiply-add, compare. inc == 0xffffffff marks
+// Fast path of advance_t for the common case — the whole run stays inside t's binade and dt is not an exact tie
+// there — with the per-binade increment kept in registers across the leaps of one ray (a ray crosses one or two
+// binades of t): shift, compare, one wide multiply-add (64 bits: n * inc can exceed 2^32 and must not wrap back
+// into the binade), compare. Bit-identical to n repeated additions either way. inc == 0xffffffff marks
 // "no closed form in this binade" (t below dt's binade, dt < ulp(t)/2, an exact tie, subnormals): with it the
 // binade check below always fails and advance_t takes over.
 struct LeapCache {

@@ -1,7 +1,9 @@
 // headless.cpp — offscreen harness next to the reference's windowed presenter (src/lib.rs:45-208).
 // Runs the xor example's Demo (examples/xor/main.rs) without a window: generate the volume once,
 // then render `frames` frames of an orbit, print the mean frame time, optionally dump the last frame.
-//   usage: headless [frames=360] [W=1280] [H=720] [single|tile] [out.rgba8]
+// Mode `sweep` hands the whole orbit to the library in chunks of 24 cameras (Context::capture_sweep ->
+// vkrt_frames_host): several frames per launch, present fused, D2H pipelined — the offline-recording path.
+//   usage: headless [frames=360] [W=1280] [H=720] [single|tile|sweep] [out.rgba8]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -27,6 +29,28 @@ int main(int argc, char** argv) {
         Context ctx(0, W, H);
         Xor demo;
         demo.tile_mode = argc > 4 && strcmp(argv[4], "tile") == 0;
+        if (argc > 4 && strcmp(argv[4], "sweep") == 0) {
+            demo.init(ctx);
+            std::vector<VkrtCameraUniform> cams;
+            std::vector<uint8_t> last;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (unsigned i = 0; i < frames; ++i) {
+                ctx.camera.set_yaw(1.0f + 6.2831853f * (float)i / (float)(frames ? frames : 1));
+                cams.push_back(ctx.camera.get_proj_view_matrix());
+                if (cams.size() == 24 || i + 1 == frames) {
+                    last = ctx.capture_sweep(cams);  // presented RGBA8 frames, in order
+                    cams.clear();
+                }
+            }
+            const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            printf("%u frames %ux%u (sweep, frames delivered to host memory) in %.3f s -> %.1f frames/s\n", frames, W, H, s, frames / s);
+            if (argc > 5 && !last.empty()) {
+                const size_t one = (size_t)W * H * 4;
+                FILE* f = fopen(argv[5], "wb");
+                if (f) { fwrite(last.data() + last.size() - one, 1, one, f); fclose(f); }
+            }
+            return 0;
+        }
         const auto t0 = std::chrono::steady_clock::now();
         run_headless(demo, ctx, frames, [&](Context& c, unsigned i) {
             c.camera.set_yaw(1.0f + 6.2831853f * (float)i / (float)(frames ? frames : 1));

@@ -121,6 +121,14 @@ class Context {
         check(vkrt_readback_rgba8(ctx_, px.data()));
         return px;
     }
+    // A whole camera sweep for a host consumer — what the recorder does frame by frame (src/lib.rs:132-140,
+    // src/utils/recorder.rs:79-127) — in one call: groups of frames per launch, present fused, D2H pipelined.
+    // Returns cams.size() tightly packed RGBA8 frames.
+    std::vector<uint8_t> capture_sweep(const std::vector<VkrtCameraUniform>& cams) {
+        std::vector<uint8_t> px((size_t)width_ * height_ * 4 * cams.size());
+        if (!cams.empty()) check(vkrt_frames_host(ctx_, cams.data(), (int)cams.size(), &global_uniform, px.data(), 0));
+        return px;
+    }
     std::vector<uint16_t> read_backbuffer() {
         std::vector<uint16_t> px((size_t)width_ * height_ * 4);
         check(vkrt_readback(ctx_, px.data()));
