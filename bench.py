@@ -208,6 +208,28 @@ def m0_section(rt, abi, device, K, Wm, no_cpu):
     return out
 
 
+def host_sweep(ctx, rt, cams, frame_ids, per_call, group):
+    """Frames `frame_ids` of the orbit through vkrt_frames_host into page-locked host memory, `per_call` frames per
+    blocking call; returns the summed wall time of the calls (the L2 flush before each call is not timed)."""
+    if not frame_ids:
+        return 0.0
+    pinned = rt.PinnedArray((per_call, H, W, 4), np.uint8)
+    out = pinned.array
+    ctx.frames_host([cams[i % ORBIT] for i in range(per_call)], out, group=group)  # warm-up: buffers, clocks
+    tot, done = 0.0, 0
+    while done < len(frame_ids):
+        n = min(per_call, len(frame_ids) - done)
+        cs = [cams[f] for f in frame_ids[done:done + n]]
+        ctx.flush_l2()
+        ctx.sync()
+        t0 = time.perf_counter()
+        ctx.frames_host(cs, out[:n], group=group)  # blocking: returns when the n frames are in host memory
+        tot += time.perf_counter() - t0
+        done += n
+    pinned.close()
+    return tot
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -393,21 +415,8 @@ def run_gpu(args):
         # the call a user of a sweep makes: vkrt_frames_host — cameras in, presented RGBA8 frames out in page-locked host memory;
         # groups of B frames per launch, present fused into the raycast epilogue, D2H of a group overlapping the next raycast
         PER_CALL = 24
-        pinned = rt.PinnedArray((PER_CALL, H, W, 4), np.uint8)
-        out = pinned.array
-        ctx.frames_host([cams[i % ORBIT] for i in range(PER_CALL)], out, group=min(B, 4))
-        tot, done = 0.0, 0
-        while done < K:
-            n = min(PER_CALL, K - done)
-            cs = [cams[(Wm + done + k) % ORBIT] for k in range(n)]
-            ctx.flush_l2()
-            ctx.sync()
-            t0 = time.perf_counter()
-            ctx.frames_host(cs, out[:n], group=min(B, 4))  # blocking: returns when the n frames are in host memory
-            tot += time.perf_counter() - t0
-            done += n
+        tot = host_sweep(ctx, rt, cams, [(Wm + i) % ORBIT for i in range(K)], PER_CALL, min(B, 4))
         e2e_frames = K / tot
-        pinned.close()
         # one frame per call (vkrt_frame_host, blocking), for comparison
         pinned1 = rt.PinnedArray((H, W, 4), np.uint8)
         n1 = min(K, 120)
@@ -449,6 +458,22 @@ def run_gpu(args):
     if group is not None:
         timeouts = ctx.sortfirst_timeouts() if rank == 0 else 0
         group.close()
+        # e2e with every rank delivering ITS share of the sweep (a contiguous range of frames) into its own host
+        # memory through its own PCIe link — vkrt_frames_host per rank, no NVLink traffic at all; the funnel through
+        # rank 0's link measured above is kept as `through_rank0`
+        lo_f, hi_f = rank * K // world, (rank + 1) * K // world
+        barrier()
+        my_tot = host_sweep(ctx, rt, cams, [(Wm + i) % ORBIT for i in range(lo_f, hi_f)], 24, 4)
+        tt = torch.tensor([my_tot], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        barrier()
+        funnel = e2e
+        e2e = {"value": K / float(tt.item()) if float(tt.item()) > 0 else 0.0, "unit": "frames/s", "h2d_bytes_per_step": 144 + 48,
+               "d2h_bytes_per_step": W * H * 4,
+               "how": f"every rank renders a contiguous 1/{world} of the sweep with vkrt_frames_host (24 frames per blocking call, groups of 4 frames "
+                      "per launch, present fused, D2H overlapping the next group) into its own page-locked host memory over its own PCIe link; "
+                      "K frames over the slowest rank's summed call time, L2 flushed before each call (flush untimed)",
+               "through_rank0": funnel}
     if rank == 0:
         ms = total_ms / K
         frames_per_launch = step_stride
