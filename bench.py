@@ -16,7 +16,8 @@ presented RGBA8 frames out into pinned host memory).
 
 --impl reference times the CPU restatement of the reference (the oracle port; the reference itself
 needs Rust + wgpu + Vulkan, none of which exist here) on all host cores, on the same workload.
-N > 1 (torchrun): image tiles are sharded sort-first across ranks and written into rank 0's frame.
+N > 1 (torchrun): sort-first — groups of consecutive frames are dealt round-robin to the ranks (volume replicated), every
+frame lands in rank 0's ring of frames over NVLink; --granularity tiles splits every frame into image tiles instead.
 """
 from __future__ import annotations
 
@@ -329,7 +330,8 @@ def run_gpu(args):
         from vokselis_b200 import sortfirst
 
         # 1080p frames take a fraction of a millisecond on one GPU: deal whole frames — groups of B consecutive
-        # frames, one launch per group — round-robin; every frame still lands in rank 0's ring by peer stores.
+        # frames, one launch per group — round-robin; every frame still lands in rank 0's ring (peers ship a group
+        # with one copy-engine transfer over NVLink, overlapping their next launch).
         group = sortfirst.SortFirstGroup(ctx, rank, world, granularity=args.granularity, tile=120, batch=B if args.granularity == "frames" else 1)
         GB = group.batch
 
@@ -381,7 +383,7 @@ def run_gpu(args):
         return (ctx.timing_read(mine).astype(np.float64) if mine > 0 else np.zeros(0)), wall
 
     def whole_job_ms(ms):
-        total = float(ms.sum())  # this rank's busy device time (its launches: kernel + peer stores + arrival signals)
+        total = float(ms.sum())  # this rank's busy device time: its launches (the group transfers overlap them on the copy stream)
         if world > 1:
             t = torch.tensor([total], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
