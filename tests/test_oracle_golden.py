@@ -75,6 +75,27 @@ def test_oracle_equals_translated_reference_when_present(oracle):
         assert np.array_equal(ref, got)
 
 
+def test_full_reference_configuration_oracle_equals_translated_reference(oracle):
+    """The reference's own configuration end to end (SURVEY §8c pin iii): xor.wgsl `cs_main` at 256^3 with time = 0
+    (examples/xor/main.rs:135-146), raycast_compute.wgsl `single` at 1280x720 with the xor example's camera
+    (examples/xor/main.rs:273-279), then present.wgsl — the hand restatement against the machine-translated
+    reference, bit for bit, and the frozen hit count 179,515."""
+    from oracle import ref_binding as rb
+
+    if not rb.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    W, H = 1280, 720
+    color, normal = rb.xor_generate(256, 0.0)
+    oc, on = oracle.generate_xor(256, 0.0)
+    assert np.array_equal(color, oc) and np.array_equal(normal, on)
+    cam = oracle.camera_uniform(3.0, -0.5, 1.0, (0.0, 0.0, 0.0), W / H)
+    ref = rb.raycast_compute(cam, color, normal, W, H)
+    got, aux, st = oracle.render(abi.default_params(0), cam, W, H, color=color, normal=normal)
+    assert np.array_equal(ref, got)
+    assert st.rays_hit == 179515 and int((aux >> 31).sum()) == 179515
+    assert np.array_equal(rb.present(ref), oracle.present(got))
+
+
 @pytest.mark.parametrize("seed", range(5))
 def test_oracle_equals_translated_reference_randomised(oracle, seed):
     """Random volumes (NaN / inf / negative texels, non-cubic dims on both sides of the dt floor), random
