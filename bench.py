@@ -106,12 +106,37 @@ def load_peaks() -> dict:
     if m.exists():
         try:
             peaks["micro"] = json.loads(m.read_text())
+            peaks["micro_source"] = "profiles/microbench_r01.json (committed copy, measured on this pool's B200 in round 1)"
         except Exception:
             pass
     return peaks
 
 
+def run_microbench(device: int):
+    """The texel-path / L1 / L2 / HBM peaks of THIS GPU, measured in THIS job by build/microbench (bench/microbench.cu),
+    outside every timed region. Returns (dict, clocks) or (None, None)."""
+    exe = ROOT / "build" / "microbench"
+    if not exe.exists():
+        return None, None
+    clocks = ClockSampler(device)
+    clocks.start()
+    try:
+        r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=240)  # device 0 = the N=1 bench device
+        out = json.loads(r.stdout) if r.returncode == 0 else None
+    except Exception:
+        out = None
+    return out, clocks.stop()
+
+
 # ------------------------------------------------------------------------------------------------
+def host_cores() -> int:
+    """Host cores this process may use — NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_run(steps: int, warmup: int, tiles_per_step: int = 4) -> dict:
     """The reference's CPU arm: oracle port of the M1 march on all host cores. Each step renders a
     stratified 1/36 sample of one orbit frame (4 of 144 tiles of 160x120 px... see `sample`)."""
@@ -126,13 +151,13 @@ def cpu_reference_run(steps: int, warmup: int, tiles_per_step: int = 4) -> dict:
     ntiles = cols * rows
     stride = ntiles // tiles_per_step
     frame = np.zeros((H, W, 4), np.uint16)
-    cores = ob.num_threads()
+    cores = host_cores()  # passed to the oracle explicitly (num_threads(nt)), whatever OMP_NUM_THREADS says
 
     def step(i):
         cam = ob.camera_uniform(*orbit_camera(None, i))
         ids = [(i * 7 + k * stride) % ntiles for k in range(tiles_per_step)]
         offs = np.array([[(t % cols) * ts, (t // cols) * ts] for t in ids], np.float32)
-        _, _, st = ob.render(p, cam, W, H, scalar=vol, offsets=offs, frame=frame, want_aux=False)
+        _, _, st = ob.render(p, cam, W, H, scalar=vol, offsets=offs, frame=frame, want_aux=False, nthreads=cores)
         return st.samples_reference
 
     for i in range(warmup):
@@ -193,13 +218,14 @@ def m0_section(rt, abi, device, K, Wm, no_cpu):
             from oracle import ref_binding as rb
 
             if rb.available():
-                rb.raycast_compute(cam0, color, normal, 1280, 720)  # warm-up
+                nt = host_cores()
+                rb.raycast_compute(cam0, color, normal, 1280, 720, nthreads=nt)  # warm-up
                 t0 = time.perf_counter()
                 reps = 2
                 for _ in range(reps):
-                    rb.raycast_compute(cam0, color, normal, 1280, 720)
+                    rb.raycast_compute(cam0, color, normal, 1280, 720, nthreads=nt)
                 dt = (time.perf_counter() - t0) / reps
-                out["cpu_reference_wgsl"] = {"value": 1.0 / dt, "unit": "frames/s", "cores": rb.num_threads(), "kind": "reference",
+                out["cpu_reference_wgsl"] = {"value": 1.0 / dt, "unit": "frames/s", "cores": nt, "kind": "reference",
                                              "sample": f"{reps} full 1280x720 frames of `single` (xor camera), oracle/_ref = the reference's "
                                                        "raycast_compute.wgsl machine-translated to C++ (oracle/wgsl2cpp.py), OpenMP over rows"}
             else:
@@ -235,7 +261,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    r = cpu_reference_run(args.steps, args.warmup)
+    # ~10 frame-equivalents in total whatever K is (a 1080p M1 frame costs the oracle ~0.3-0.6 s on 16-32 cores)
+    tiles = max(4, min(144, int(round(1440 / max(args.steps, 1)))))
+    r = cpu_reference_run(args.steps, args.warmup, tiles_per_step=tiles)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
@@ -295,19 +323,25 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
 
-    # ---- sample statistics of the workload (untimed, DBG kernel) -------------------------------
+    # ---- sample statistics of the workload (untimed, DBG kernel) over exactly the cameras the timed passes render ----
     samples_ref = samples_fetched = 0
     if rank == 0:
         q = rt.default_params(abi.MODE_M1)
         q.skip_empty, q.count_samples, q.layout = 1, 1, p.layout
         ctx.set_params(q)
-        probe = list(range(0, ORBIT, 30))
-        ctx.reset_stats()
-        for i in probe:
-            ctx.render(cams[i])
-        st = ctx.stats()
-        samples_ref = st.samples_reference / len(probe)
-        samples_fetched = st.samples_fetched / len(probe)
+        probe = sorted({(Wm + i) % ORBIT for i in range(K)})
+        weight = {f: 0 for f in probe}
+        for i in range(K):
+            weight[(Wm + i) % ORBIT] += 1
+        tot_ref = tot_fetched = 0
+        for f in probe:
+            ctx.reset_stats()
+            ctx.render(cams[f])
+            st = ctx.stats()
+            tot_ref += weight[f] * st.samples_reference
+            tot_fetched += weight[f] * st.samples_fetched
+        samples_ref = tot_ref / K          # mean per timed frame
+        samples_fetched = tot_fetched / K
         ctx.set_params(p)
 
     # frames per launch (grid.z = frame). --batch 0 = choose: 8 on one GPU; for N ranks the group size that minimises the
@@ -483,10 +517,18 @@ def run_gpu(args):
         # Algorithmic bytes per ray-sample: 8 taps x 1 B; units per launch = the samples the
         # kernel actually fetches for one frame. The 16 MiB volume is L1/L2-resident, so the texture path
         # (two tld4 gathers per sample) is the binding memory resource, not HBM; both are reported.
-        kernel_ms = float(launch_ms.mean())  # average launch duration of the dominant kernel (CUDA events, context stream)
-        micro = peaks.get("micro", {})
-        alg_bytes = samples_fetched * 8.0 * frames_per_launch
-        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        # achieved = algorithmic bytes of the frames ACTUALLY launched / their summed launch time (rank 0's launches; a last,
+        # shorter launch counts with its own frames). At N = 1 this equals samples_per_frame.fetched x 8 B / ms_per_step.
+        my_frames = K if world == 1 else max(int(round(K * len(launch_ms) / max(L, 1))), 1)
+        sum_ms = float(launch_ms.sum())
+        kernel_ms = sum_ms / max(len(launch_ms), 1)   # average launch duration (CUDA events on the launching stream)
+        micro, micro_clocks = (run_microbench(local) if world == 1 else (None, None))
+        micro_source = "build/microbench (bench/microbench.cu) run by this bench.py process on this GPU right after the timed regions"
+        if not micro:
+            micro, micro_source = peaks.get("micro", {}), peaks.get("micro_source", "none")
+        alg_bytes_total = samples_fetched * 8.0 * my_frames
+        alg_bytes = alg_bytes_total / max(len(launch_ms), 1)  # per (average) launch
+        achieved = alg_bytes_total / (sum_ms * 1e-3) / 1e9
         tld4_peak = micro.get("tld4_a2d_u8_F16_ginstr_s")  # G tld4/s; 4 B of texels each -> GB/s of texel bytes = 4x
         l1_peak = 4.0 * tld4_peak if tld4_peak else None
         traffic = None
@@ -497,12 +539,13 @@ def run_gpu(args):
                 traffic = tj.get("raycast_m1_gather_u8_skip_batch8_dram_bytes_per_launch") if frames_per_launch == 8 else None
             except Exception:
                 pass
-        hbm_bytes = min(NVOL ** 3, alg_bytes) + frames_per_launch * W * H * 8.0
+        hbm_bytes = min(NVOL ** 3, alg_bytes) + (my_frames / max(len(launch_ms), 1)) * W * H * 8.0
         roofline = {
             "kernel": "raycast_kernel<M1, GATHER, SKIP>", "bound": "tex",
             "achieved": achieved, "peak": l1_peak, "unit": "GB/s", "frac": (achieved / l1_peak) if l1_peak else None, "traffic": traffic,
-            "peak_source": "profiles/microbench_r01.json tld4_a2d_u8_F16 x 4 B (measured on this pool's B200 by bench/microbench.cu: coherent 8x4 "
-                           "tld4 gathers, L1-resident); tex3D trilinear peak for comparison: %s Gfetch/s" % micro.get("tex3d_linear_u8_F16_gfetch_s"),
+            "peak_source": "tld4_a2d_u8_F16 x 4 B (coherent 8x4 tld4 gathers, L1-resident) from %s; tex3D trilinear peak for comparison: %s Gfetch/s"
+                           % (micro_source, micro.get("tex3d_linear_u8_F16_gfetch_s")),
+            "peak_clocks": micro_clocks, "microbench": micro if world == 1 else None,
             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
             "hbm": {"bound": "hbm", "achieved": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["hbm_source"],

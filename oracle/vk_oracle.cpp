@@ -407,7 +407,9 @@ int vko_render(const VkoVolume* vol, const VkrtParams* params, const VkrtCameraU
         const int ts = P.tile_size;
         for (int k = 0; k < n_offsets; ++k) {
             const float offx = offsets[k].x, offy = offsets[k].y;
-            const uint32_t ox = (uint32_t)f2i(offx), oy = (uint32_t)f2i(offy);
+            // vec2<u32>(vec2<f32>): truncates and SATURATES (negative / NaN -> 0), like oracle/wgsl_rt.hpp to_u32
+            auto sat_u32 = [](float f) -> uint32_t { return (!(f == f) || f <= 0.0f) ? 0u : (f >= 4294967296.0f ? 0xffffffffu : (uint32_t)f); };
+            const uint32_t ox = sat_u32(offx), oy = sat_u32(offy);
 #pragma omp parallel for schedule(dynamic, 4) num_threads(nt) reduction(+ : hits, its, fet)
             for (int gy = 0; gy < ts; ++gy) {
                 for (int gx = 0; gx < ts; ++gx) {

@@ -137,6 +137,8 @@ def test_oracle_equals_translated_reference_randomised(oracle, seed):
     ts = int(rng.choice([16, 32, 48]))
     table = np.array([[x * ts + float(rng.choice([0.0, 0.25, 0.5])), y * ts + float(rng.choice([0.0, 0.75]))]
                       for y in range(H // ts + 1) for x in range(W // ts + 1)], np.float32)
+    # a negative offset: the ray uses gid + offset, the store saturates to gid + 0 (vec2<u32>(f32))
+    table = np.concatenate([table, np.array([[-3.5, 0.0], [float(ts), -2.25]], np.float32)])
     p.tile_size = ts
     got_t, _, _ = oracle.render(p, cam, W, H, color=color.view(np.uint16), normal=normal.view(np.uint16), offsets=table)
     ref_t = rb.raycast_compute(cam, color.view(np.uint16), normal.view(np.uint16), W, H, entry="tile", offsets=table, tile_size=ts)

@@ -51,6 +51,10 @@ struct VkrtContext {
     int W = 0, H = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    // recorded on `stream` after a layout (BRICKED / TEXTURE / GATHER) was built there; a render launched on another
+    // stream (the sort-first root renders on copy_stream) waits for it before reading the layout
+    cudaEvent_t ev_layout = nullptr;
+    bool layout_pending = false;
     cudaEvent_t ev_slot_ready[2] = {nullptr, nullptr}, ev_slot_copied[2] = {nullptr, nullptr};
     VkrtParams params{};
     // frame resources
@@ -117,6 +121,7 @@ void free_layouts(VkrtContext* c) {
     c->tex_a = c->tex_b = 0;
     c->arr_a = c->arr_b = nullptr;
     c->bricked = nullptr;
+    c->layout_pending = false;
 }
 void free_volume(VkrtContext* c) {
     free_layouts(c);
@@ -215,8 +220,8 @@ int copy_to_array(cudaArray_t arr, const void* src, size_t elem_bytes, int nx, i
     return VKRT_OK;
 }
 
-// Build whatever the selected layout needs (idempotent).
-int ensure_layout(VkrtContext* c) {
+// Build whatever the selected layout needs (idempotent). Work is queued on c->stream.
+int build_layout(VkrtContext* c) {
     if (c->kind == VOL_NONE) return fail(VKRT_ERR_NO_VOLUME, "no volume uploaded or generated");
     const int layout = c->params.layout;
     if (layout == VKRT_LAYOUT_LINEAR) return VKRT_OK;
@@ -280,6 +285,17 @@ int ensure_layout(VkrtContext* c) {
     return fail(VKRT_ERR_UNSUPPORTED, "layout BRICKED is not available for scalar volumes");
 }
 
+int ensure_layout(VkrtContext* c) {
+    const void* before[3] = {c->bricked, (const void*)c->tex_a, (const void*)c->tex_g};
+    const int rc = build_layout(c);
+    if (rc) return rc;
+    if (before[0] != c->bricked || before[1] != (const void*)c->tex_a || before[2] != (const void*)c->tex_g) {
+        CK(cudaEventRecord(c->ev_layout, c->stream));
+        c->layout_pending = true;
+    }
+    return VKRT_OK;
+}
+
 int set_dims(VkrtContext* c, int nx, int ny, int nz) {
     if (nx <= 0 || ny <= 0 || nz <= 0 || nx > 8192 || ny > 8192 || nz > 8192) return fail(VKRT_ERR_INVALID, "volume dimensions out of range");
     c->nx = nx; c->ny = ny; c->nz = nz;
@@ -293,7 +309,7 @@ int build_occupancy(VkrtContext* c) {
     CK(cudaMalloc(&c->dist, cells));
     CK(cudaMalloc(&scratch, cells < 64 ? 64 : cells));
     cudaError_t e;
-    if (c->kind == VOL_RGBA16F) e = launch_occupancy_m0((const uint2*)c->lin_a, c->nx, c->ny, c->nz, c->nbx, c->nby, c->nbz, c->dist, c->stream);
+    if (c->kind == VOL_RGBA16F) e = launch_occupancy_m0((const uint2*)c->lin_a, (const uint2*)c->lin_b, c->nx, c->ny, c->nz, c->nbx, c->nby, c->nbz, c->dist, c->stream);
     else e = launch_occupancy_m1(c->lin_a, c->dtype, c->nx, c->ny, c->nz, c->nbx, c->nby, c->nbz, c->dist, c->stream);
     // bricks outside the grid: empty for M0 (out-of-range texels read 0), occupied for M1 (clamp-to-edge)
     if (e == cudaSuccess) e = launch_distance_transform(c->dist, scratch, c->nbx, c->nby, c->nbz, c->kind == VOL_RGBA16F ? 255 : 0, kMaxLeapBricks, c->stream);
@@ -306,6 +322,18 @@ int build_occupancy(VkrtContext* c) {
     if (e != cudaSuccess) return cuda_fail(e, "build_occupancy");
     for (int k = 0; k < 3; ++k) { c->occ_lo[k] = bounds[k]; c->occ_hi[k] = bounds[3 + k]; }
     return VKRT_OK;
+}
+
+// An upload / generate that failed half-way must not leave a context that claims a resident volume with null
+// arrays: drop whatever was installed, keep the error text.
+int volume_guard(VkrtContext* c, int rc) {
+    if (rc != VKRT_OK && c) {
+        const std::string keep = g_last_error;
+        cudaSetDevice(c->device);
+        free_volume(c);
+        g_last_error = keep;
+    }
+    return rc;
 }
 
 bool params_ok(const VkrtParams* p, std::string& why) {
@@ -389,22 +417,21 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     if (P.mode == VKRT_MODE_M1 && c->kind != VOL_SCALAR) return fail(VKRT_ERR_INVALID, "mode M1 needs a scalar volume (vkrt_upload_scalar)");
     int rc = ensure_layout(c);
     if (rc) return rc;
+    // a layout built just now was queued on c->stream: a launch on another stream must not overtake it
+    if (on && on != c->stream && c->layout_pending) CK(cudaStreamWaitEvent(on, c->ev_layout, 0));
     // Skipping is exact only when a transparent sample is a bit-exact no-op: for M0 that requires
-    // clear_color.a == 0 (raycast_compute.wgsl:89,91); otherwise fall back to the full march.
-    const bool skip = P.skip_empty && !(P.mode == VKRT_MODE_M0 && P.clear_color[3] != 0.0f);
+    // clear_color.a == 0 (raycast_compute.wgsl:89,91). And the reference tests `a >= threshold` only after
+    // compositing a sample (:92), so with initial_alpha >= alpha_threshold it stops after its FIRST sample, which a
+    // leap would pass over. Otherwise fall back to the full march.
+    const bool skip = P.skip_empty && !(P.mode == VKRT_MODE_M0 && P.clear_color[3] != 0.0f) && P.initial_alpha < P.alpha_threshold;
 
     RenderArgs A{};
     A.W = c->W; A.H = c->H;
     A.n_frames = n_frames;
-    {
-        static int use_cull = -1;  // VKRT_CULL=0 switches it off (A/B only)
-        if (use_cull < 0) { const char* e = getenv("VKRT_CULL"); use_cull = e ? atoi(e) != 0 : 1; }
-        for (int f = 0; f < n_frames; ++f) {
-            memcpy(A.inv[f], cam[f].inv_proj, sizeof A.inv[f]);
-            int centre_row;
-            cull_rect(A.inv[f], A.W, A.H, A.cull[f], &centre_row);
-            if (!use_cull) { A.cull[f][0] = A.cull[f][1] = -3.0e38f; A.cull[f][2] = A.cull[f][3] = 3.0e38f; }
-        }
+    for (int f = 0; f < n_frames; ++f) {
+        memcpy(A.inv[f], cam[f].inv_proj, sizeof A.inv[f]);
+        int centre_row;
+        cull_rect(A.inv[f], A.W, A.H, A.cull[f], &centre_row);
     }
     A.n_tiles = 0; A.tile_size = P.tile_size; A.offsets = nullptr;
     if (offsets && n > 0) {
@@ -435,19 +462,12 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     A.hx = A.fx / 2.0f; A.hy = A.fy / 2.0f; A.hz = A.fz / 2.0f;
     A.nbx = c->nbx; A.nby = c->nby; A.nbz = c->nbz;
     A.dist = c->dist;
-    {
-        static int lcm = -1;  // VKRT_LEAP_CLOSED_MIN overrides (exploration)
-        if (lcm < 0) { const char* e = getenv("VKRT_LEAP_CLOSED_MIN"); lcm = e ? atoi(e) : 64; }
-        A.leap_closed_min = lcm;
-    }
+    A.leap_closed_min = 64;  // shorter leaps replay their additions (profiles/r01_leap_threshold.md)
     // shrink leap regions by ~16 ulp of the largest voxel coordinate (rounding of p and q)
     A.leap_eps = 16.0f * 1.1920929e-07f * (float)(c->nx > c->ny ? (c->nx > c->nz ? c->nx : c->nz) : (c->ny > c->nz ? c->ny : c->nz));
     {
-        static int use_bb = -1;  // VKRT_BBOX=0 switches the clip off (A/B only)
-        if (use_bb < 0) { const char* e = getenv("VKRT_BBOX"); use_bb = e ? atoi(e) != 0 : 1; }
         const int n3[3] = {c->nx, c->ny, c->nz};
         for (int k = 0; k < 3; ++k) {
-            if (!use_bb) { A.bb_lo[k] = -3.0e38f; A.bb_hi[k] = 3.0e38f; continue; }
             if (c->occ_hi[0] < c->occ_lo[0]) { A.bb_lo[k] = 1.0f; A.bb_hi[k] = -1.0f; continue; }
             // voxel q = (p + 1) * n/2  ->  p = 2q/n - 1; one voxel of margin (float rounding is ~1e-4 of that)
             const double lo = (double)c->occ_lo[k] * 8.0 - 1.0, hi = std::min((double)(c->occ_hi[k] + 1) * 8.0, (double)n3[k]) + 1.0;
@@ -529,6 +549,7 @@ int vkrt_create(int device, int width, int height, VkrtContext** out_ctx) {
         if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) break;
         if ((e = cudaEventCreate(&c->ev_begin)) != cudaSuccess) break;
         if ((e = cudaEventCreate(&c->ev_end)) != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&c->ev_layout, cudaEventDisableTiming)) != cudaSuccess) break;
         for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
             e = cudaEventCreateWithFlags(&c->ev_slot_ready[i], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_slot_copied[i], cudaEventDisableTiming);
@@ -571,6 +592,7 @@ int vkrt_destroy(VkrtContext* c) {
         if (c->ev_group_ready[i]) cudaEventDestroy(c->ev_group_ready[i]);
         if (c->ev_group_copied[i]) cudaEventDestroy(c->ev_group_copied[i]);
     }
+    if (c->ev_layout) cudaEventDestroy(c->ev_layout);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -602,7 +624,7 @@ int vkrt_get_params(VkrtContext* c, VkrtParams* out) {
     return VKRT_OK;
 }
 
-int vkrt_upload_rgba16f(VkrtContext* c, const uint16_t* color, const uint16_t* normal, int nx, int ny, int nz) {
+static int upload_rgba16f_impl(VkrtContext* c, const uint16_t* color, const uint16_t* normal, int nx, int ny, int nz) {
     if (!c || !color || !normal) return fail(VKRT_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
@@ -621,7 +643,9 @@ int vkrt_upload_rgba16f(VkrtContext* c, const uint16_t* color, const uint16_t* n
     return VKRT_OK;
 }
 
-int vkrt_upload_scalar(VkrtContext* c, const void* data, int dtype, int nx, int ny, int nz) {
+int vkrt_upload_rgba16f(VkrtContext* c, const uint16_t* color, const uint16_t* normal, int nx, int ny, int nz) { return volume_guard(c, upload_rgba16f_impl(c, color, normal, nx, ny, nz)); }
+
+static int upload_scalar_impl(VkrtContext* c, const void* data, int dtype, int nx, int ny, int nz) {
     if (!c || !data) return fail(VKRT_ERR_INVALID, "NULL argument");
     if (dtype < VKRT_U8 || dtype > VKRT_F32) return fail(VKRT_ERR_INVALID, "unknown dtype");
     CK(cudaSetDevice(c->device));
@@ -641,7 +665,9 @@ int vkrt_upload_scalar(VkrtContext* c, const void* data, int dtype, int nx, int 
     return VKRT_OK;
 }
 
-int vkrt_generate_xor(VkrtContext* c, const VkrtUniform* un, int n, int which) {
+int vkrt_upload_scalar(VkrtContext* c, const void* data, int dtype, int nx, int ny, int nz) { return volume_guard(c, upload_scalar_impl(c, data, dtype, nx, ny, nz)); }
+
+static int generate_xor_impl(VkrtContext* c, const VkrtUniform* un, int n, int which) {
     if (!c || !un) return fail(VKRT_ERR_INVALID, "NULL argument");
     if (which < 0 || which > 1) return fail(VKRT_ERR_INVALID, "which must be 0 (noise_volume) or 1 (volume)");
     CK(cudaSetDevice(c->device));
@@ -657,7 +683,9 @@ int vkrt_generate_xor(VkrtContext* c, const VkrtUniform* un, int n, int which) {
     return build_occupancy(c);
 }
 
-int vkrt_generate_synthetic(VkrtContext* c, int kind, int dtype, int nx, int ny, int nz, uint32_t seed) {
+int vkrt_generate_xor(VkrtContext* c, const VkrtUniform* un, int n, int which) { return volume_guard(c, generate_xor_impl(c, un, n, which)); }
+
+static int generate_synthetic_impl(VkrtContext* c, int kind, int dtype, int nx, int ny, int nz, uint32_t seed) {
     if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
     if (kind < 0 || kind > 3) return fail(VKRT_ERR_INVALID, "kind must be 0 (noise fog), 1 (sparse blobs), 2 (smooth lattice) or 3 (thin smooth fog)");
     if (dtype < VKRT_U8 || dtype > VKRT_F32) return fail(VKRT_ERR_INVALID, "unknown dtype");
@@ -674,17 +702,20 @@ int vkrt_generate_synthetic(VkrtContext* c, int kind, int dtype, int nx, int ny,
     return build_occupancy(c);
 }
 
-int vkrt_scalar_to_rgba16f(VkrtContext* c) {
+int vkrt_generate_synthetic(VkrtContext* c, int kind, int dtype, int nx, int ny, int nz, uint32_t seed) { return volume_guard(c, generate_synthetic_impl(c, kind, dtype, nx, ny, nz, seed)); }
+
+static int scalar_to_rgba16f_impl(VkrtContext* c) {
     if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
     if (c->kind != VOL_SCALAR || c->windowed) return fail(VKRT_ERR_NO_VOLUME, "no (whole) scalar volume resident");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     const size_t bytes = (size_t)c->nx * c->ny * c->nz * 8;
     void *col = nullptr, *nrm = nullptr;
-    CK(cudaMalloc(&col, bytes));
-    CK(cudaMalloc(&nrm, bytes));
-    CK(launch_scalar_to_rgba16f(c->lin_a, c->dtype, (uint2*)col, (uint2*)nrm, c->nx, c->ny, c->nz, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    cudaError_t e = cudaMalloc(&col, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&nrm, bytes);
+    if (e == cudaSuccess) e = launch_scalar_to_rgba16f(c->lin_a, c->dtype, (uint2*)col, (uint2*)nrm, c->nx, c->ny, c->nz, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { cudaFree(col); cudaFree(nrm); return cuda_fail(e, "vkrt_scalar_to_rgba16f"); }
     const int nx = c->nx, ny = c->ny, nz = c->nz;
     free_volume(c);
     int rc = set_dims(c, nx, ny, nz);
@@ -694,6 +725,8 @@ int vkrt_scalar_to_rgba16f(VkrtContext* c) {
     c->kind = VOL_RGBA16F;
     return build_occupancy(c);
 }
+
+int vkrt_scalar_to_rgba16f(VkrtContext* c) { return volume_guard(c, scalar_to_rgba16f_impl(c)); }
 
 int vkrt_download_scalar(VkrtContext* c, void* out) {
     if (!c || !out) return fail(VKRT_ERR_INVALID, "NULL argument");
@@ -1210,6 +1243,9 @@ int fill_partial_args(VkrtContext* c, const VkrtCameraUniform* cam, PartialArgs&
     const VkrtParams& P = c->params;
     if ((P.mode == VKRT_MODE_M0) != (c->kind == VOL_RGBA16F)) return fail(VKRT_ERR_INVALID, "mode does not match the resident volume kind");
     if (P.mode == VKRT_MODE_M0 && P.clear_color[3] != 0.0f) return fail(VKRT_ERR_UNSUPPORTED, "sort-last needs clear_color.a == 0");
+    // the reference tests the threshold only after compositing a sample: with initial_alpha >= alpha_threshold it takes
+    // exactly one sample, which the per-brick leaps and the a_in >= threshold shortcut would drop
+    if (!(P.initial_alpha < P.alpha_threshold)) return fail(VKRT_ERR_UNSUPPORTED, "sort-last needs initial_alpha < alpha_threshold");
     memset(&A, 0, sizeof A);
     if (cam) memcpy(A.inv, cam->inv_proj, sizeof A.inv);
     A.W = c->W; A.H = c->H;
@@ -1274,7 +1310,7 @@ int build_window_occupancy(VkrtContext* c) {
 }
 }  // namespace
 
-int vkrt_upload_window(VkrtContext* c, const void* a, const void* b, int dtype, const int gn[3], const int own_lo[3], const int own_hi[3]) {
+static int upload_window_impl(VkrtContext* c, const void* a, const void* b, int dtype, const int gn[3], const int own_lo[3], const int own_hi[3]) {
     if (!c || !a || !gn || !own_lo || !own_hi) return fail(VKRT_ERR_INVALID, "NULL argument");
     if (dtype < -1 || dtype > VKRT_F32) return fail(VKRT_ERR_INVALID, "dtype must be -1 (rgba16f pair) or a VkrtDtype");
     if (dtype == -1 && !b) return fail(VKRT_ERR_INVALID, "rgba16f window needs both arrays");
@@ -1294,17 +1330,19 @@ int vkrt_upload_window(VkrtContext* c, const void* a, const void* b, int dtype, 
         void* lin = nullptr;
         const size_t padded = (size_t)((c->nx + 7) >> 3) * ((c->ny + 7) >> 3) * ((c->nz + 7) >> 3) * 512 * eb;
         CK(cudaMalloc(&lin, bytes));
-        CK(cudaMalloc(&c->lin_a, padded));
-        CK(cudaMemcpyAsync(lin, a, bytes, cudaMemcpyHostToDevice, c->stream));
-        cudaError_t e = launch_brick_window(lin, c->lin_a, (int)eb, c->nx, c->ny, c->nz, c->stream);
+        cudaError_t e = cudaMalloc(&c->lin_a, padded);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(lin, a, bytes, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = launch_brick_window(lin, c->lin_a, (int)eb, c->nx, c->ny, c->nz, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        cudaFree(lin);
-        if (e != cudaSuccess) return cuda_fail(e, "launch_brick_window");
+        cudaFree(lin);  // staging copy: released on every exit
+        if (e != cudaSuccess) return cuda_fail(e, "vkrt_upload_window: staging / bricking the window");
     }
     return build_window_occupancy(c);
 }
 
-int vkrt_generate_synthetic_window(VkrtContext* c, int kind, int dtype, const int gn[3], const int own_lo[3], const int own_hi[3], uint32_t seed) {
+int vkrt_upload_window(VkrtContext* c, const void* a, const void* b, int dtype, const int gn[3], const int own_lo[3], const int own_hi[3]) { return volume_guard(c, upload_window_impl(c, a, b, dtype, gn, own_lo, own_hi)); }
+
+static int generate_synthetic_window_impl(VkrtContext* c, int kind, int dtype, const int gn[3], const int own_lo[3], const int own_hi[3], uint32_t seed) {
     if (!c || !gn || !own_lo || !own_hi) return fail(VKRT_ERR_INVALID, "NULL argument");
     if (kind < 0 || kind > 3 || dtype < VKRT_U8 || dtype > VKRT_F32) return fail(VKRT_ERR_INVALID, "bad kind / dtype");
     CK(cudaSetDevice(c->device));
@@ -1317,6 +1355,8 @@ int vkrt_generate_synthetic_window(VkrtContext* c, int kind, int dtype, const in
     CK(launch_synth(c->lin_a, kind, dtype, c->nx, c->ny, c->nz, c->win_lo[0], c->win_lo[1], c->win_lo[2], gn[0], gn[1], gn[2], seed, c->stream, 1));
     return build_window_occupancy(c);
 }
+
+int vkrt_generate_synthetic_window(VkrtContext* c, int kind, int dtype, const int gn[3], const int own_lo[3], const int own_hi[3], uint32_t seed) { return volume_guard(c, generate_synthetic_window_impl(c, kind, dtype, gn, own_lo, own_hi, seed)); }
 
 int vkrt_window_info(VkrtContext* c, int win_lo[3], int win_n[3]) {
     if (!c || !c->windowed) return fail(VKRT_ERR_INVALID, "no windowed volume resident");

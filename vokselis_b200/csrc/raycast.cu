@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
         const VkrtOffset o = A.offsets[blockIdx.z];
         offx = o.x;
         offy = o.y;
-        px = gx + (uint32_t)__float2int_rz(offx);
-        py = gy + (uint32_t)__float2int_rz(offy);
+        px = gx + __float2uint_rz(offx);  // vec2<u32>(f32) saturates: a negative offset stores at gid + 0
+        py = gy + __float2uint_rz(offy);
         valid = gx < (uint32_t)A.tile_size && gy < (uint32_t)A.tile_size;
     }
     valid = valid && px < (uint32_t)A.W && py < (uint32_t)A.H;  // out-of-range textureStore is dropped
@@ -363,16 +363,9 @@ cudaError_t launch3(const RenderArgs& A, dim3 grid, dim3 block, cudaStream_t s, 
 }  // namespace
 
 cudaError_t launch_raycast(const RenderArgs& A, int mode, int layout, int dtype, bool skip, bool dbg, cudaStream_t s) {
-    // Block = bw x bh pixels; blockDim.x = 8 makes every warp an 8x4-pixel tile. VKRT_BLOCK=WxH overrides
-    // (exploration only; W*H must be a multiple of 32 and <= 256).
-    static int bw = 0, bh = 0;
-    if (bw == 0) {
-        bw = 8; bh = 16;  // 8x16: measured best on B200 (profiles/r01_blockshape.md); warps stay 8x4-pixel tiles
-        if (const char* e = getenv("VKRT_BLOCK")) {
-            int w = 0, h = 0;
-            if (sscanf(e, "%dx%d", &w, &h) == 2 && w > 0 && h > 0 && (w * h) % 32 == 0 && w * h <= 256) { bw = w; bh = h; }
-        }
-    }
+    // Block = 8x16 pixels: blockDim.x = 8 makes every warp an 8x4-pixel tile; measured best on B200
+    // (profiles/r01_blockshape.md).
+    const int bw = 8, bh = 16;
     const dim3 block((unsigned)bw, (unsigned)bh, 1);
     dim3 grid;
     if (A.n_tiles > 0) {

@@ -82,7 +82,7 @@ cudaError_t launch_raycast(const RenderArgs& A, int mode, int layout, int dtype,
 cudaError_t launch_interleave_bricked(const uint2* color, const uint2* normal, uint4* out, int nx, int ny, int nz,
                                       int nbx, int nby, int nbz, cudaStream_t s);
 // dist: one byte per brick, built in two steps: occupancy (0 / 255) then the Chebyshev distance transform
-cudaError_t launch_occupancy_m0(const uint2* color, int nx, int ny, int nz, int nbx, int nby, int nbz, uint8_t* dist,
+cudaError_t launch_occupancy_m0(const uint2* color, const uint2* normal, int nx, int ny, int nz, int nbx, int nby, int nbz, uint8_t* dist,
                                 cudaStream_t s);
 cudaError_t launch_occupancy_m1(const void* scalar, int dtype, int nx, int ny, int nz, int nbx, int nby, int nbz,
                                 uint8_t* dist, cudaStream_t s);

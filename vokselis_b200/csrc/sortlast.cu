@@ -310,8 +310,8 @@ __global__ void __launch_bounds__(256) window_occupancy_kernel(const PartialArgs
         const size_t row = MODE == VKRT_MODE_M0 ? ((size_t)(iz - A.wz) * A.ny + (iy - A.wy)) * A.nx : part_z(A, iz - A.wz) + part_y(A, iy - A.wy);
         for (int ix = x0; ix <= x1; ++ix) {
             if (MODE == VKRT_MODE_M0) {
-                const float a = unpack_rgba16f(__ldg(reinterpret_cast<const uint2*>(A.vol_a) + row + (ix - A.wx))).w;
-                any = any || (m0_alpha(a) != 0.0f);
+                const size_t i = row + (ix - A.wx);
+                any = any || !m0_texel_skippable(__ldg(reinterpret_cast<const uint2*>(A.vol_a) + i), __ldg(reinterpret_cast<const uint2*>(A.vol_b) + i));
             } else {
                 const float v = win_load<DTYPE>(A.vol_a, row + part_x(A, ix - A.wx)) * (DTYPE == VKRT_U8 ? 1.0f / 255.0f : 1.0f);
                 any = any || !(v <= 0.0999999f);

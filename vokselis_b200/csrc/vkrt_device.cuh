@@ -185,10 +185,24 @@ __device__ __forceinline__ float m0_alpha(float ca) {
     return VKRT_SMOOTHSTEP(0.0f, 0.7f, a3);
 }
 
+// A texel a sample may be skipped over (exact empty-space skipping): per-sample alpha exactly 0 AND
+// nothing non-finite that 0 * (.) would turn into NaN in the full march — colour inf/NaN, normal +-inf (NaN normals
+// are harmless: every use goes through fmaxf / __saturatef, and the generator fills empty space with them).
+__device__ __forceinline__ bool m0_texel_skippable(uint2 c, uint2 n) {
+    const float a = __half2float(__ushort_as_half((unsigned short)(c.y >> 16)));
+    if (m0_alpha(a) != 0.0f) return false;
+    const uint32_t cx = c.x & 0x7C00u, cy = (c.x >> 16) & 0x7C00u, cz = c.y & 0x7C00u;
+    if (cx == 0x7C00u || cy == 0x7C00u || cz == 0x7C00u) return false;
+    const uint32_t nx = n.x & 0x7FFFu, ny = (n.x >> 16) & 0x7FFFu, nz = n.y & 0x7FFFu;
+    return !(nx == 0x7C00u || ny == 0x7C00u || nz == 0x7C00u);
+}
+
 __device__ __forceinline__ void m0_shade(Rgba& col, float4 c, float4 n, f3 p, const float* clear) {
     const float kL = 0.33333334f;  // normalize(-2,-2,-1) = (-2/3, -2/3, -1/3)
     const float kP = 0.57735026f;  // normalize(1,1,-1) = (1,1,-1)/sqrt(3)
-    const float shade_s = fmaxf(0.0f, -n.y);  // dot((0,-1,0), n); fmaxf drops NaN
+    // dot((0,-1,0), n) summed like the oracle, (0*n.x + -1*n.y) + 0*n.z: a non-finite n.x or n.z makes it NaN, which
+    // fmaxf drops (raycast_compute.wgsl:74 on golden G2's inf normals)
+    const float shade_s = fmaxf(0.0f, __fadd_rn(__fsub_rn(__fmul_rn(0.0f, n.x), n.y), __fmul_rn(0.0f, n.z)));
     const float vol_alpha = m0_alpha(c.w);
     const float ndl = fmaxf(fmaf(-kL, n.z, fmaf(-2.0f * kL, n.y, __fmul_rn(-2.0f * kL, n.x))), 0.0f);
     const float pd = VKRT_SMOOTHSTEP(0.3f, 1.5f, fmaf(-kP, p.z, fmaf(kP, p.y, __fmul_rn(kP, p.x))));

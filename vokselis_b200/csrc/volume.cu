@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) interleave_bricked_kernel(const uint2* __
 }
 
 // one warp per brick
-__global__ void __launch_bounds__(256) occupancy_m0_kernel(const uint2* __restrict__ color, int nx, int ny, int nz, int nbx, int nby,
+__global__ void __launch_bounds__(256) occupancy_m0_kernel(const uint2* __restrict__ color, const uint2* __restrict__ normal, int nx, int ny, int nz, int nbx, int nby,
                                                            int nbz, uint8_t* __restrict__ dist) {
     const uint32_t cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t lane = threadIdx.x & 31u;
@@ -47,9 +47,8 @@ __global__ void __launch_bounds__(256) occupancy_m0_kernel(const uint2* __restri
     for (int k = (int)lane; k < 512; k += 32) {
         const int ix = bx * 8 + (k & 7), iy = by * 8 + ((k >> 3) & 7), iz = bz * 8 + (k >> 6);
         if (ix < nx && iy < ny && iz < nz) {
-            const uint2 c = __ldg(color + ((size_t)iz * ny + iy) * nx + ix);
-            const float a = unpack_rgba16f(c).w;
-            any = any || (m0_alpha(a) != 0.0f);  // the very function the march uses
+            const size_t i = ((size_t)iz * ny + iy) * nx + ix;
+            any = any || !m0_texel_skippable(__ldg(color + i), __ldg(normal + i));  // alpha through the very function the march uses
         }
     }
     any = __any_sync(0xffffffffu, any);
@@ -420,9 +419,9 @@ cudaError_t launch_interleave_bricked(const uint2* color, const uint2* normal, u
     return cudaGetLastError();
 }
 
-cudaError_t launch_occupancy_m0(const uint2* color, int nx, int ny, int nz, int nbx, int nby, int nbz, uint8_t* dist, cudaStream_t s) {
+cudaError_t launch_occupancy_m0(const uint2* color, const uint2* normal, int nx, int ny, int nz, int nbx, int nby, int nbz, uint8_t* dist, cudaStream_t s) {
     const size_t cells = (size_t)nbx * nby * nbz;
-    occupancy_m0_kernel<<<(unsigned)((cells + 7) / 8), 256, 0, s>>>(color, nx, ny, nz, nbx, nby, nbz, dist);
+    occupancy_m0_kernel<<<(unsigned)((cells + 7) / 8), 256, 0, s>>>(color, normal, nx, ny, nz, nbx, nby, nbz, dist);
     return cudaGetLastError();
 }
 
