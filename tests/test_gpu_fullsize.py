@@ -1,7 +1,11 @@
-"""BASELINE.json's configurations at FULL size on the GPU, checked through size-independent properties
-(the oracle would need minutes to hours for these): exact empty-space skipping == full march, `tile` over
-the reference's offset table == `single`, frame-to-frame determinism, LINEAR == GATHER within the parity
-tolerance, and reference-semantics sample counts independent of skipping."""
+"""BASELINE.json's configurations at FULL size on the GPU, checked through size-independent properties: exact
+empty-space skipping == full march, `tile` over the reference's offset table == `single`, frame-to-frame
+determinism, LINEAR == GATHER within the parity tolerance, and reference-semantics sample counts independent of
+skipping. configs[0] and configs[1] (256^3 at 1280x720 / 1920x1080) are ALSO compared with the oracle directly at
+their own size in tests/test_gpu_baseline_size.py (a frame costs the oracle about a second); for configs[2]/[3]
+(1024^3 fp16, 2048^3 u8 at 3840x2160: 2-8 GiB volumes, ~10^9 samples per frame) the oracle comparison runs on the
+same generators at reduced size (test_gpu_parity.py::test_synthetic_configs_small_match_oracle) and the full size
+is covered by the properties below."""
 import numpy as np
 import pytest
 

@@ -200,8 +200,11 @@ def test_m1_exact_paths_match_oracle(rt, oracle, xor_cam, dtype, skip, layout):
         ctx.present()
         got8, aux, st = ctx.readback_rgba8(), ctx.readback_aux(), ctx.stats()
     assert np.array_equal(aux >> 31, ref_aux >> 31), "ray-hit mask differs"
-    mism = (aux != ref_aux).mean()
-    assert mism <= 1e-3, f"iteration counts differ on {mism:.2%} of pixels"
+    # the sample value differs from the oracle's in the last ulp (tap normalisation, reciprocal instead of division in
+    # smoothstep), which can move the 0.95 crossing by ONE sample on a rare ray — never by more
+    dd = aux.astype(np.int64) - ref_aux.astype(np.int64)
+    mism = (dd != 0).mean()
+    assert mism <= 1e-3 and np.abs(dd).max() <= 1, f"iteration counts differ on {mism:.2%} of pixels, max |diff| {np.abs(dd).max()}"
     assert st.rays_hit == ref_st.rays_hit
     if skip:
         assert st.samples_fetched < st.samples_reference
@@ -230,7 +233,8 @@ def test_synthetic_configs_small_match_oracle(rt, oracle, kind, dtype, n):
     p.dt_scale = 2.0
     ref, ref_aux, _ = oracle.render(p, cam, W, H, scalar=vol)
     assert np.array_equal(aux >> 31, ref_aux >> 31)
-    assert (aux != ref_aux).mean() <= 1e-3
+    dd = aux.astype(np.int64) - ref_aux.astype(np.int64)
+    assert (dd != 0).mean() <= 1e-3 and np.abs(dd).max() <= 1, f"iteration counts: {(dd != 0).mean():.2%} differ, max |diff| {np.abs(dd).max()}"
     check_images(got8, oracle.present(ref))
 
 
