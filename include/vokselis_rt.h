@@ -95,8 +95,11 @@ typedef enum VkrtLayout {
     VKRT_LAYOUT_LINEAR = 0,  /* as uploaded: x fastest, then y, then z */
     VKRT_LAYOUT_BRICKED = 1, /* cache-line bricks, see DESIGN.md */
     VKRT_LAYOUT_TEXTURE = 2, /* cudaArray + tex3D */
-    VKRT_LAYOUT_GATHER = 3   /* M1 only: layered cudaArray + two tld4 gathers per sample (the 8 taps in 2 texture
+    VKRT_LAYOUT_GATHER = 3,  /* M1 only: layered cudaArray + two tld4 gathers per sample (the 8 taps in 2 texture
                                 instructions), fp32 interpolation weights in the SM: exact like LINEAR */
+    VKRT_LAYOUT_QUAD = 4     /* M1 only: 3-D cudaArray whose texel (x+1, y+1, z) holds the pre-gathered 2x2 xy footprint
+                                v(x..x+1, y..y+1, z) (clamp-to-edge baked in); two tex3D POINT fetches per sample return
+                                the 8 taps, fp32 weights in the SM: exact like LINEAR, 4x the volume's memory */
 } VkrtLayout;
 
 /* Everything the reference hard-codes as a WGSL literal or Rust const on this path. Defaults

@@ -122,3 +122,100 @@ def test_long_leap_from_a_small_t_does_not_wrap():
                 ref = np.float32(ref + dt)
             assert leap_t(t0, dt, n).view(np.uint32) == ref.view(np.uint32)
             assert leap_cached(t0, dt, n, [0xFFFFFFFF, 0xFFFFFFFF]).view(np.uint32) == ref.view(np.uint32)
+
+
+# ---- leap_steps (vkrt_device.cuh): cached increment, tie binades in closed form, no integer division ---------------
+def binade_inc2(e, dt):
+    db = int(np.float32(dt).view(np.uint32))
+    ed, shift = db >> 23, e - (db >> 23)
+    if shift < 0 or shift > 24 or ed == 0 or e == 0:
+        return 0xFFFFFFFF
+    M = (db & 0x7FFFFF) | 0x800000
+    if shift == 0:
+        return M
+    m, rem, half = M >> shift, M & ((1 << shift) - 1), 1 << (shift - 1)
+    if rem == half:
+        return 0x80000000 | (m + (m & 1))
+    return m + (1 if rem > half else 0)
+
+
+def leap_steps(t, dt, n, cache, stats=None):
+    t, dt = np.float32(t), np.float32(dt)
+    tb = int(t.view(np.uint32))
+    e = tb >> 23
+    if e == cache[0] and cache[1] < 0x80000000:
+        nb = tb + n * cache[1]
+        if (nb >> 23) == e:
+            if stats is not None:
+                stats["fast"] = stats.get("fast", 0) + 1
+            return np.uint32(nb).view(np.float32)
+    while True:
+        tb = int(t.view(np.uint32))
+        e = tb >> 23
+        if e != cache[0]:
+            cache[0], cache[1] = e, binade_inc2(e, dt)
+        inc = cache[1]
+        closed = inc != 0xFFFFFFFF and not ((inc >> 31) and (tb & 1))
+        if closed:
+            inc &= 0x7FFFFFFF
+            nb = tb + n * inc
+            if (nb >> 23) == e:
+                return np.uint32(nb).view(np.float32)
+            room = (((e + 1) << 23) - 1) - tb
+            m = int(np.float32(np.float32(room) / np.float32(inc))) - 1  # (__fdividef: within 2 ulp; the verify below covers it)
+            if m >= 1 and m < n and m * inc <= room:
+                t = np.uint32(tb + m * inc).view(np.float32)
+                n -= m
+        t = np.float32(t + dt)
+        if stats is not None:
+            stats["real"] = stats.get("real", 0) + 1
+        n -= 1
+        if n == 0:
+            return t
+
+
+def _tie_dt(rng, t_binade_exp):
+    """A dt that is an exact tie ((m + 1/2) ulp) in the binade 2^t_binade_exp."""
+    shift = int(rng.integers(1, 12))
+    M = (int(rng.integers(0x800000, 0x1000000)) >> shift << shift) | (1 << (shift - 1))
+    return np.uint32(((127 + t_binade_exp - shift) << 23) | (M & 0x7FFFFF)).view(np.float32)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_leap_steps_equals_repeated_addition(seed):
+    rng = np.random.default_rng(500 + seed)
+    stats = {}
+    for case in range(60):
+        t = ref = np.float32(rng.uniform(0, 5) if rng.uniform() < 0.75 else (0.0 if rng.uniform() < 0.5 else rng.uniform(0, 0.05)))
+        r = rng.uniform()
+        if r < 0.3:
+            dt = np.float32(0.01)
+        elif r < 0.6:
+            dt = _tie_dt(rng, int(rng.integers(0, 3)))  # exact ties somewhere in t's range [1, 8)
+        else:
+            dt = np.float32(10 ** rng.uniform(-4, -1.5))
+        cache = [0xFFFFFFFF, 0xFFFFFFFF]
+        for _ in range(14):
+            n = int(rng.integers(1, 12)) if rng.uniform() < 0.7 else int(rng.integers(12, 900))
+            for _ in range(n):
+                ref = np.float32(ref + dt)
+            t = leap_steps(t, dt, n, cache, stats)
+            assert t.view(np.uint32) == ref.view(np.uint32), (case, t, ref, dt, n)
+            if rng.uniform() < 0.6:
+                t = ref = np.float32(ref + dt)  # an ordinary sample step in between
+    assert stats.get("fast", 0) > 100  # the one-multiply-add path carries most leaps
+
+
+def test_leap_steps_tie_binade_is_closed_form():
+    """dt = 0.0078125 * 1.5 = (m + 1/2) ulp for t in [2, 4) with a suitable mantissa: the run must not fall back to one real
+    addition per step."""
+    rng = np.random.default_rng(7)
+    dt = _tie_dt(rng, 1)
+    for t0 in (np.float32(2.0), np.float32(2.0000002), np.float32(3.1)):
+        stats, cache = {}, [0xFFFFFFFF, 0xFFFFFFFF]
+        ref = t0
+        for _ in range(60):
+            ref = np.float32(ref + dt)
+        got = leap_steps(t0, dt, 60, cache, stats)
+        assert got.view(np.uint32) == ref.view(np.uint32)
+        assert stats.get("real", 0) <= 3

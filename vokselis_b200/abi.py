@@ -10,7 +10,7 @@ import ctypes as C
 
 MODE_M0, MODE_M1 = 0, 1
 DTYPE_U8, DTYPE_F16, DTYPE_F32 = 0, 1, 2
-LAYOUT_LINEAR, LAYOUT_BRICKED, LAYOUT_TEXTURE, LAYOUT_GATHER = 0, 1, 2, 3
+LAYOUT_LINEAR, LAYOUT_BRICKED, LAYOUT_TEXTURE, LAYOUT_GATHER, LAYOUT_QUAD = 0, 1, 2, 3, 4
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_VOLUME, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 

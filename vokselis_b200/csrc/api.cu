@@ -90,8 +90,8 @@ struct VkrtContext {
     void* lin_a = nullptr;  // rgba16f colour | scalar grid (upload layout)
     void* lin_b = nullptr;  // rgba16f normal
     uint4* bricked = nullptr;
-    cudaArray_t arr_a = nullptr, arr_b = nullptr, arr_g = nullptr;
-    cudaTextureObject_t tex_a = 0, tex_b = 0, tex_g = 0;  // tex_g: layered + gather (LAYOUT_GATHER)
+    cudaArray_t arr_a = nullptr, arr_b = nullptr, arr_g = nullptr, arr_q = nullptr;
+    cudaTextureObject_t tex_a = 0, tex_b = 0, tex_g = 0, tex_q = 0;  // tex_g: layered + gather (LAYOUT_GATHER); tex_q: pre-gathered quads (LAYOUT_QUAD)
     uint8_t* dist = nullptr;  // brick distance field (0 = occupied)
     int occ_lo[3] = {0, 0, 0}, occ_hi[3] = {-1, -1, -1};  // bounding box of the occupied bricks (inclusive); hi < lo = none
     // brick-partitioned (sort-last) state: the resident volume is a window of a larger global grid
@@ -112,9 +112,11 @@ void free_layouts(VkrtContext* c) {
     if (c->tex_a) cudaDestroyTextureObject(c->tex_a);
     if (c->tex_b) cudaDestroyTextureObject(c->tex_b);
     if (c->tex_g) cudaDestroyTextureObject(c->tex_g);
+    if (c->tex_q) cudaDestroyTextureObject(c->tex_q);
     if (c->arr_g) cudaFreeArray(c->arr_g);
-    c->tex_g = 0;
-    c->arr_g = nullptr;
+    if (c->arr_q) cudaFreeArray(c->arr_q);
+    c->tex_g = c->tex_q = 0;
+    c->arr_g = c->arr_q = nullptr;
     if (c->arr_a) cudaFreeArray(c->arr_a);
     if (c->arr_b) cudaFreeArray(c->arr_b);
     if (c->bricked) cudaFree(c->bricked);
@@ -226,7 +228,7 @@ int build_layout(VkrtContext* c) {
     const int layout = c->params.layout;
     if (layout == VKRT_LAYOUT_LINEAR) return VKRT_OK;
     if (c->kind == VOL_RGBA16F) {
-        if (layout == VKRT_LAYOUT_GATHER) return fail(VKRT_ERR_UNSUPPORTED, "layout GATHER is for scalar volumes (mode M1)");
+        if (layout == VKRT_LAYOUT_GATHER || layout == VKRT_LAYOUT_QUAD) return fail(VKRT_ERR_UNSUPPORTED, "layouts GATHER and QUAD are for scalar volumes (mode M1)");
         if (layout == VKRT_LAYOUT_BRICKED && !c->bricked) {
             const size_t total = (size_t)c->nbx * c->nby * c->nbz * 512;
             CK(cudaMalloc(&c->bricked, total * sizeof(uint4)));
@@ -282,14 +284,35 @@ int build_layout(VkrtContext* c) {
         }
         return VKRT_OK;
     }
+    if (layout == VKRT_LAYOUT_QUAD) {
+        if (!c->tex_q) {
+            cudaChannelFormatDesc d;
+            size_t eb;
+            if (c->dtype == VKRT_U8) { d = cudaCreateChannelDesc<uchar4>(); eb = 1; }
+            else if (c->dtype == VKRT_F16) { d = cudaCreateChannelDescHalf4(); eb = 2; }
+            else { d = cudaCreateChannelDesc<float4>(); eb = 4; }
+            const int qx = c->nx + 1, qy = c->ny + 1;
+            void* stage = nullptr;
+            CK(cudaMalloc(&stage, (size_t)qx * qy * c->nz * 4 * eb));
+            cudaError_t e = launch_pregather_quads(c->lin_a, c->dtype, stage, c->nx, c->ny, c->nz, c->stream);
+            if (e == cudaSuccess) e = cudaMalloc3DArray(&c->arr_q, &d, make_cudaExtent((size_t)qx, (size_t)qy, (size_t)c->nz));
+            int rc = e == cudaSuccess ? copy_to_array(c->arr_q, stage, 4 * eb, qx, qy, c->nz, c->stream) : cuda_fail(e, "LAYOUT_QUAD staging");
+            if (rc == VKRT_OK && (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) rc = cuda_fail(e, "LAYOUT_QUAD staging");
+            cudaFree(stage);
+            if (rc) return rc;
+            rc = make_texture(c->arr_q, false, false, c->dtype == VKRT_U8, &c->tex_q);  // point filter, clamp-to-edge (z), unorm8 -> float in hardware
+            if (rc) return rc;
+        }
+        return VKRT_OK;
+    }
     return fail(VKRT_ERR_UNSUPPORTED, "layout BRICKED is not available for scalar volumes");
 }
 
 int ensure_layout(VkrtContext* c) {
-    const void* before[3] = {c->bricked, (const void*)c->tex_a, (const void*)c->tex_g};
+    const void* before[4] = {c->bricked, (const void*)c->tex_a, (const void*)c->tex_g, (const void*)c->tex_q};
     const int rc = build_layout(c);
     if (rc) return rc;
-    if (before[0] != c->bricked || before[1] != (const void*)c->tex_a || before[2] != (const void*)c->tex_g) {
+    if (before[0] != c->bricked || before[1] != (const void*)c->tex_a || before[2] != (const void*)c->tex_g || before[3] != (const void*)c->tex_q) {
         CK(cudaEventRecord(c->ev_layout, c->stream));
         c->layout_pending = true;
     }
@@ -340,7 +363,7 @@ bool params_ok(const VkrtParams* p, std::string& why) {
     if (!p) { why = "params is NULL"; return false; }
     if (p->struct_size != sizeof(VkrtParams)) { why = "VkrtParams.struct_size mismatch"; return false; }
     if (p->mode != VKRT_MODE_M0 && p->mode != VKRT_MODE_M1) { why = "unknown mode"; return false; }
-    if (p->layout < VKRT_LAYOUT_LINEAR || p->layout > VKRT_LAYOUT_GATHER) { why = "unknown layout"; return false; }
+    if (p->layout < VKRT_LAYOUT_LINEAR || p->layout > VKRT_LAYOUT_QUAD) { why = "unknown layout"; return false; }
     if (!(p->dt_scale > 0.0f)) { why = "dt_scale must be > 0"; return false; }
     if (!(p->dt_floor >= 0.0f)) { why = "dt_floor must be >= 0"; return false; }
     if (p->tile_size <= 0 || p->tile_size > 16384) { why = "tile_size out of range"; return false; }
@@ -456,13 +479,12 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     } else {
         A.vol_a = c->lin_a;
     }
-    A.tex_a = (layout == VKRT_LAYOUT_GATHER) ? c->tex_g : c->tex_a; A.tex_b = c->tex_b;
+    A.tex_a = layout == VKRT_LAYOUT_GATHER ? c->tex_g : (layout == VKRT_LAYOUT_QUAD ? c->tex_q : c->tex_a); A.tex_b = c->tex_b;
     A.nx = c->nx; A.ny = c->ny; A.nz = c->nz;
     A.fx = (float)c->nx; A.fy = (float)c->ny; A.fz = (float)c->nz;
     A.hx = A.fx / 2.0f; A.hy = A.fy / 2.0f; A.hz = A.fz / 2.0f;
     A.nbx = c->nbx; A.nby = c->nby; A.nbz = c->nbz;
     A.dist = c->dist;
-    A.leap_closed_min = 64;  // shorter leaps replay their additions (profiles/r01_leap_threshold.md)
     // shrink leap regions by ~16 ulp of the largest voxel coordinate (rounding of p and q)
     A.leap_eps = 16.0f * 1.1920929e-07f * (float)(c->nx > c->ny ? (c->nx > c->nz ? c->nx : c->nz) : (c->ny > c->nz ? c->ny : c->nz));
     {

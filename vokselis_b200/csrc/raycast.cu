@@ -116,6 +116,14 @@ __device__ __forceinline__ float m1_sample(const RenderArgs& A, float qx, float 
         const float4 g1 = tld4_layer(A.tex_a, zb, flx + 1.0f, fly + 1.0f);
         return lerp3(g0.w, g0.z, g0.x, g0.y, g1.w, g1.z, g1.x, g1.y, fx, fy, fz);
     }
+    if (LAYOUT == VKRT_LAYOUT_QUAD) {
+        // Texel (x0+1, y0+1, z) holds the pre-gathered 2x2 xy footprint v(x0..x0+1, y0..y0+1, z) with clamp-to-edge baked
+        // in (volume.cu pregather_quads_kernel); z clamps through the texture's address mode. Two POINT fetches of a 3-D
+        // texture return the 8 taps; no gather footprint, 3-D tiled locality across layers.
+        const float4 g0 = tex3D<float4>(A.tex_a, flx + 1.5f, fly + 1.5f, flz + 0.5f);
+        const float4 g1 = tex3D<float4>(A.tex_a, flx + 1.5f, fly + 1.5f, flz + 1.5f);
+        return lerp3(g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, fx, fy, fz);
+    }
     const int x0 = (int)flx, y0 = (int)fly, z0 = (int)flz;
     // clamp-to-edge on both taps, like the oracle's scalar_at()
     const int xa2 = min(max(x0, 0), A.nx - 1), xb2 = min(max(x0 + 1, 0), A.nx - 1);
@@ -251,11 +259,8 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
                             ++iters;
                             t = xadd(t, dt);
                         }
-                    } else if (n0 >= A.leap_closed_min) {
-                        t = leap_cached(t, dt, n0, lc);
-                    } else {  // measured faster than the closed form at these lengths (profiles/r01_bounds_clip.md)
-#pragma unroll 4
-                        for (int j = 0; j < n0; ++j) t = xadd(t, dt);
+                    } else {
+                        t = leap_steps(t, dt, n0, lc);
                     }
                 }
             }
@@ -284,11 +289,8 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
                             ++iters;
                             t = xadd(t, dt);
                         }
-                    } else if (n >= A.leap_closed_min) {
-                        t = leap_cached(t, dt, n, lc);  // closed form, bit-identical to n additions
                     } else {
-#pragma unroll 4
-                        for (int j = 0; j < n; ++j) t = xadd(t, dt);
+                        t = leap_steps(t, dt, n, lc);  // closed form, bit-identical to n additions
                     }
                     continue;
                 }
@@ -382,6 +384,7 @@ cudaError_t launch_raycast(const RenderArgs& A, int mode, int layout, int dtype,
     } else {
         if (layout == VKRT_LAYOUT_TEXTURE) return launch3<VKRT_MODE_M1, VKRT_LAYOUT_TEXTURE, 0>(A, grid, block, s, skip, dbg);
         if (layout == VKRT_LAYOUT_GATHER) return launch3<VKRT_MODE_M1, VKRT_LAYOUT_GATHER, 0>(A, grid, block, s, skip, dbg);
+        if (layout == VKRT_LAYOUT_QUAD) return launch3<VKRT_MODE_M1, VKRT_LAYOUT_QUAD, 0>(A, grid, block, s, skip, dbg);
         if (layout == VKRT_LAYOUT_LINEAR) {
             switch (dtype) {
                 case VKRT_U8: return launch3<VKRT_MODE_M1, VKRT_LAYOUT_LINEAR, VKRT_U8>(A, grid, block, s, skip, dbg);

@@ -35,7 +35,6 @@ struct RenderArgs {
     // Bounding box of the occupied bricks, grown by one voxel, in the box's own coordinates ([-1,1]^3): every
     // sample outside it is a no-op. bb_lo[0] > bb_hi[0] = nothing is occupied.
     float bb_lo[3], bb_hi[3];
-    int leap_closed_min;  // leaps of at least this many samples use the closed-form advance (leap_t)
     // parameters (VkrtParams)
     float dt_scale, dt_floor, alpha_threshold, initial_alpha;
     float clear[4];
@@ -88,6 +87,7 @@ cudaError_t launch_occupancy_m1(const void* scalar, int dtype, int nx, int ny, i
                                 uint8_t* dist, cudaStream_t s);
 cudaError_t launch_occupied_bounds(const uint8_t* dist, int nbx, int nby, int nbz, int* d_out6, cudaStream_t s);
 cudaError_t launch_distance_transform(uint8_t* dist, uint8_t* scratch, int nbx, int nby, int nbz, int border, int max_d, cudaStream_t s);
+cudaError_t launch_pregather_quads(const void* vol, int dtype, void* out_texels, int nx, int ny, int nz, cudaStream_t s);
 cudaError_t launch_generate_xor(uint2* color, uint2* normal, int n, float time, int which, cudaStream_t s);
 
 cudaError_t launch_scalar_to_rgba16f(const void* vol, int dtype, uint2* color, uint2* normal, int nx, int ny, int nz, cudaStream_t s);

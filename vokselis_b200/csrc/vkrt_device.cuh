@@ -130,33 +130,63 @@ __device__ __forceinline__ float advance_t(float t, float dt, int n) {
     return t;
 }
 
-// Fast path of advance_t for the common case — the whole run stays inside t's binade and dt is not an exact tie
-// there — with the per-binade increment kept in registers across the leaps of one ray (a ray crosses one or two
-// binades of t): shift, compare, one wide multiply-add (64 bits: n * inc can exceed 2^32 and must not wrap back
-// into the binade), compare. Bit-identical to n repeated additions either way. inc == 0xffffffff marks
-// "no closed form in this binade" (t below dt's binade, dt < ulp(t)/2, an exact tie, subnormals): with it the
-// binade check below always fails and advance_t takes over.
+// leap_steps: the same result — t after n additions t = fl(t + dt), bit for bit — for the raycast loop, where a ray
+// leaps many times (short leaps mostly) and crosses one or two binades of t inside the volume:
+//  * the per-binade increment is cached in registers across the leaps of a ray (LeapCache);
+//  * a leap that stays inside t's binade is ONE 64-bit multiply-add on the bit pattern (n * inc can exceed 2^32 and
+//    must not wrap back into the binade) and a compare;
+//  * a leap that reaches the end of the binade takes as many steps as provably stay inside (quotient by a float
+//    reciprocal, one below the estimate, verified in integers — no integer division), then real additions across
+//    the boundary, then goes on in the next binade;
+//  * an exact tie (dt = (m + 1/2) ulp(t)) rounds to even: from an even significand every step adds the even one of
+//    {m, m+1}, so after at most one real addition the closed form applies there too;
+//  * t below dt's binade, subnormals: real additions.
+// cache.inc: < 2^24 = increment; bit 31 set = tie binade (low bits: the even increment); 0xffffffff = no closed form.
 struct LeapCache {
     uint32_t e, inc;  // biased exponent the increment was derived for (0xffffffff = none yet)
 };
 __device__ __forceinline__ uint32_t binade_inc(uint32_t e, float dt) {
     const uint32_t db = __float_as_uint(dt), ed = db >> 23;
     const int shift = (int)e - (int)ed;
-    if (shift < 1 || shift > 24 || ed == 0u) return 0xffffffffu;
+    if (shift < 0 || shift > 24 || ed == 0u || e == 0u) return 0xffffffffu;
     const uint32_t M = (db & 0x7fffffu) | 0x800000u;
-    const uint32_t rem = M & ((1u << shift) - 1u), half = 1u << (shift - 1);
-    if (rem == half) return 0xffffffffu;
-    return (M >> shift) + (rem > half ? 1u : 0u);  // >= 1 for shift <= 24
+    if (shift == 0) return M;
+    const uint32_t m = M >> shift, rem = M & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    if (rem == half) return 0x80000000u | (m + (m & 1u));
+    return m + (rem > half ? 1u : 0u);  // >= 1 for shift <= 24
 }
-__device__ __forceinline__ float leap_cached(float t, float dt, int n, LeapCache& c) {
-    const uint32_t tb = __float_as_uint(t), e = tb >> 23;  // t >= 0
-    if (e != c.e) {
-        c.e = e;
-        c.inc = binade_inc(e, dt);
+__device__ __forceinline__ float leap_steps_slow(float t, float dt, int n, LeapCache& c) {
+    for (;;) {
+        const uint32_t tb = __float_as_uint(t), e = tb >> 23;  // t >= 0
+        if (e != c.e) {
+            c.e = e;
+            c.inc = binade_inc(e, dt);
+        }
+        uint32_t inc = c.inc;
+        const bool closed = inc != 0xffffffffu && !((inc >> 31) && (tb & 1u));  // tie binade: only from an even significand
+        if (closed) {
+            inc &= 0x7fffffffu;
+            const unsigned long long nb = (unsigned long long)tb + (unsigned long long)(uint32_t)n * inc;
+            if ((nb >> 23) == (unsigned long long)e) return __uint_as_float((uint32_t)nb);
+            // the run leaves this binade: steps that provably stay inside (one below the float quotient, verified)
+            const uint32_t room = (((e + 1u) << 23) - 1u) - tb;
+            const int m = __float2int_rz(__fdividef((float)room, (float)inc)) - 1;
+            if (m >= 1 && m < n && (unsigned long long)(uint32_t)m * inc <= (unsigned long long)room) {
+                t = __uint_as_float(tb + (uint32_t)m * inc);
+                n -= m;
+            }
+        }
+        t = xadd(t, dt);  // a real addition: towards / across the boundary, off an odd tie significand, below dt's binade
+        if (--n == 0) return t;
     }
-    const unsigned long long nb = (unsigned long long)tb + (unsigned long long)(uint32_t)n * c.inc;
-    if ((nb >> 23) == (unsigned long long)e) return __uint_as_float((uint32_t)nb);
-    return advance_t(t, dt, n);
+}
+__device__ __forceinline__ float leap_steps(float t, float dt, int n, LeapCache& c) {
+    const uint32_t tb = __float_as_uint(t), e = tb >> 23;
+    if (e == c.e && (int)c.inc >= 0) {  // fast path: cached plain increment, run stays inside the binade
+        const unsigned long long nb = (unsigned long long)tb + (unsigned long long)(uint32_t)n * c.inc;
+        if ((nb >> 23) == (unsigned long long)e) return __uint_as_float((uint32_t)nb);
+    }
+    return leap_steps_slow(t, dt, n, c);
 }
 
 // ---- shading (tolerance-checked, FMA allowed) ----------------------------------------------
@@ -228,9 +258,10 @@ __device__ __forceinline__ void m1_shade(Rgba& col, float s) {
     // v == 0 (s <= 0.1, most of a sparse volume): w = 0 and the palette is finite, so the sample leaves colour
     // and alpha bit-identical — skip the three cosines. v is never NaN (__saturatef).
     if (!(v > 0.0f)) return;
+    // vertigo palette 0.5 + 0.5 cos(TAU (c v + d)): TAU folded into the constants (colour is tolerance-checked)
     const float pr = fmaf(0.5f, __cosf(__fmul_rn(TAU, v)), 0.5f);
-    const float pg = fmaf(0.5f, __cosf(__fmul_rn(TAU, fmaf(1.7f, v, 0.15f))), 0.5f);
-    const float pb = fmaf(0.5f, __cosf(__fmul_rn(TAU, fmaf(0.4f, v, 0.20f))), 0.5f);
+    const float pg = fmaf(0.5f, __cosf(fmaf(TAU * 1.7f, v, TAU * 0.15f)), 0.5f);
+    const float pb = fmaf(0.5f, __cosf(fmaf(TAU * 0.4f, v, TAU * 0.20f)), 0.5f);
     const float w = __fmul_rn(__fsub_rn(1.0f, col.a), v);
     col.r = fmaf(w, pr, col.r);
     col.g = fmaf(w, pg, col.g);

@@ -411,6 +411,34 @@ cudaError_t launch_flush_l2(uint4* buf, size_t n16, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// LAYOUT_QUAD staging: texel (tx, ty, z) of an (nx+1) x (ny+1) x nz grid = the 2x2 xy footprint whose low corner is
+// voxel (tx-1, ty-1, z), both taps of each axis clamped to the grid (clamp-to-edge, like the oracle's scalar_at()).
+// Channels: (x0,y0), (x1,y0), (x0,y1), (x1,y1). A sample with x0 = floor(qx - 0.5) in [-1, nx-1] reads texel x0 + 1.
+template <class T4, class T>
+__global__ void __launch_bounds__(256) pregather_quads_kernel(const T* __restrict__ vol, T4* __restrict__ out, int nx, int ny, int nz) {
+    const size_t total = (size_t)(nx + 1) * (ny + 1) * nz;
+    const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= total) return;
+    const int tx = (int)(o % (size_t)(nx + 1)), ty = (int)((o / (size_t)(nx + 1)) % (size_t)(ny + 1)), z = (int)(o / ((size_t)(nx + 1) * (ny + 1)));
+    const int x0 = max(tx - 1, 0), x1 = min(tx, nx - 1), y0 = max(ty - 1, 0), y1 = min(ty, ny - 1);
+    const size_t r0 = ((size_t)z * ny + y0) * nx, r1 = ((size_t)z * ny + y1) * nx;
+    T4 q;
+    q.x = __ldg(vol + r0 + x0); q.y = __ldg(vol + r0 + x1); q.z = __ldg(vol + r1 + x0); q.w = __ldg(vol + r1 + x1);
+    out[o] = q;
+}
+
+cudaError_t launch_pregather_quads(const void* vol, int dtype, void* out, int nx, int ny, int nz, cudaStream_t s) {
+    const size_t total = (size_t)(nx + 1) * (ny + 1) * nz;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    switch (dtype) {
+        case VKRT_U8: pregather_quads_kernel<uchar4, unsigned char><<<blocks, 256, 0, s>>>((const unsigned char*)vol, (uchar4*)out, nx, ny, nz); break;
+        case VKRT_F16: pregather_quads_kernel<ushort4, unsigned short><<<blocks, 256, 0, s>>>((const unsigned short*)vol, (ushort4*)out, nx, ny, nz); break;
+        case VKRT_F32: pregather_quads_kernel<float4, float><<<blocks, 256, 0, s>>>((const float*)vol, (float4*)out, nx, ny, nz); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_interleave_bricked(const uint2* color, const uint2* normal, uint4* out, int nx, int ny, int nz, int nbx, int nby,
                                       int nbz, cudaStream_t s) {
     const size_t total = (size_t)nbx * nby * nbz * 512;
