@@ -50,6 +50,7 @@ struct VkrtContext {
     int device = 0;
     int W = 0, H = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // second render stream: sort-first tiles of consecutive frames alternate streams, so one frame's tail overlaps the next frame's head
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // recorded on `stream` after a layout (BRICKED / TEXTURE / GATHER) was built there; a render launched on another
     // stream (the sort-first root renders on copy_stream) waits for it before reading the layout
@@ -467,7 +468,10 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
         }
         if ((int)c->offsets_cache.size() != n || memcmp(c->offsets_cache.data(), offsets, (size_t)n * sizeof(VkrtOffset)) != 0) {
             c->offsets_cache.assign(offsets, offsets + n);
+            CK(cudaStreamSynchronize(c->copy_stream));  // a sort-first push on the copy stream may still be reading the old table
             CK(cudaMemcpyAsync(c->d_offsets, c->offsets_cache.data(), (size_t)n * sizeof(VkrtOffset), cudaMemcpyHostToDevice, c->stream));
+            // a launch on another stream (the sort-first root renders on the copy stream) must see the new table
+            CK(cudaStreamSynchronize(c->stream));
         }
         A.offsets = c->d_offsets;
         A.n_tiles = n;
@@ -569,6 +573,7 @@ int vkrt_create(int device, int width, int height, VkrtContext** out_ctx) {
     do {
         if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) break;
         if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess) break;
         if ((e = cudaEventCreate(&c->ev_begin)) != cudaSuccess) break;
         if ((e = cudaEventCreate(&c->ev_end)) != cudaSuccess) break;
         if ((e = cudaEventCreateWithFlags(&c->ev_layout, cudaEventDisableTiming)) != cudaSuccess) break;
@@ -599,6 +604,7 @@ int vkrt_destroy(VkrtContext* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
     free_volume(c);
     free_frame(c);
     if (c->counters) cudaFree(c->counters);
@@ -619,6 +625,7 @@ int vkrt_destroy(VkrtContext* c) {
     if (c->ev_end) cudaEventDestroy(c->ev_end);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     delete c;
     return VKRT_OK;
 }
@@ -845,6 +852,7 @@ int vkrt_sync(VkrtContext* c) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamSynchronize(c->copy_stream));
+    CK(cudaStreamSynchronize(c->stream2));
     return VKRT_OK;
 }
 
@@ -1034,6 +1042,8 @@ int vkrt_timing_read(VkrtContext* c, float* ms, int n) {
     if ((size_t)n > c->ring_count) return fail(VKRT_ERR_INVALID, "fewer renders recorded than requested");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->copy_stream));  // the sort-first root renders (and records its events) on its other streams
+    CK(cudaStreamSynchronize(c->stream2));
     const size_t cap = c->ring_begin.size();
     for (int i = 0; i < n; ++i) {  // oldest of the last n first
         const size_t k = (c->ring_next + cap - (size_t)n + (size_t)i) % cap;
@@ -1125,6 +1135,7 @@ int vkrt_sortfirst_leave(VkrtContext* c) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamSynchronize(c->copy_stream));  // group transfers into rank 0's ring may still be in flight
+    CK(cudaStreamSynchronize(c->stream2));
     sf_release(c);
     return VKRT_OK;
 }
@@ -1154,6 +1165,7 @@ int vkrt_sortfirst_render(VkrtContext* c, const VkrtCameraUniform* cam, const Vk
     if (!c || !c->sf_base) return fail(VKRT_ERR_INVALID, "context is not in a sort-first group");
     CK(cudaSetDevice(c->device));
     const int slot = (int)(frame_index % (uint64_t)c->sf_slots);
+    const bool tiles = offsets && n > 0;
     cudaEvent_t eb = nullptr, ee = nullptr;
     if (!c->ring_begin.empty()) {
         eb = c->ring_begin[c->ring_next];
@@ -1162,14 +1174,48 @@ int vkrt_sortfirst_render(VkrtContext* c, const VkrtCameraUniform* cam, const Vk
         if (c->ring_count < c->ring_begin.size()) ++c->ring_count;
     }
     // slot reuse: the frame that used this slot last (frame_index - slots) must have been consumed
-    if (frame_index >= (uint64_t)c->sf_slots)
-        CK(launch_flag_wait(sf_consumed(c), frame_index - (uint64_t)c->sf_slots + 1, sf_timeouts(c), c->stream));
-    if (eb) CK(cudaEventRecord(eb, c->stream));
-    c->frame = sf_slot(c, slot);  // root: local memory; peers: rank 0's memory over NVLink
-    int rc = do_render(c, cam, un, (offsets && n > 0) ? offsets : nullptr, (offsets && n > 0) ? n : 0, false);
+    const bool must_wait = frame_index >= (uint64_t)c->sf_slots;
+    const uint64_t consumed_target = must_wait ? frame_index - (uint64_t)c->sf_slots + 1 : 0;
+    if (c->sf_rank == 0) {
+        // root: its tiles go straight into the ring slot (local memory) — on the SECOND stream: the context's stream
+        // carries the in-order waits for every frame, and a render queued behind the wait for the peers' tiles of frame f
+        // would keep the root from starting its share of frame f + 1.
+        // Consecutive frames alternate between two render streams: a frame's tiles on 1/N of the GPUs are a short launch
+        // whose duration is set by its longest rays; the next frame's launch fills the SMs its tail leaves idle.
+        cudaStream_t rs = (frame_index & 1) ? c->stream2 : c->copy_stream;
+        if (must_wait) CK(launch_flag_wait(sf_consumed(c), consumed_target, sf_timeouts(c), rs));
+        if (eb) CK(cudaEventRecord(eb, rs));
+        int rc = do_render(c, cam, un, tiles ? offsets : nullptr, tiles ? n : 0, false, 1, sf_slot(c, slot), nullptr, rs);
+        if (rc) return rc;
+        if (ee) CK(cudaEventRecord(ee, rs));
+        CK(launch_flag_add(sf_arrive(c, slot), 1ull, rs));
+        return VKRT_OK;
+    }
+    // peer: render into a LOCAL frame (two of them, alternating), then ship the tiles (or the whole frame) to rank 0's
+    // ring slot on the copy stream — whole tile rows in 16-byte stores over NVLink — overlapping this rank's next
+    // launch. The slot-reuse wait sits on the copy stream, so rendering runs ahead of rank 0's consumption.
+    int rc = ensure_batch(c, 1);
     if (rc) return rc;
-    CK(launch_flag_add(sf_arrive(c, slot), 1ull, c->stream));  // after the kernel: its (peer) stores are performed
-    if (ee) CK(cudaEventRecord(ee, c->stream));
+    const int b = c->sf_parity;
+    c->sf_parity ^= 1;
+    cudaStream_t ps = b ? c->stream2 : c->stream;  // local frame b is always rendered on stream b (see the root's note)
+    CK(cudaStreamWaitEvent(ps, c->ev_group_copied[b], 0));  // local frame b has left (two frames back)
+    if (eb) CK(cudaEventRecord(eb, ps));
+    rc = do_render(c, cam, un, tiles ? offsets : nullptr, tiles ? n : 0, false, 1, c->batch_frames[b], nullptr, ps);
+    if (rc) return rc;
+    if (ee) CK(cudaEventRecord(ee, ps));
+    CK(cudaEventRecord(c->ev_group_ready[b], ps));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_group_ready[b], 0));
+    if (must_wait) CK(launch_flag_wait(sf_consumed(c), consumed_target, sf_timeouts(c), c->copy_stream));
+    if (tiles) {
+        bool vec16 = (c->W % 2 == 0) && (c->params.tile_size % 2 == 0);
+        for (int i = 0; i < n && vec16; ++i) vec16 = ((long long)offsets[i].x % 2) == 0 && offsets[i].x >= 0.0f;
+        CK(launch_push_tiles(c->batch_frames[b], sf_slot(c, slot), c->d_offsets, n, c->params.tile_size, c->W, c->H, vec16, c->copy_stream));
+    } else {
+        CK(cudaMemcpyAsync(sf_slot(c, slot), c->batch_frames[b], sf_frame_bytes(c), cudaMemcpyDeviceToDevice, c->copy_stream));
+    }
+    CK(launch_flag_add(sf_arrive(c, slot), 1ull, c->copy_stream));  // after the transfer, system scope
+    CK(cudaEventRecord(c->ev_group_copied[b], c->copy_stream));
     return VKRT_OK;
 }
 

@@ -94,6 +94,9 @@ cudaError_t launch_scalar_to_rgba16f(const void* vol, int dtype, uint2* color, u
 cudaError_t launch_synth(void* out, int kind, int dtype, int nx, int ny, int nz, int ox, int oy, int oz, int gnx, int gny, int gnz,
                          uint32_t seed, cudaStream_t s, int bricked = 0);
 cudaError_t launch_brick_window(const void* lin, void* out, int elem_bytes, int nx, int ny, int nz, cudaStream_t s);
+// vec16: every tile origin x and W are even (16-byte aligned rows): two pixels per store
+cudaError_t launch_push_tiles(const uint2* src, uint2* dst, const VkrtOffset* d_offsets, int n_tiles, int tile, int W, int H, bool vec16,
+                              cudaStream_t s);
 cudaError_t launch_flush_l2(uint4* buf, size_t n16, cudaStream_t s);
 cudaError_t launch_flag_wait(const unsigned long long* flag, unsigned long long target, unsigned long long* timeouts, cudaStream_t s);
 cudaError_t launch_flag_add(unsigned long long* flag, unsigned long long v, cudaStream_t s);

@@ -343,7 +343,42 @@ __global__ void flag_set_kernel(unsigned long long* flag, unsigned long long v) 
     *(volatile unsigned long long*)flag = v;
 }
 
+// Sort-first: ship the tiles a rank has rendered into its LOCAL frame to the same pixels of a frame in rank 0's memory
+// (a CUDA-IPC mapping: the stores go out over NVLink). Whole tile rows with 16-byte stores by consecutive lanes, so the
+// link carries full 128-byte lines — the raycast kernel's own 8-byte stores of 8x4-pixel warps (64-byte row segments)
+// cost its launch 20-30 % (profiles/scaling_r01.md). grid = (tile, group of 16 rows).
+template <class V, int PX>
+__global__ void __launch_bounds__(256) push_tiles_kernel(const uint2* __restrict__ src, uint2* __restrict__ dst, const VkrtOffset* __restrict__ offsets,
+                                                         int tile, int W, int H) {
+    const VkrtOffset o = offsets[blockIdx.x];
+    const uint32_t x0 = __float2uint_rz(o.x), y0 = __float2uint_rz(o.y);
+    if (x0 >= (uint32_t)W || y0 >= (uint32_t)H) return;
+    const int cols = min(tile, W - (int)x0) / PX;  // vectors per row (PX pixels each)
+    const int r0 = (int)blockIdx.y * 16, r1 = min(min(r0 + 16, tile), H - (int)y0);
+    for (int i = (int)threadIdx.x; i < (r1 - r0) * cols; i += (int)blockDim.x) {
+        const int r = r0 + i / cols, cidx = i % cols;
+        const size_t px = ((size_t)(y0 + r) * W + x0) + (size_t)cidx * PX;
+        *reinterpret_cast<V*>(dst + px) = *reinterpret_cast<const V*>(src + px);
+    }
+    if (PX == 2 && ((min(tile, W - (int)x0)) & 1)) {  // odd clipped width: the last pixel of each row
+        const int c = min(tile, W - (int)x0) - 1;
+        for (int r = r0 + (int)threadIdx.x; r < r1; r += (int)blockDim.x) {
+            const size_t px = ((size_t)(y0 + r) * W + x0) + (size_t)c;
+            dst[px] = src[px];
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_push_tiles(const uint2* src, uint2* dst, const VkrtOffset* d_offsets, int n_tiles, int tile, int W, int H, bool vec16,
+                              cudaStream_t s) {
+    if (n_tiles <= 0) return cudaSuccess;
+    const dim3 grid((unsigned)n_tiles, (unsigned)((tile + 15) / 16));
+    if (vec16) push_tiles_kernel<uint4, 2><<<grid, 256, 0, s>>>(src, dst, d_offsets, tile, W, H);
+    else push_tiles_kernel<uint2, 1><<<grid, 256, 0, s>>>(src, dst, d_offsets, tile, W, H);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_scalar_to_rgba16f(const void* vol, int dtype, uint2* color, uint2* normal, int nx, int ny, int nz, cudaStream_t s) {
     const size_t total = (size_t)nx * ny * nz;

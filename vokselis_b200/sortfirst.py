@@ -54,7 +54,7 @@ def frame_owner(frame_index: int, world: int, batch: int = 1) -> int:
 class SortFirstGroup:
     def __init__(self, ctx: rt.Context, rank: int, world: int, granularity: str = "tiles", tile: int = 120, slots: int | None = None,
                  dist=None, batch: int = 1):
-        if dist is None:
+        if dist is None and world > 1:
             import torch.distributed as dist  # noqa: PLC0415
         if granularity not in ("tiles", "frames"):
             raise ValueError(granularity)
@@ -72,10 +72,11 @@ class SortFirstGroup:
             ctx.set_params(p)
             self.tiles = partition_tiles(ctx.width, ctx.height, tile, rank, world)
         box = [ctx.sortfirst_create_root(world, self.slots) if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        if rank != 0:
-            ctx.sortfirst_join(rank, box[0])
-        dist.barrier()
+        if world > 1:  # (world == 1: the same pipeline on one GPU — ring, two render streams — without any plumbing)
+            dist.broadcast_object_list(box, src=0)
+            if rank != 0:
+                ctx.sortfirst_join(rank, box[0])
+            dist.barrier()
         self.frame = 0       # next frame index to submit (same on every rank)
         self.consumed = 0    # root: next frame to wait for
 
@@ -140,9 +141,11 @@ class SortFirstGroup:
 
     def close(self):
         self.ctx.sync()
-        self.dist.barrier()
+        if self.world > 1:
+            self.dist.barrier()
         self.ctx.sortfirst_leave()
-        self.dist.barrier()
+        if self.world > 1:
+            self.dist.barrier()
 
     # -- measurement helpers used by bench.py -----------------------------------------------------
     def my_frames(self, first: int, count: int) -> int:

@@ -14,6 +14,8 @@ shaders/raycast_compute.wgsl:88-91, is what the partial passes split.
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 
@@ -91,27 +93,53 @@ class SortLastGroup:
         self.ain = torch.empty(n, dtype=torch.float32, device=dev)
         self.rgba = torch.empty(n * 4, dtype=torch.float32, device=dev)
 
-    def render(self, cam):
-        """All ranks call this; rank 0's context frame holds the result afterwards. Asynchronous."""
+    PHASES = ("march", "all_gather", "resolve", "remarch", "reduce", "finalize")
+
+    @staticmethod
+    def eye_of(cam):
+        """The point every ray of `cam` passes through, derived from the matrix the kernels actually use: the camera
+        centre is the pre-image of the clip-space direction (0, 0, 1, 0), i.e. column 2 of inv_proj, dehomogenised
+        (raycast_compute.wgsl:107-116 builds rays from inv_proj only; view_position is not read by the shader). Falls
+        back to view_position for matrices without a finite centre (orthographic / identity)."""
+        m = [float(v) for v in cam.inv_proj[:]]  # column-major 4x4
+        w = m[11]
+        if abs(w) > 1e-12 and all(math.isfinite(v) for v in m[8:12]):
+            return (m[8] / w, m[9] / w, m[10] / w)
+        return tuple(float(v) for v in cam.view_position[:3])
+
+    def render(self, cam, timed: bool = False):
+        """All ranks call this; rank 0's context frame holds the result afterwards. Asynchronous. timed: record a
+        CUDA event on the context's stream between the phases (read with phase_ms() after a sync)."""
         torch, dist, ctx = self.torch, self.dist, self.ctx
-        eye = tuple(cam.view_position[:3])
-        order = visibility_order(eye, self.gn, self.grid)
+        order = visibility_order(self.eye_of(cam), self.gn, self.grid)
         before = order[: order.index(self.rank)]
+        mark = ctx.mark if timed else (lambda i: None)
         with torch.cuda.stream(self.stream):
+            mark(0)
             if self.scheme == "two-pass":  # alpha-only march, then the colour march with the exact incoming alpha
                 ctx.partial_alpha(cam, self.T.data_ptr())
             else:  # ONE march from alpha 0 (relative partial); early termination is resolved afterwards
                 ctx.partial_relative(cam, self.rgba.data_ptr(), self.T.data_ptr())
+            mark(1)
             if self.world > 1:
                 dist.all_gather_into_tensor(self.T_all, self.T)
             else:
                 self.T_all.copy_(self.T)
+            mark(2)
             if self.scheme == "two-pass":
                 ctx.partial_ain(self.T_all.data_ptr(), before, self.ain.data_ptr())
             else:
                 ctx.partial_resolve(self.T_all.data_ptr(), before, self.rgba.data_ptr(), self.ain.data_ptr())
+            mark(3)
             ctx.partial_color(cam, self.ain.data_ptr(), self.rgba.data_ptr())  # deferred: only the flagged pixels
+            mark(4)
             if self.world > 1:
                 dist.reduce(self.rgba, dst=0, op=dist.ReduceOp.SUM)
+            mark(5)
             if self.rank == 0:
                 ctx.partial_finalize(cam, self.rgba.data_ptr())
+            mark(6)
+
+    def phase_ms(self) -> dict:
+        """Device time of each phase of the last render(timed=True) on this rank's stream."""
+        return {name: self.ctx.mark_elapsed(i, i + 1) for i, name in enumerate(self.PHASES)}
