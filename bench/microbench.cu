@@ -176,6 +176,13 @@ int main() {
             CK(cudaDestroyTextureObject(t));
             CK(cudaFreeArray(arr));
         }
+        {  // rgba8 unorm texels, point filter: the LAYOUT_QUAD fetch (pre-gathered xy quads, two fetches per sample)
+            cudaTextureObject_t t = make_tex(&arr, cudaCreateChannelDesc<uchar4>(), F, 4, false, true);
+            float ms = time_ms([&] { tex_point_kernel<float4><<<blocks, threads>>>(t, F, sink); });
+            printf(" \"tex3d_point_rgba8_F%d_gfetch_s\": %.2f,\n", F, fetches / ms * 1e-6);
+            CK(cudaDestroyTextureObject(t));
+            CK(cudaFreeArray(arr));
+        }
         {
             cudaTextureObject_t t = make_tex(&arr, cudaCreateChannelDesc<unsigned char>(), F, 1, true, true);
             float ms = time_ms([&] { tex_linear_kernel<<<blocks, threads>>>(t, F, sink); });

@@ -240,6 +240,12 @@ VKRT_API int vkrt_frame_host(VkrtContext* ctx, const VkrtCameraUniform* cam, con
  * buffer obtained here (a pageable buffer is staged through the context's own pinned slots). */
 VKRT_API int vkrt_alloc_host(size_t bytes, void** out);
 VKRT_API int vkrt_free_host(void* ptr);
+/* Page-lock host memory the CALLER owns (e.g. a POSIX shared-memory segment mapped by several processes, one per
+ * GPU) so that every GPU can DMA its frames straight into ONE consumer's memory over its own PCIe link
+ * (cudaHostRegister, portable). The screenshot readback of the reference (src/context/screenshot.rs:37-77) copies
+ * into a mapped buffer of its own process; this is its multi-GPU counterpart. */
+VKRT_API int vkrt_host_register(void* ptr, size_t bytes);
+VKRT_API int vkrt_host_unregister(void* ptr);
 VKRT_API int vkrt_frame_host_async(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un,
                                    int slot /* 0 or 1 */);
 VKRT_API int vkrt_frame_host_wait(VkrtContext* ctx, int slot, uint8_t* rgba8 /* may be NULL */);

@@ -54,6 +54,46 @@ def test_tile_partition_covers_frame_once_world2_gloo(W, H, tile):
     assert (cover == 1).all()
 
 
+def _shared_frames_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT))
+    from vokselis_b200 import rt
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, H, W = 6, 9, 16
+    seg = rt.SharedHostFrames(rank, world, dist, n, H, W, register=False)  # page-locking needs the CUDA driver: GPU tier
+    lo, hi = rank * n // world, (rank + 1) * n // world  # every rank delivers a contiguous share of the sweep
+    for f in range(lo, hi):
+        seg.array[f] = 10 * rank + f
+    dist.barrier()
+    if rank == 0:
+        q.put([int(seg.array[f].min()) * 1000 + int(seg.array[f].max()) for f in range(n)])
+    seg.close()
+    dist.destroy_process_group()
+
+
+def test_shared_host_frames_world2_gloo():
+    """The host-side gather of a sort-first sweep: one segment, created by rank 0, mapped by every rank; each rank
+    writes its share of the frames, rank 0 (the consumer) sees all of them."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 77) % 2000
+    procs = [ctx.Process(target=_shared_frames_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    seen = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = [(10 * (0 if f < 3 else 1) + f) for f in range(6)]
+    assert seen == [v * 1000 + v for v in expect]
+
+
 @pytest.mark.gpu
 def test_sortfirst_two_gpus_bit_exact():
     import torch

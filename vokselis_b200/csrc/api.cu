@@ -888,6 +888,17 @@ int vkrt_free_host(void* p) {
     return VKRT_OK;
 }
 
+int vkrt_host_register(void* p, size_t bytes) {
+    if (!p || bytes == 0) return fail(VKRT_ERR_INVALID, "bad argument");
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return VKRT_OK;
+}
+
+int vkrt_host_unregister(void* p) {
+    if (p) CK(cudaHostUnregister(p));
+    return VKRT_OK;
+}
+
 namespace {
 bool is_pinned_host(const void* p) {
     cudaPointerAttributes a{};

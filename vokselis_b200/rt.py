@@ -32,7 +32,7 @@ EXPORTS = [
     "vkrt_reset_stats", "vkrt_timing_enable", "vkrt_timing_read", "vkrt_flush_l2", "vkrt_volume_info", "vkrt_camera_uniform", "vkrt_dispatch_optimal",
     "vkrt_sortfirst_create_root", "vkrt_sortfirst_join", "vkrt_sortfirst_leave", "vkrt_sortfirst_partition", "vkrt_sortfirst_render", "vkrt_sortfirst_render_batch",
     "vkrt_sortfirst_consume", "vkrt_sortfirst_timeouts", "vkrt_sortfirst_wait", "vkrt_mark", "vkrt_mark_elapsed",
-    "vkrt_alloc_host", "vkrt_free_host", "vkrt_generate_synthetic", "vkrt_download_scalar", "vkrt_scalar_to_rgba16f",
+    "vkrt_alloc_host", "vkrt_free_host", "vkrt_host_register", "vkrt_host_unregister", "vkrt_generate_synthetic", "vkrt_download_scalar", "vkrt_scalar_to_rgba16f",
     "vkrt_upload_window", "vkrt_generate_synthetic_window", "vkrt_window_info", "vkrt_partial_alpha", "vkrt_partial_ain",
     "vkrt_partial_color", "vkrt_partial_finalize", "vkrt_partial_relative", "vkrt_partial_resolve",
 ]
@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
         "vkrt_partial_relative": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp, vp]),
         "vkrt_partial_resolve": (ci, [vp, vp, vp, ci, vp, vp]),
         "vkrt_free_host": (ci, [vp]),
+        "vkrt_host_register": (ci, [vp, C.c_size_t]),
+        "vkrt_host_unregister": (ci, [vp]),
         "vkrt_mark_elapsed": (ci, [vp, ci, ci, C.POINTER(cf)]),
         "vkrt_sortfirst_join": (ci, [vp, ci, vp]),
         "vkrt_sortfirst_leave": (ci, [vp]),
@@ -524,6 +526,55 @@ class PinnedArray:
             self.close()
         except Exception:
             pass
+
+
+class SharedHostFrames:
+    """n frames of RGBA8 [n, H, W, 4] in ONE host segment that every rank's process maps (POSIX shared memory created by
+    rank 0) and page-locks (vkrt_host_register), so that each GPU delivers its frames into the consumer's memory over
+    its own PCIe link: the gather to rank 0 of a sort-first sweep whose consumer lives on the host. `dist` is only the
+    plumbing that ships the segment's name. register=False skips the page-locking (CPU tests of the plumbing)."""
+
+    def __init__(self, rank: int, world: int, dist, n: int, height: int, width: int, register: bool = True):
+        from multiprocessing import shared_memory
+
+        self.rank, self.world, self.dist = rank, world, dist
+        self.nbytes = n * height * width * 4
+        box = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
+            box[0] = self.shm.name
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=box[0])
+            try:  # this process does not own the segment: keep Python's resource tracker from unlinking it at exit
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.array = np.ndarray((n, height, width, 4), np.uint8, buffer=self.shm.buf)
+        self._addr = self.array.ctypes.data
+        self._registered = False
+        if register:
+            _check(lib().vkrt_host_register(C.c_void_p(self._addr), self.nbytes))
+            self._registered = True
+        if world > 1:
+            dist.barrier()
+
+    def close(self):
+        if getattr(self, "shm", None) is None:
+            return
+        if self._registered:
+            lib().vkrt_host_unregister(C.c_void_p(self._addr))
+            self._registered = False
+        self.array = None
+        if self.world > 1:
+            self.dist.barrier()
+        self.shm.close()
+        if self.rank == 0:
+            self.shm.unlink()
+        self.shm = None
 
 
 def sortfirst_partition(width: int, height: int, tile_size: int, rank: int, world: int) -> np.ndarray:

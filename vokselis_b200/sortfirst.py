@@ -28,18 +28,17 @@ from . import rt
 MAX_SLOTS = 256  # kSfMaxSlots in csrc/api.cu
 
 
-# measured device ms per frame of a launch of b frames (bench workload, profiles/r01_batch.md)
-_MS_PER_FRAME = {1: 0.215, 2: 0.165, 3: 0.149, 4: 0.141, 5: 0.137, 6: 0.133, 7: 0.131, 8: 0.129}
-
-
 def choose_batch(steps: int, world: int) -> int:
-    """Frames per launch for `steps` frames dealt to `world` ranks in groups, round-robin: the group size that
-    minimises the busiest rank's time (360 frames in groups of 8 give 4 ranks 12/11/11/11 groups; groups of 6 give
-    15 each). A short last group is padded to a full one, hence the ceilings."""
-    def busiest_ms(b):
+    """Frames per launch for `steps` frames dealt to `world` ranks in groups, round-robin: the group size that leaves the
+    busiest rank with the fewest frames (360 frames in groups of 8 give 4 ranks 12/11/11/11 groups; groups of 6 give 15
+    each); among equals the largest, because a launch of more frames fills the GPU better. A short last group is padded
+    to a full one, hence the ceilings. Pure dealing arithmetic: no measured costs enter."""
+    def busiest_frames(b):
         groups = -(-steps // b)
-        return -(-groups // world) * b * _MS_PER_FRAME[b]
-    return min((b for b in _MS_PER_FRAME if 2 * world * b <= MAX_SLOTS), key=busiest_ms)
+        return -(-groups // world) * b
+    sizes = [b for b in range(1, rt.MAX_BATCH + 1) if 2 * world * b <= MAX_SLOTS]
+    best = min(busiest_frames(b) for b in sizes)
+    return max(b for b in sizes if busiest_frames(b) == best)
 
 
 def partition_tiles(width: int, height: int, tile: int, rank: int, world: int) -> np.ndarray:
