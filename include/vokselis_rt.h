@@ -216,6 +216,11 @@ VKRT_API int vkrt_frames_host(VkrtContext* ctx, const VkrtCameraUniform* cams, i
 /* Present — replaces the present pass (shaders/present.wgsl:23-35,111-119;
  * src/context/present_pipeline.rs:123-136): ACES + sRGB of the frame into a W x H RGBA8 buffer. */
 VKRT_API int vkrt_present(VkrtContext* ctx);
+/* The same pass onto a target of another size, as when the window differs from the 1280x720 backbuffer
+ * (src/context.rs:285-289 samples the backbuffer with the bilinear clamp-to-edge sampler of
+ * src/context/present_pipeline.rs:110-118; README's volume.png is such a stretched capture): the presented
+ * out_w x out_h RGBA8 image is copied to `rgba8` (host, out_w*out_h*4 bytes); blocks. */
+VKRT_API int vkrt_present_scaled(VkrtContext* ctx, int out_w, int out_h, uint8_t* rgba8);
 
 /* Result consumers — replace `ScreenshotCtx::capture_frame` (src/context/screenshot.rs:37-77).
  * Both block until the stream is idle. Rows are top-first, tightly packed. */

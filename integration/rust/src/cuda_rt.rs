@@ -24,6 +24,8 @@ extern "C" {
     fn vkrt_render(ctx: *mut VkrtContext, cam: *const CameraUniform, un: *const Uniform, offset: *const Offset) -> c_int;
     fn vkrt_render_tiles(ctx: *mut VkrtContext, cam: *const CameraUniform, un: *const Uniform, offsets: *const Offset, n: c_int) -> c_int;
     fn vkrt_present(ctx: *mut VkrtContext) -> c_int;
+    // present stretched onto a window of another size (src/context.rs:285-289 + present_pipeline.rs:110-118)
+    fn vkrt_present_scaled(ctx: *mut VkrtContext, out_w: c_int, out_h: c_int, rgba8: *mut u8) -> c_int;
     fn vkrt_readback(ctx: *mut VkrtContext, rgba16f: *mut u16) -> c_int;
     fn vkrt_readback_rgba8(ctx: *mut VkrtContext, rgba8: *mut u8) -> c_int;
     fn vkrt_sync(ctx: *mut VkrtContext) -> c_int;
@@ -31,6 +33,9 @@ extern "C" {
     fn vkrt_frames_host(ctx: *mut VkrtContext, cams: *const CameraUniform, n: c_int, un: *const Uniform, rgba8: *mut u8, group: c_int) -> c_int;
     fn vkrt_alloc_host(bytes: usize, out: *mut *mut c_void) -> c_int;   // page-locked memory: keeps the D2H copies asynchronous
     fn vkrt_free_host(ptr: *mut c_void) -> c_int;
+    // page-lock memory the caller owns (e.g. a shared-memory segment mapped by one process per GPU)
+    fn vkrt_host_register(ptr: *mut c_void, bytes: usize) -> c_int;
+    fn vkrt_host_unregister(ptr: *mut c_void) -> c_int;
 }
 
 pub struct CudaRaycast { ctx: *mut VkrtContext, pub width: u32, pub height: u32 }
@@ -72,4 +77,31 @@ impl CudaRaycast {
         check(unsafe { vkrt_frames_host(self.ctx, cams.as_ptr(), cams.len() as _, un, out.as_mut_ptr(), 0) })
     }
 }
+impl CudaRaycast {
+    /// What `Context::render` shows in a window that differs from the backbuffer (src/context.rs:285-289).
+    pub fn present_to(&self, out_w: u32, out_h: u32) -> color_eyre::eyre::Result<Vec<u8>> {
+        let mut px = vec![0u8; (out_w * out_h * 4) as usize];
+        check(unsafe { vkrt_present_scaled(self.ctx, out_w as _, out_h as _, px.as_mut_ptr()) })?;
+        Ok(px)
+    }
+}
+
+/// The event -> camera mapping of `run` (src/lib.rs:64-66,150-176), kept as it is in the crate: the CUDA path only
+/// consumes `camera.get_proj_view_matrix()`. Listed here because a headless host (no winit) has to feed it itself;
+/// vokselis_b200/host/vokselis.hpp (`OrbitInput`) and vokselis_b200/rt.py carry the same mapping and tests.
+pub struct OrbitInput { pub mouse_dragged: bool }
+impl OrbitInput {
+    pub const ROTATE_SPEED: f32 = 0.0025; // src/lib.rs:65
+    pub const ZOOM_SPEED: f32 = 0.002;    // src/lib.rs:66
+    pub fn button(&mut self, pressed: bool) { self.mouse_dragged = pressed; }
+    pub fn mouse_wheel_lines(&self, cam: &mut crate::Camera, scroll: f32) { cam.add_zoom(-(scroll * 1.0) * Self::ZOOM_SPEED); }
+    pub fn mouse_wheel_pixels(&self, cam: &mut crate::Camera, scroll_y: f64) { cam.add_zoom(-(scroll_y as f32) * Self::ZOOM_SPEED); }
+    pub fn mouse_motion(&self, cam: &mut crate::Camera, dx: f64, dy: f64) {
+        if self.mouse_dragged {
+            cam.add_yaw(-dx as f32 * Self::ROTATE_SPEED);
+            cam.add_pitch(dy as f32 * Self::ROTATE_SPEED);
+        }
+    }
+}
+
 impl Drop for CudaRaycast { fn drop(&mut self) { unsafe { vkrt_destroy(self.ctx); } } }

@@ -161,11 +161,19 @@ def scalar_to_rgba16f(scalar: np.ndarray):
     return color, normal
 
 
-def present(frame: np.ndarray) -> np.ndarray:
+def present(frame: np.ndarray, out_w: int | None = None, out_h: int | None = None) -> np.ndarray:
     H, W = frame.shape[:2]
     frame = np.ascontiguousarray(frame).view(np.uint16)
-    out = np.empty((H, W, 4), np.uint8)
-    rc = lib().vko_present(_ptr(frame), W, H, _ptr(out))
+    if out_w is None and out_h is None:
+        out = np.empty((H, W, 4), np.uint8)
+        rc = lib().vko_present(_ptr(frame), W, H, _ptr(out))
+    else:
+        out_w, out_h = out_w or W, out_h or H
+        out = np.empty((out_h, out_w, 4), np.uint8)
+        L = lib()
+        L.vko_present_scaled.restype = C.c_int
+        L.vko_present_scaled.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        rc = L.vko_present_scaled(_ptr(frame), W, H, out_w, out_h, _ptr(out))
     assert rc == 0
     return out
 

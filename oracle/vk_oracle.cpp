@@ -653,6 +653,43 @@ int vko_present(const uint16_t* frame, int W, int H, uint8_t* rgba8) {
     return VKRT_OK;
 }
 
+// The same pass onto a target of another size (window != backbuffer): the full-screen triangle's interpolated uv is
+// the fragment centre over the target size (shaders/present.wgsl:98-104), `textureSample` is the bilinear,
+// clamp-to-edge sampler of src/context/present_pipeline.rs:110-118 (fp32 weights, a + f (b - a), x then y).
+int vko_present_scaled(const uint16_t* frame, int W, int H, int outW, int outH, uint8_t* rgba8) {
+    if (!frame || !rgba8 || W <= 0 || H <= 0 || outW <= 0 || outH <= 0) return VKRT_ERR_INVALID;
+    auto at = [&](int x, int y, int k) {
+        x = x < 0 ? 0 : (x >= W ? W - 1 : x);
+        y = y < 0 ? 0 : (y >= H ? H - 1 : y);
+        return h2f(frame[((size_t)y * W + x) * 4 + k]);
+    };
+#pragma omp parallel for schedule(static)
+    for (int oy = 0; oy < outH; ++oy) {
+        for (int ox = 0; ox < outW; ++ox) {
+            const float u = ((float)ox + 0.5f) / (float)outW, v = ((float)oy + 0.5f) / (float)outH;
+            const float ux = u * (float)W - 0.5f, uy = v * (float)H - 0.5f;
+            const float flx = std::floor(ux), fly = std::floor(uy);
+            const float fx = ux - flx, fy = uy - fly;
+            const int ix = f2i(flx), iy = f2i(fly);
+            float c[4];
+            for (int k = 0; k < 4; ++k) {
+                const float a = at(ix, iy, k), b = at(ix + 1, iy, k), cc = at(ix, iy + 1, k), d = at(ix + 1, iy + 1, k);
+                const float ab = a + fx * (b - a), cd = cc + fx * (d - cc);
+                c[k] = ab + fy * (cd - ab);
+            }
+            for (int k = 0; k < 3; ++k) {
+                const float x = c[k];
+                const float t = wclamp((x * (2.51f * x + 0.03f)) / (x * (2.43f * x + 0.59f) + 0.14f), 0.0f, 1.0f);
+                const float sel = std::ceil(t - 0.0031308f);
+                c[k] = wmix(12.92f * t, 1.055f * std::pow(t, 0.41666f) - 0.055f, sel);
+            }
+            for (int k = 0; k < 4; ++k)
+                rgba8[((size_t)oy * outW + ox) * 4 + k] = (uint8_t)std::nearbyint(wclamp(c[k], 0.0f, 1.0f) * 255.0f);
+        }
+    }
+    return VKRT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // src/camera.rs:93-113,148-171 with glam 0.20.5 semantics (crates.io; not vendored in the reference):
 //   Mat4::look_at_rh(eye, center, up) = look_to_rh(eye, center - eye, up):

@@ -63,6 +63,8 @@ VKO_API int vko_scalar_to_rgba16f(const void* scalar, int dtype, int nx, int ny,
 
 /* shaders/present.wgsl:23-35,111-119 at 1:1 scale (no stretch): rgba16f -> rgba8 unorm. */
 VKO_API int vko_present(const uint16_t* frame, int W, int H, uint8_t* rgba8);
+/* the same pass stretched onto an outW x outH target (bilinear clamp-to-edge sampler, present_pipeline.rs:110-118) */
+VKO_API int vko_present_scaled(const uint16_t* frame, int W, int H, int outW, int outH, uint8_t* rgba8);
 
 /* src/camera.rs:93-113,148-171 */
 VKO_API int vko_camera_uniform(float zoom, float pitch, float yaw, const float target[3], float aspect,

@@ -670,3 +670,21 @@ def test_batched_launch_equals_single_frames(rt, oracle, noise64, mode):
         # the single-frame API is untouched by the batch buffers
         ctx.render(cams[2])
         assert np.array_equal(ctx.readback(), singles[2])
+
+
+def test_present_stretched_matches_oracle(rt, oracle, noise64, xor_cam):
+    """vkrt_present_scaled (window != backbuffer, shaders/present.wgsl:111-119 through the bilinear clamp-to-edge sampler of
+    src/context/present_pipeline.rs:110-118) against the oracle: <= 1 LSB (pow differs in the last ulp), also at 1:1 against
+    vkrt_present. 958x1050 is the window size of the reference's README capture."""
+    W, H = 1280, 720
+    color, normal = noise64
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_rgba16f(color, normal)
+        ctx.render(xor_cam)
+        ctx.present()
+        frame, one = ctx.readback(), ctx.readback_rgba8()
+        assert np.abs(ctx.present_scaled(W, H).astype(np.int32) - one.astype(np.int32)).max() <= 1
+        for ow, oh in ((958, 1050), (640, 360), (1920, 1080), (333, 77)):
+            got = ctx.present_scaled(ow, oh)
+            ref = oracle.present(frame, ow, oh)
+            assert np.abs(got.astype(np.int32) - ref.astype(np.int32)).max() <= 1, (ow, oh)

@@ -170,3 +170,27 @@ def test_box_screen_bounds_contain_every_hit_pixel(rt, oracle):
     sing = abi.CameraUniform()
     (x0, y0, x1, y1), row = rt.box_screen_bounds(sing, 64, 36)
     assert x0 < -1e30 and y1 > 1e30 and row == -1
+
+
+def test_orbit_input_mapping(rt):
+    """src/lib.rs:64-66,150-176: drag -> yaw/pitch at 0.0025 rad per pixel (yaw against x), wheel -> zoom at 0.002 per line
+    (up = closer), motion without the button ignored; the camera's own clamps apply (src/camera.rs:115-132)."""
+    import math
+
+    cam = rt.Camera(3.0, -0.5, 1.0, (0.0, 0.0, 0.0), 16 / 9)
+    inp = rt.OrbitInput()
+    inp.mouse_motion(cam, 50.0, 50.0)
+    assert (cam.yaw, cam.pitch) == (1.0, -0.5)
+    inp.button(True)
+    inp.mouse_motion(cam, 8.0, -3.0)
+    assert cam.yaw == pytest.approx(1.0 - 8 * 0.0025, abs=1e-7) and cam.pitch == pytest.approx(-0.5 - 3 * 0.0025, abs=1e-7)
+    inp.mouse_motion(cam, 0.0, 1.0e6)
+    assert cam.pitch == pytest.approx(math.pi / 2, abs=1e-6) and cam.pitch < math.pi / 2
+    inp.button(False)
+    inp.mouse_wheel_lines(cam, 2.0)
+    assert cam.zoom == pytest.approx(3.0 - 2 * 0.002, abs=1e-7)
+    inp.mouse_wheel_pixels(cam, 1.0e6)
+    assert cam.zoom == pytest.approx(0.3)
+    inp.mouse_wheel_lines(cam, -1.0e6)
+    assert cam.zoom == pytest.approx(50.0)
+    assert cam.updated

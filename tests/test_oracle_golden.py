@@ -278,3 +278,22 @@ def test_sort_last_partials_recompose(oracle, noise64, xor_cam):
     out = np.where(hit[..., None], rgb + np.array(p.clear_color[:3], np.float32), np.array(p.clear_color[:3], np.float32))
     ref = full.view(np.float16).astype(np.float32)[..., :3]
     assert np.abs(out.astype(np.float16).astype(np.float32) - ref).max() <= 2e-3
+
+
+def test_present_stretched_equals_translated_reference(oracle):
+    """The present pass onto a target of another size (window != backbuffer; README's volume.png is a 958x1050 capture of
+    the 1280x720 backbuffer): hand restatement == the reference's present.wgsl fs_main + bilinear clamp sampler, bit for
+    bit, for up- and down-scaling; at the backbuffer's own size it equals the 1:1 pass up to one LSB."""
+    from oracle import ref_binding as rb
+
+    rng = np.random.default_rng(9)
+    H, W = 36, 64
+    frame = rng.uniform(0.0, 2.5, size=(H, W, 4)).astype(np.float16)
+    frame[..., 3] = 1.0
+    f16 = frame.view(np.uint16)
+    # at the backbuffer's own size uv * W - 0.5 lands on the texel up to an ulp: the bilinear blend moves a value by ~1e-7
+    assert np.abs(oracle.present(f16, W, H).astype(int) - oracle.present(f16).astype(int)).max() <= 1
+    if not rb.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    for ow, oh in ((W, H), (96, 105), (29, 17), (128, 72), (1, 1)):
+        assert np.array_equal(oracle.present(f16, ow, oh), rb.present(f16, ow, oh)), (ow, oh)

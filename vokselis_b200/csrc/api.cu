@@ -815,6 +815,21 @@ int vkrt_present(VkrtContext* c) {
     return VKRT_OK;
 }
 
+int vkrt_present_scaled(VkrtContext* c, int out_w, int out_h, uint8_t* rgba8) {
+    if (!c || !rgba8) return fail(VKRT_ERR_INVALID, "NULL argument");
+    if (out_w <= 0 || out_h <= 0 || out_w > 32768 || out_h > 32768) return fail(VKRT_ERR_INVALID, "target size out of range");
+    CK(cudaSetDevice(c->device));
+    uint32_t* tmp = nullptr;
+    const size_t bytes = (size_t)out_w * out_h * 4;
+    CK(cudaMalloc(&tmp, bytes));
+    cudaError_t e = launch_present_scaled(c->frame, tmp, c->W, c->H, out_w, out_h, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rgba8, tmp, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return cuda_fail(e, "vkrt_present_scaled");
+    return VKRT_OK;
+}
+
 int vkrt_readback(VkrtContext* c, uint16_t* out) {
     if (!c || !out) return fail(VKRT_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(c->device));

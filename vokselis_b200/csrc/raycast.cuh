@@ -104,5 +104,6 @@ cudaError_t launch_flag_set(unsigned long long* flag, unsigned long long v, cuda
 
 // present.cu
 cudaError_t launch_present(const uint2* frame, uint32_t* rgba8, int W, int H, cudaStream_t s);
+cudaError_t launch_present_scaled(const uint2* frame, uint32_t* rgba8, int W, int H, int outW, int outH, cudaStream_t s);
 
 }  // namespace vkrt

@@ -3,7 +3,10 @@
 // then render `frames` frames of an orbit, print the mean frame time, optionally dump the last frame.
 // Mode `sweep` hands the whole orbit to the library in chunks of 24 cameras (Context::capture_sweep ->
 // vkrt_frames_host): several frames per launch, present fused, D2H pipelined — the offline-recording path.
-//   usage: headless [frames=360] [W=1280] [H=720] [single|tile|sweep] [out.rgba8]
+// Mode `drag` replays a scripted mouse drag + wheel through OrbitInput (the event mapping of src/lib.rs:150-176) and
+// renders ONE frame with the resulting camera: 40 motion events of (+8, -3) pixels with the button held, 5 without,
+// two wheel lines up.
+//   usage: headless [frames=360] [W=1280] [H=720] [single|tile|sweep|drag] [out.rgba8]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -48,6 +51,22 @@ int main(int argc, char** argv) {
                 const size_t one = (size_t)W * H * 4;
                 FILE* f = fopen(argv[5], "wb");
                 if (f) { fwrite(last.data() + last.size() - one, 1, one, f); fclose(f); }
+            }
+            return 0;
+        }
+        if (argc > 4 && strcmp(argv[4], "drag") == 0) {
+            OrbitInput input;
+            input.button(true);
+            for (int i = 0; i < 40; ++i) input.mouse_motion(ctx.camera, 8.0, -3.0);
+            input.button(false);
+            for (int i = 0; i < 5; ++i) input.mouse_motion(ctx.camera, 100.0, 100.0);  // not dragging: ignored
+            input.mouse_wheel_lines(ctx.camera, 2.0f);
+            run_headless(demo, ctx, 1, [](Context&, unsigned) {});
+            printf("drag: yaw %.9g pitch %.9g zoom %.9g\n", ctx.camera.yaw, ctx.camera.pitch, ctx.camera.zoom);
+            if (argc > 5) {
+                const auto px = ctx.capture_frame();
+                FILE* f = fopen(argv[5], "wb");
+                if (f) { fwrite(px.data(), 1, px.size(), f); fclose(f); }
             }
             return 0;
         }

@@ -13,6 +13,7 @@
 //   VolumeTexture              src/context/volume_texture.rs  vokselis::VolumeTexture
 //   RaycastPipeline            examples/xor/raycast.rs        vokselis::RaycastPipeline ("single" | "tile")
 //   trait Demo, run()          src/lib.rs:37-45        vokselis::Demo, vokselis::run_headless()
+//   mouse / wheel -> camera    src/lib.rs:64-66,150-176  vokselis::OrbitInput
 //   dispatch_optimal           src/utils/mod.rs:15-18  vokselis::dispatch_optimal
 #pragma once
 #include <cstdint>
@@ -55,6 +56,23 @@ struct VKRT_API Camera {
 
    private:
     void fix_eye();
+};
+
+// The event -> camera mapping of `run` (src/lib.rs:64-66,150-176): dragging with the mouse button held turns the orbit by
+// 0.0025 rad per pixel (yaw against the x motion, pitch with the y motion), the wheel zooms by 0.002 per line / pixel
+// (scrolling up moves in). Windowing itself is out of scope; a host that has events feeds them here.
+struct OrbitInput {
+    static constexpr float ROTATE_SPEED = 0.0025f;  // src/lib.rs:65
+    static constexpr float ZOOM_SPEED = 0.002f;     // src/lib.rs:66
+    bool mouse_dragged = false;                     // src/lib.rs:64
+    void button(bool pressed) { mouse_dragged = pressed; }                                                   // :150-159
+    void mouse_wheel_lines(Camera& cam, float scroll) const { cam.add_zoom(-(scroll * 1.0f) * ZOOM_SPEED); }  // :160-168, LineDelta
+    void mouse_wheel_pixels(Camera& cam, double scroll_y) const { cam.add_zoom(-(float)scroll_y * ZOOM_SPEED); }  // PixelDelta
+    void mouse_motion(Camera& cam, double dx, double dy) const {                                             // :169-174
+        if (!mouse_dragged) return;
+        cam.add_yaw(-(float)dx * ROTATE_SPEED);
+        cam.add_pitch((float)dy * ROTATE_SPEED);
+    }
 };
 
 // `impl Default for Uniform` (src/context/global_ubo.rs:67-81)

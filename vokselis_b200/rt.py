@@ -26,7 +26,7 @@ EXPORTS = [
     "vkrt_create", "vkrt_destroy", "vkrt_resize", "vkrt_last_error", "vkrt_default_params", "vkrt_set_params",
     "vkrt_get_params", "vkrt_upload_rgba16f", "vkrt_upload_scalar", "vkrt_generate_xor", "vkrt_download_rgba16f",
     "vkrt_render", "vkrt_render_tiles", "vkrt_tile_table", "vkrt_box_screen_bounds",
-    "vkrt_render_batch", "vkrt_batch_frame_device_ptr", "vkrt_readback_batch", "vkrt_frames_host", "vkrt_present", "vkrt_readback", "vkrt_readback_rgba8", "vkrt_readback_rgba8_async",
+    "vkrt_render_batch", "vkrt_batch_frame_device_ptr", "vkrt_readback_batch", "vkrt_frames_host", "vkrt_present", "vkrt_present_scaled", "vkrt_readback", "vkrt_readback_rgba8", "vkrt_readback_rgba8_async",
     "vkrt_readback_aux", "vkrt_sync", "vkrt_frame_host", "vkrt_frame_host_async", "vkrt_frame_host_wait",
     "vkrt_frame_host_slot_ptr", "vkrt_frame_device_ptr", "vkrt_frame_rgba8_device_ptr", "vkrt_stream", "vkrt_stats",
     "vkrt_reset_stats", "vkrt_timing_enable", "vkrt_timing_read", "vkrt_flush_l2", "vkrt_volume_info", "vkrt_camera_uniform", "vkrt_dispatch_optimal",
@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
         "vkrt_readback_batch": (ci, [vp, ci, vp]),
         "vkrt_frames_host": (ci, [vp, vp, ci, C.POINTER(Uniform), vp, ci]),
         "vkrt_present": (ci, [vp]),
+        "vkrt_present_scaled": (ci, [vp, ci, ci, vp]),
         "vkrt_readback": (ci, [vp, vp]),
         "vkrt_readback_rgba8": (ci, [vp, vp]),
         "vkrt_readback_rgba8_async": (ci, [vp, vp]),
@@ -217,6 +218,31 @@ class Camera:
         return out
 
 
+class OrbitInput:
+    """The event -> camera mapping of the reference's `run` (src/lib.rs:64-66,150-176), float32 like the Rust code."""
+
+    ROTATE_SPEED = np.float32(0.0025)  # src/lib.rs:65
+    ZOOM_SPEED = np.float32(0.002)     # src/lib.rs:66
+
+    def __init__(self):
+        self.mouse_dragged = False
+
+    def button(self, pressed: bool):
+        self.mouse_dragged = bool(pressed)
+
+    def mouse_wheel_lines(self, cam: "Camera", scroll: float):
+        cam.add_zoom(float(-(np.float32(scroll) * np.float32(1.0)) * self.ZOOM_SPEED))
+
+    def mouse_wheel_pixels(self, cam: "Camera", scroll_y: float):
+        cam.add_zoom(float(-np.float32(scroll_y) * self.ZOOM_SPEED))
+
+    def mouse_motion(self, cam: "Camera", dx: float, dy: float):
+        if not self.mouse_dragged:
+            return
+        cam.add_yaw(float(-np.float32(dx) * self.ROTATE_SPEED))
+        cam.add_pitch(float(np.float32(dy) * self.ROTATE_SPEED))
+
+
 class Context:
     """Device + stream + rgba16f frame: the part of src/context.rs the raycast path needs."""
 
@@ -326,6 +352,12 @@ class Context:
 
     def present(self):
         _check(lib().vkrt_present(self._h))
+
+    def present_scaled(self, out_w: int, out_h: int) -> np.ndarray:
+        """vkrt_present_scaled: the present pass stretched onto an out_w x out_h target (window != backbuffer)."""
+        out = np.empty((out_h, out_w, 4), np.uint8)
+        _check(lib().vkrt_present_scaled(self._h, out_w, out_h, _vp(out)))
+        return out
 
     def sync(self):
         _check(lib().vkrt_sync(self._h))
