@@ -140,21 +140,25 @@ def binade_inc2(e, dt):
 
 
 def leap_steps(t, dt, n, cache, stats=None):
+    """vkrt_device.cuh leap_steps / leap_steps_slow. cache = [eb, inc]: eb = e << 23 of the binade whose plain increment
+    (< 2^19) is cached, 0xFFFFFFFF = none. The fast path is 32-bit: n <= 4095."""
     t, dt = np.float32(t), np.float32(dt)
     tb = int(t.view(np.uint32))
-    e = tb >> 23
-    if e == cache[0] and cache[1] < 0x80000000:
-        nb = tb + n * cache[1]
-        if (nb >> 23) == e:
+    if n <= 4095:
+        nb = (tb + n * cache[1]) & 0xFFFFFFFF
+        if (((tb ^ cache[0]) | (nb ^ cache[0])) >> 23) == 0:
             if stats is not None:
                 stats["fast"] = stats.get("fast", 0) + 1
             return np.uint32(nb).view(np.float32)
     while True:
         tb = int(t.view(np.uint32))
         e = tb >> 23
-        if e != cache[0]:
-            cache[0], cache[1] = e, binade_inc2(e, dt)
-        inc = cache[1]
+        if (e << 23) == cache[0]:
+            inc = cache[1]
+        else:
+            inc = binade_inc2(e, dt)
+            if inc < (1 << 19):
+                cache[0], cache[1] = e << 23, inc
         closed = inc != 0xFFFFFFFF and not ((inc >> 31) and (tb & 1))
         if closed:
             inc &= 0x7FFFFFFF
@@ -194,7 +198,7 @@ def test_leap_steps_equals_repeated_addition(seed):
             dt = _tie_dt(rng, int(rng.integers(0, 3)))  # exact ties somewhere in t's range [1, 8)
         else:
             dt = np.float32(10 ** rng.uniform(-4, -1.5))
-        cache = [0xFFFFFFFF, 0xFFFFFFFF]
+        cache = [0xFFFFFFFF, 0]
         for _ in range(14):
             n = int(rng.integers(1, 12)) if rng.uniform() < 0.7 else int(rng.integers(12, 900))
             for _ in range(n):
@@ -212,7 +216,7 @@ def test_leap_steps_tie_binade_is_closed_form():
     rng = np.random.default_rng(7)
     dt = _tie_dt(rng, 1)
     for t0 in (np.float32(2.0), np.float32(2.0000002), np.float32(3.1)):
-        stats, cache = {}, [0xFFFFFFFF, 0xFFFFFFFF]
+        stats, cache = {}, [0xFFFFFFFF, 0]
         ref = t0
         for _ in range(60):
             ref = np.float32(ref + dt)

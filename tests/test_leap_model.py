@@ -93,17 +93,22 @@ def position(eye, d, t, h):
 
 
 def leap_count(sc, d_brick, idx, q, rq, drift, eps):
-    r = f32(F(d_brick * 8 - 4) - eps)
-    e = []
+    """raycast.cu leap_count, operation by operation: R = 8d - (4 + eps); per axis h = sg*R + (4 - q) (one FMA),
+    w = 8*b + h (one FMA), s = w * rq; the grid clip only where a partial last brick sticks out (M1);
+    n = max(trunc(fma(min(s), 1 - drift, 0.98)), 1) with min(s) capped at 4094."""
+    R = fma(F(8), F(d_brick), f32(-(F(4) + eps)))
+    keep = f32(F(1) - drift)
+    s = []
     for k in range(3):
-        m = F((idx[k] >> 3) * 8 + 4)
-        ek = f32(m + (r if rq[k] >= 0 else -r))
-        if sc.mode == 1:
-            ek = min(ek, f32(F(sc.n) - eps))
-        e.append(ek)
-    s = [f32(f32(e[k] - q[k]) * rq[k]) for k in range(3)]
-    sm = min(min(s[0], s[1]), min(s[2], F(4096)))
-    return max(trunc_i(f32(sm - fma(sm, drift, F(0.02)))) + 1, 1)
+        sg = F(1) if rq[k] >= 0 else F(-1)
+        h = fma(sg, R, f32(F(4) - q[k]))
+        w = fma(F(8), F(idx[k] >> 3), h)
+        sk = f32(w * rq[k])
+        if sc.mode == 1 and (sc.n & 7) != 0 and sg > 0:
+            sk = min(sk, f32(f32(f32(F(sc.n) - eps) - q[k]) * rq[k]))
+        s.append(sk)
+    sm = min(min(s[0], s[1]), min(s[2], F(4094)))
+    return max(trunc_i(fma(sm, keep, F(0.98))), 1)
 
 
 def walk(sc, eye, d, dt_scale, dt_floor, max_steps=40000):

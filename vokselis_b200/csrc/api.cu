@@ -487,6 +487,7 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     A.nx = c->nx; A.ny = c->ny; A.nz = c->nz;
     A.fx = (float)c->nx; A.fy = (float)c->ny; A.fz = (float)c->nz;
     A.hx = A.fx / 2.0f; A.hy = A.fy / 2.0f; A.hz = A.fz / 2.0f;
+    A.one = 1.0f;
     A.nbx = c->nbx; A.nby = c->nby; A.nbz = c->nbz;
     A.dist = c->dist;
     // shrink leap regions by ~16 ulp of the largest voxel coordinate (rounding of p and q)
@@ -501,6 +502,8 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
             A.bb_hi[k] = (float)(2.0 * hi / n3[k] - 1.0);
         }
     }
+    A.leap_r0 = -(4.0f + A.leap_eps);
+    A.leap_clip = ((c->nx | c->ny | c->nz) & 7) != 0;
     A.leap_lim[0] = A.fx - A.leap_eps; A.leap_lim[1] = A.fy - A.leap_eps; A.leap_lim[2] = A.fz - A.leap_eps;
     A.dt_scale = P.dt_scale; A.dt_floor = P.dt_floor; A.alpha_threshold = P.alpha_threshold; A.initial_alpha = P.initial_alpha;
     memcpy(A.clear, P.clear_color, sizeof A.clear);

@@ -43,12 +43,8 @@ template <> struct Scalar<VKRT_F32> {
     static __device__ __forceinline__ float load(const void* p, size_t i) { return __ldg((const float*)p + i); }
 };
 
-// Distance field over the 8^3-voxel bricks: 0 = some sample in the brick can be non-transparent;
+// Distance field over the 8^3-voxel bricks (A.dist): 0 = some sample in the brick can be non-transparent;
 // d >= 1 = every brick within Chebyshev radius d-1 (this one included) is empty.
-__device__ __forceinline__ uint32_t brick_distance(const RenderArgs& A, int ix, int iy, int iz) {
-    const uint32_t cell = ((uint32_t)(iz >> 3) * (uint32_t)A.nby + (uint32_t)(iy >> 3)) * (uint32_t)A.nbx + (uint32_t)(ix >> 3);
-    return __ldg(A.dist + cell);
-}
 
 // ---- texel fetch, M0 (nearest, two rgba16f texels at one integer coordinate) -----------------
 template <int LAYOUT>
@@ -85,23 +81,68 @@ __device__ __forceinline__ float4 tld4_layer(cudaTextureObject_t tex, int layer,
     return r;
 }
 
-// a + f*(b - a), x then y then z, every operation spelled out (see the determinism note in vkrt_device.cuh)
+// Packed fp32x2 arithmetic (sm_100a FADD2 / FMUL2 / FFMA2): two IEEE round-to-nearest operations per issue slot, each
+// component rounded exactly like the scalar __fadd_rn / __fmul_rn / __fmaf_rn, never contracted. The kernel is bound by
+// instruction issue, so the x/y halves of the position arithmetic and the pairs of the trilinear
+// interpolation go through these; ptxas broadcasts a scalar or an immediate to both halves for free.
+// (Inline PTX, not the __fadd2_rn / __fmul2_rn intrinsics: nvcc contracts those two into one FFMA2, which would change
+// the bits of p = eye + t*dir; `.rn` PTX instructions are never fused.)
+#define VKRT_F32X2_OP2(name, op)                                                                                         \
+    __device__ __forceinline__ float2 name(float2 a, float2 b) {                                                         \
+        float2 r;                                                                                                        \
+        asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; " op " rc, ra, rb; mov.b64 {%0, %1}, rc;}" \
+            : "=f"(r.x), "=f"(r.y)                                                                                       \
+            : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                                                                   \
+        return r;                                                                                                        \
+    }
+VKRT_F32X2_OP2(add2, "add.rn.f32x2")
+VKRT_F32X2_OP2(mul2, "mul.rn.f32x2")
+#undef VKRT_F32X2_OP2
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return add2(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rn.f32x2 rd, ra, rb, rc; "
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+__device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
+
+// a + f*(b - a), every operation spelled out (see the determinism note in vkrt_device.cuh). Order: z, then y, then x —
+// the order in which the pre-gathered quads pair up for the packed form; every layout uses it, so all layouts
+// produce identical bits (the oracle interpolates x, y, z: same value up to rounding, tolerance-checked).
 __device__ __forceinline__ float lerp1(float a, float b, float f) { return fmaf(f, __fsub_rn(b, a), a); }
+__device__ __forceinline__ float2 lerp2(float2 a, float2 b, float2 f) { return fma2(f, sub2(b, a), a); }
 __device__ __forceinline__ float lerp3(float c000, float c100, float c010, float c110, float c001, float c101, float c011, float c111,
                                        float fx, float fy, float fz) {
-    const float c00 = lerp1(c000, c100, fx), c10 = lerp1(c010, c110, fx), c01 = lerp1(c001, c101, fx), c11 = lerp1(c011, c111, fx);
-    return lerp1(lerp1(c00, c10, fy), lerp1(c01, c11, fy), fz);
+    const float c00 = lerp1(c000, c001, fz), c10 = lerp1(c100, c101, fz), c01 = lerp1(c010, c011, fz), c11 = lerp1(c110, c111, fz);
+    return lerp1(lerp1(c00, c01, fy), lerp1(c10, c11, fy), fx);
+}
+// the same on two texels of the QUAD layout: g = (v(x0,y0), v(x1,y0), v(x0,y1), v(x1,y1)) at z0 and z1
+__device__ __forceinline__ float lerp3_quads(float4 g0, float4 g1, float fx, float fy, float fz) {
+    const float2 fz2 = dup2(fz);
+    const float2 a = lerp2(make_float2(g0.x, g0.y), make_float2(g1.x, g1.y), fz2);  // (c00, c10)
+    const float2 b = lerp2(make_float2(g0.z, g0.w), make_float2(g1.z, g1.w), fz2);  // (c01, c11)
+    const float2 c = lerp2(a, b, dup2(fy));                                         // (c0, c1)
+    return lerp1(c.x, c.y, fx);
 }
 
 // ---- scalar sample, M1 (linear filter, clamp-to-edge) ----------------------------------------
 template <int LAYOUT, int DTYPE>
-__device__ __forceinline__ float m1_sample(const RenderArgs& A, float qx, float qy, float qz) {
+__device__ __forceinline__ float m1_sample(const RenderArgs& A, float2 qxy, float qz) {
     if (LAYOUT == VKRT_LAYOUT_TEXTURE) {
-        return tex3D<float>(A.tex_a, qx, qy, qz);  // hardware trilinear, 8-bit weights
+        return tex3D<float>(A.tex_a, qxy.x, qxy.y, qz);  // hardware trilinear, 8-bit weights
     }
-    const float ux = __fsub_rn(qx, 0.5f), uy = __fsub_rn(qy, 0.5f), uz = __fsub_rn(qz, 0.5f);
-    const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
-    const float fx = __fsub_rn(ux, flx), fy = __fsub_rn(uy, fly), fz = __fsub_rn(uz, flz);
+    // q - 0.5 as RN(q * 1 + -0.5): qxy comes out of a packed multiplication, and ptxas would contract a plain packed
+    // addition with it (see RenderArgs::one), rounding u once instead of twice
+    const float2 uxy = fma2(qxy, dup2(A.one), dup2(-0.5f));
+    const float uz = __fsub_rn(qz, 0.5f);
+    const float2 flxy = make_float2(floorf(uxy.x), floorf(uxy.y));
+    const float flz = floorf(uz);
+    const float2 fxy = sub2(uxy, flxy);
+    const float fx = fxy.x, fy = fxy.y, fz = __fsub_rn(uz, flz);
+    const float flx = flxy.x, fly = flxy.y;
     if (LAYOUT == VKRT_LAYOUT_GATHER) {
         // (Measured, ncu: in the dense case this path is bound by the texture DATA pipe — l1tex throughput
         // 97 %, data_pipe_tex_wavefronts 83 %, ~35 sectors per warp-level tld4 because the lanes of a warp sit
@@ -120,9 +161,12 @@ __device__ __forceinline__ float m1_sample(const RenderArgs& A, float qx, float 
         // Texel (x0+1, y0+1, z) holds the pre-gathered 2x2 xy footprint v(x0..x0+1, y0..y0+1, z) with clamp-to-edge baked
         // in (volume.cu pregather_quads_kernel); z clamps through the texture's address mode. Two POINT fetches of a 3-D
         // texture return the 8 taps; no gather footprint, 3-D tiled locality across layers.
-        const float4 g0 = tex3D<float4>(A.tex_a, flx + 1.5f, fly + 1.5f, flz + 0.5f);
-        const float4 g1 = tex3D<float4>(A.tex_a, flx + 1.5f, fly + 1.5f, flz + 1.5f);
-        return lerp3(g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, fx, fy, fz);
+        // (the second fetch addresses the same x, y texel through its own coordinate pair, fl + 1.25: one FADD2 instead of
+        // two register copies into the second TEX's operand registers)
+        const float2 cxy = add2(flxy, dup2(1.5f)), cxy1 = add2(flxy, dup2(1.25f));
+        const float4 g0 = tex3D<float4>(A.tex_a, cxy.x, cxy.y, flz + 0.5f);
+        const float4 g1 = tex3D<float4>(A.tex_a, cxy1.x, cxy1.y, flz + 1.5f);
+        return lerp3_quads(g0, g1, fx, fy, fz);
     }
     const int x0 = (int)flx, y0 = (int)fly, z0 = (int)flz;
     // clamp-to-edge on both taps, like the oracle's scalar_at()
@@ -139,10 +183,10 @@ __device__ __forceinline__ float m1_sample(const RenderArgs& A, float qx, float 
     return __fmul_rn(lerp3(c000, c100, c010, c110, c001, c101, c011, c111, fx, fy, fz), S::kScale);
 }
 
-// Per-ray constants of the leap length model: reciprocal of the voxel-space advance per step on each axis
-// (sign = direction of travel; 1e30 for an axis the ray does not move along) and the drift allowance.
+// Per-ray constants of the leap length model: reciprocal of the voxel-space advance per step on each axis (sign =
+// direction of travel; 1e30 for an axis the ray does not move along), that sign as +-1, and 1 - the drift allowance.
 struct LeapRay {
-    float rqx, rqy, rqz, drift_per_step;
+    float rqx, rqy, rqz, sgx, sgy, sgz, keep;
 };
 
 // How many consecutive samples, this one included, provably stay inside the empty region around the sample's
@@ -152,27 +196,29 @@ struct LeapRay {
 // so after n <= s steps the model is off by at most s * drift_per_step steps (+ a fixed 0.02). The result is
 // >= 1: the current sample's emptiness was read from its exact index.
 //
-// Written around the brick centre m = 8*(i>>3) + 4: the exit plane on an axis is m +- r with
-// r = 4 + 8(d-1) - eps, the sign being the ray's direction on that axis (copied from rq with one LOP3), so
-// there is no per-axis select. In M1 the region is also clipped to the grid (clamp-to-edge sampling: outside
-// is NOT empty; the distance field's border is "occupied", so only a partial last brick can stick out):
-// min(., dims - eps), which never binds for the low plane.
+// Written around the brick centre 8b + 4 (b = brick coordinate, already computed for the distance lookup): the exit
+// plane on an axis is centre + sg * R with R = 8d - 4 - eps, so the distance to it is w = 8b + (sg*R + (4 - q)) and
+// s = w * rq. (Not u*rq + R*|rq|: for a ray almost parallel to a face rq is huge and that sum cancels.) x and y go
+// through the packed FADD2 / FFMA2 / FMUL2: 11 floating-point instructions for the three axes. In M1 the region is
+// also clipped to the grid when a partial last brick sticks out of it (A.leap_clip; clamp-to-edge sampling: outside is
+// NOT empty; the distance field's border is "occupied", so whole bricks never stick out).
 template <int MODE>
-__device__ __forceinline__ int leap_count(const RenderArgs& A, const LeapRay& L, uint32_t d, int ix, int iy, int iz,
-                                          float qx, float qy, float qz) {
-    const float r = (float)((int)d * 8 - 4) - A.leap_eps;
-    const uint32_t rb = __float_as_uint(r);  // r > 0
-    const float mx = (float)((ix >> 3) * 8 + 4), my = (float)((iy >> 3) * 8 + 4), mz = (float)((iz >> 3) * 8 + 4);
-    float ex = mx + __uint_as_float(rb | (__float_as_uint(L.rqx) & 0x80000000u));
-    float ey = my + __uint_as_float(rb | (__float_as_uint(L.rqy) & 0x80000000u));
-    float ez = mz + __uint_as_float(rb | (__float_as_uint(L.rqz) & 0x80000000u));
-    if (MODE == VKRT_MODE_M1) {
-        ex = fminf(ex, A.leap_lim[0]); ey = fminf(ey, A.leap_lim[1]); ez = fminf(ez, A.leap_lim[2]);
+__device__ __forceinline__ int leap_count(const RenderArgs& A, const LeapRay& L, uint32_t d, int bx, int by, int bz, float2 qxy, float qz) {
+    const float R = fmaf(8.0f, (float)d, A.leap_r0);  // 8d - (4 + eps)
+    const float2 hxy = fma2(make_float2(L.sgx, L.sgy), dup2(R), add2(make_float2(-qxy.x, -qxy.y), dup2(4.0f)));
+    const float hz = fmaf(L.sgz, R, __fsub_rn(4.0f, qz));
+    const float2 wxy = fma2(dup2(8.0f), make_float2((float)bx, (float)by), hxy);
+    const float wz = fmaf(8.0f, (float)bz, hz);
+    const float2 sxy = mul2(wxy, make_float2(L.rqx, L.rqy));
+    float sx = sxy.x, sy = sxy.y, sz = __fmul_rn(wz, L.rqz);
+    if (MODE == VKRT_MODE_M1 && A.leap_clip) {  // uniform; only grids whose dims are not multiples of 8
+        if (L.sgx > 0.0f) sx = fminf(sx, (A.leap_lim[0] - qxy.x) * L.rqx);
+        if (L.sgy > 0.0f) sy = fminf(sy, (A.leap_lim[1] - qxy.y) * L.rqy);
+        if (L.sgz > 0.0f) sz = fminf(sz, (A.leap_lim[2] - qz) * L.rqz);
     }
-    const float sx = (ex - qx) * L.rqx, sy = (ey - qy) * L.rqy, sz = (ez - qz) * L.rqz;
-    const float sm = fminf(fminf(sx, sy), fminf(sz, 4096.0f));
-    // samples j = 0 .. floor(s - margin) (this one is j = 0) lie inside the region
-    return max(__float2int_rz(sm - fmaf(sm, L.drift_per_step, 0.02f)) + 1, 1);
+    const float sm = fminf(fminf(sx, sy), fminf(sz, (float)(kLeapFastMax - 1)));
+    // samples j = 0 .. floor(s - margin) (this one is j = 0) lie inside the region: floor(s - (s*drift + 0.02)) + 1
+    return max(__float2int_rz(fmaf(sm, L.keep, 0.98f)), 1);
 }
 
 template <int MODE, int LAYOUT, int DTYPE, bool SKIP, bool DBG>
@@ -220,14 +266,17 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
         const float dt = step_dt(dir, A.fx, A.fy, A.fz, A.dt_scale, A.dt_floor);
         // Leap geometry (SKIP only; approximate on purpose, see leap_count).
         LeapRay L = {};
-        LeapCache lc = {0xffffffffu, 0xffffffffu};
+        LeapCache lc = {0xffffffffu, 0u};
+        float drift_per_step = 0.0f;
         if (SKIP) {
             const float dqx = dir.x * A.hx * dt, dqy = dir.y * A.hy * dt, dqz = dir.z * A.hz * dt;  // voxels per step
             L.rqx = fabsf(dqx) > 1e-12f ? 1.0f / dqx : 1e30f;
             L.rqy = fabsf(dqy) > 1e-12f ? 1.0f / dqy : 1e30f;
             L.rqz = fabsf(dqz) > 1e-12f ? 1.0f / dqz : 1e30f;
+            L.sgx = copysignf(1.0f, L.rqx); L.sgy = copysignf(1.0f, L.rqy); L.sgz = copysignf(1.0f, L.rqz);
             // one replayed addition moves t off the exact line by <= ulp(t)/2 <= t1 * 2^-24; in units of a step:
-            L.drift_per_step = (t1 * 5.9604645e-08f) / dt * 2.0f;  // x2 safety
+            drift_per_step = (t1 * 5.9604645e-08f) / dt * 2.0f;  // x2 safety
+            L.keep = 1.0f - drift_per_step;
         }
         // (Two traversal restructurings were measured and rejected on B200. While-while — every lane first
         // advances to its next non-empty sample on its own, then the warp shades together: 1.9x slower,
@@ -252,7 +301,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
             t_end = (tb0 < tb1 && A.bb_lo[0] <= A.bb_hi[0]) ? fminf(t1, tb1) : -1.0f;
             if (tb0 > t0 && tb0 < t_end) {
                 const float s = fminf((tb0 - t0) * __frcp_rn(dt), 1.0e6f);
-                const int n0 = __float2int_rz(s - fmaf(s, L.drift_per_step, 2.0f));
+                const int n0 = __float2int_rz(s - fmaf(s, drift_per_step, 2.0f));
                 if (n0 >= 1) {
                     if (DBG) {
                         for (int j = 0; j < n0 && t < t1; ++j) {
@@ -260,15 +309,19 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
                             t = xadd(t, dt);
                         }
                     } else {
-                        t = leap_steps(t, dt, n0, lc);
+                        t = leap_steps_slow(t, dt, n0, lc);  // up to 10^6 steps: the 64-bit form
                     }
                 }
             }
         }
+        const float2 exy = make_float2(eye.x, eye.y), dxy = make_float2(dir.x, dir.y), hxy = make_float2(A.hx, A.hy), one2 = dup2(A.one);
         while (t < t_end) {
-            // p = eye + t*dir ; q = (p + 1) * (N/2) — exact, decides the texel
-            f3 p = {xadd(eye.x, xmul(t, dir.x)), xadd(eye.y, xmul(t, dir.y)), xadd(eye.z, xmul(t, dir.z))};
-            const float qx = xmul(xadd(p.x, 1.0f), A.hx), qy = xmul(xadd(p.y, 1.0f), A.hy), qz = xmul(xadd(p.z, 1.0f), A.hz);
+            // p = eye + t*dir ; q = (p + 1) * (N/2) — exact (IEEE round-to-nearest per component, the oracle's operation
+            // order), decides the texel; x and y go through the packed FMUL2 / FADD2
+            const float2 pxy = fma2(mul2(dup2(t), dxy), one2, exy);  // RN(m * 1 + e) = RN(m + e), see A.one
+            const float pz = xadd(eye.z, xmul(t, dir.z));
+            const float2 qxy = mul2(add2(pxy, dup2(1.0f)), hxy);
+            const float qx = qxy.x, qy = qxy.y, qz = xmul(xadd(pz, 1.0f), A.hz);
             const int ix = __float2int_rz(qx), iy = __float2int_rz(qy), iz = __float2int_rz(qz);
             const bool inb = (unsigned)ix < (unsigned)A.nx && (unsigned)iy < (unsigned)A.ny && (unsigned)iz < (unsigned)A.nz;
             if (SKIP) {
@@ -280,8 +333,9 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
                 if (!inb) {
                     n = MODE == VKRT_MODE_M0 ? 1 : 0;
                 } else {
-                    const uint32_t d = brick_distance(A, ix, iy, iz);
-                    if (d != 0u) n = leap_count<MODE>(A, L, d, ix, iy, iz, qx, qy, qz);
+                    const int bx = ix >> 3, by = iy >> 3, bz = iz >> 3;
+                    const uint32_t d = __ldg(A.dist + (((uint32_t)bz * (uint32_t)A.nby + (uint32_t)by) * (uint32_t)A.nbx + (uint32_t)bx));
+                    if (d != 0u) n = leap_count<MODE>(A, L, d, bx, by, bz, qxy, qz);
                 }
                 if (n > 0) {
                     if (DBG) {
@@ -302,9 +356,10 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
             if (MODE == VKRT_MODE_M0) {
                 float4 c, n;
                 m0_fetch<LAYOUT>(A, ix, iy, iz, inb, c, n);
+                const f3 p = {pxy.x, pxy.y, pz};
                 m0_shade(col, c, n, p, A.clear);
             } else {
-                m1_shade(col, m1_sample<LAYOUT, DTYPE>(A, qx, qy, qz));
+                m1_shade(col, m1_sample<LAYOUT, DTYPE>(A, qxy, qz));
             }
             if (col.a >= A.alpha_threshold) {
                 terminated = true;

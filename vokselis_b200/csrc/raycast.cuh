@@ -1,6 +1,7 @@
 // raycast.cuh — launch interface between the C ABI (api.cu) and the kernels (raycast.cu, volume.cu, present.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/vokselis_rt.h"
@@ -11,6 +12,26 @@ namespace vkrt {
 // (lives in the constant bank, no global loads for the camera or the parameters).
 constexpr int kMaxBatch = VKRT_MAX_BATCH;
 struct RenderArgs {
+    // ---- what every iteration of the march reads, kept together at the front (ptxas re-reads kernel parameters with
+    // LDCU inside the loop rather than keeping them in registers; tried and rejected: forcing them into registers through
+    // an opaque zero costs 4-9 registers, i.e. a resident block per SM) ----
+    float hx, hy, hz;  // dims / 2
+    // 1.0f, as a value ptxas cannot see. ptxas contracts mul.rn.f32x2 followed by add.rn.f32x2 into one FFMA2 (even with
+    // -fmad=false; the scalar .rn forms are left alone), which would round p = eye + t*dir once instead of twice. The
+    // packed addition is therefore written fma(m, one, e) = RN(m * 1 + e) = RN(m + e): exact, and not fusable.
+    float one;
+    int nx, ny, nz;
+    int nbx;              // 8^3-voxel bricks per axis (occupancy grid and bricked layout)
+    const uint8_t* dist;  // per brick: 0 = occupied, d = bricks within Chebyshev radius d-1 are all empty
+    int nby, nbz;
+    cudaTextureObject_t tex_a, tex_b;
+    float alpha_threshold;
+    float leap_r0;        // -(4 + leap_eps): exit-plane offset from the brick centre is 8 d + leap_r0
+    int leap_clip;        // M1: some dim is not a multiple of 8, the partial last brick sticks out: clip regions to the grid
+    float leap_eps;       // safety shrink of leap regions, in voxels
+    float leap_lim[3];    // M1: dims - leap_eps (the clip)
+    float dt_scale, dt_floor, initial_alpha;
+    float fx, fy, fz;  // dims as f32   (textureDimensions -> vec3<f32>)
     // One launch renders n_frames cameras (`single` entry: grid.z = frame; frame f is stored at frame + f*W*H).
     // A 1080p frame with a fifth of its pixels on the box cannot fill 148 SMs, and its duration is bounded by
     // the dependent march of its longest rays; several frames of a sweep in one grid do (measured 1.85x).
@@ -24,19 +45,10 @@ struct RenderArgs {
     // volume
     const void* vol_a;  // LINEAR M0: colour texels; BRICKED M0: interleaved 16-B texels; M1: scalar grid
     const void* vol_b;  // LINEAR M0: normal texels
-    cudaTextureObject_t tex_a, tex_b;
-    int nx, ny, nz;
-    float fx, fy, fz;  // dims as f32   (textureDimensions -> vec3<f32>)
-    float hx, hy, hz;  // dims / 2
-    int nbx, nby, nbz;  // 8^3-voxel bricks per axis (occupancy grid and bricked layout)
-    const uint8_t* dist;  // per brick: 0 = occupied, d = bricks within Chebyshev radius d-1 are all empty
-    float leap_eps;       // safety shrink of leap regions, in voxels
-    float leap_lim[3];    // M1: dims - leap_eps (leap regions are clipped to the grid)
     // Bounding box of the occupied bricks, grown by one voxel, in the box's own coordinates ([-1,1]^3): every
     // sample outside it is a no-op. bb_lo[0] > bb_hi[0] = nothing is occupied.
     float bb_lo[3], bb_hi[3];
     // parameters (VkrtParams)
-    float dt_scale, dt_floor, alpha_threshold, initial_alpha;
     float clear[4];
     int m1_srgb;
     // outputs
@@ -45,6 +57,7 @@ struct RenderArgs {
     uint32_t* aux;                 // optional W*H: bit31 hit, low bits iterations
     unsigned long long* counters;  // optional [3]: rays_hit, samples_reference, samples_fetched
 };
+static_assert(offsetof(RenderArgs, nx) == 16 && offsetof(RenderArgs, dist) == 32 && offsetof(RenderArgs, tex_a) == 48, "hot block layout");
 
 // One rank's view of a brick-partitioned volume (sortlast.cu): a WINDOW of the global grid.
 struct PartialArgs {

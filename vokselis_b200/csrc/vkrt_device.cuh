@@ -132,18 +132,19 @@ __device__ __forceinline__ float advance_t(float t, float dt, int n) {
 
 // leap_steps: the same result — t after n additions t = fl(t + dt), bit for bit — for the raycast loop, where a ray
 // leaps many times (short leaps mostly) and crosses one or two binades of t inside the volume:
-//  * the per-binade increment is cached in registers across the leaps of a ray (LeapCache);
-//  * a leap that stays inside t's binade is ONE 64-bit multiply-add on the bit pattern (n * inc can exceed 2^32 and
-//    must not wrap back into the binade) and a compare;
-//  * a leap that reaches the end of the binade takes as many steps as provably stay inside (quotient by a float
-//    reciprocal, one below the estimate, verified in integers — no integer division), then real additions across
-//    the boundary, then goes on in the next binade;
-//  * an exact tie (dt = (m + 1/2) ulp(t)) rounds to even: from an even significand every step adds the even one of
-//    {m, m+1}, so after at most one real addition the closed form applies there too;
-//  * t below dt's binade, subnormals: real additions.
-// cache.inc: < 2^24 = increment; bit 31 set = tie binade (low bits: the even increment); 0xffffffff = no closed form.
+//  * the per-binade increment is cached in registers across the leaps of a ray (LeapCache) when it is plain (no tie)
+//    and below 2^19, so that n * inc with n <= kLeapFastMax cannot leave 31 bits;
+//  * a leap that stays inside the cached binade is then ONE 32-bit multiply-add on the bit pattern, one LOP3
+//    ((t ^ base) | (result ^ base): both in the binade?) and a compare;
+//  * everything else goes to leap_steps_slow: a leap that reaches the end of the binade takes as many steps as provably
+//    stay inside (quotient by a float reciprocal, one below the estimate, verified in integers — no integer division),
+//    then real additions across the boundary, then goes on in the next binade; an exact tie (dt = (m + 1/2) ulp(t))
+//    rounds to even: from an even significand every step adds the even one of {m, m+1}, so after at most one real
+//    addition the closed form applies there too; t below dt's binade, subnormals: real additions.
+// binade_inc: < 2^24 = increment; bit 31 set = tie binade (low bits: the even increment); 0xffffffff = no closed form.
+constexpr int kLeapFastMax = 4095;
 struct LeapCache {
-    uint32_t e, inc;  // biased exponent the increment was derived for (0xffffffff = none yet)
+    uint32_t eb, inc;  // eb = e << 23 for the binade `inc` belongs to (0xffffffff = none cached); inc < 2^19, plain
 };
 __device__ __forceinline__ uint32_t binade_inc(uint32_t e, float dt) {
     const uint32_t db = __float_as_uint(dt), ed = db >> 23;
@@ -158,11 +159,16 @@ __device__ __forceinline__ uint32_t binade_inc(uint32_t e, float dt) {
 __device__ __forceinline__ float leap_steps_slow(float t, float dt, int n, LeapCache& c) {
     for (;;) {
         const uint32_t tb = __float_as_uint(t), e = tb >> 23;  // t >= 0
-        if (e != c.e) {
-            c.e = e;
-            c.inc = binade_inc(e, dt);
+        uint32_t inc;
+        if ((e << 23) == c.eb) {
+            inc = c.inc;
+        } else {
+            inc = binade_inc(e, dt);
+            if (inc < (1u << 19)) {
+                c.eb = e << 23;
+                c.inc = inc;
+            }
         }
-        uint32_t inc = c.inc;
         const bool closed = inc != 0xffffffffu && !((inc >> 31) && (tb & 1u));  // tie binade: only from an even significand
         if (closed) {
             inc &= 0x7fffffffu;
@@ -180,12 +186,11 @@ __device__ __forceinline__ float leap_steps_slow(float t, float dt, int n, LeapC
         if (--n == 0) return t;
     }
 }
+// requires 1 <= n <= kLeapFastMax, t >= 0
 __device__ __forceinline__ float leap_steps(float t, float dt, int n, LeapCache& c) {
-    const uint32_t tb = __float_as_uint(t), e = tb >> 23;
-    if (e == c.e && (int)c.inc >= 0) {  // fast path: cached plain increment, run stays inside the binade
-        const unsigned long long nb = (unsigned long long)tb + (unsigned long long)(uint32_t)n * c.inc;
-        if ((nb >> 23) == (unsigned long long)e) return __uint_as_float((uint32_t)nb);
-    }
+    const uint32_t tb = __float_as_uint(t);
+    const uint32_t nb = tb + (uint32_t)n * c.inc;  // < 2^32: tb < 2^31, n * inc < 2^12 * 2^19
+    if ((((tb ^ c.eb) | (nb ^ c.eb)) >> 23) == 0u) return __uint_as_float(nb);  // t and the result both in the cached binade
     return leap_steps_slow(t, dt, n, c);
 }
 
