@@ -138,6 +138,8 @@ __device__ __forceinline__ float m1_sample(const RenderArgs& A, float2 qxy, floa
     // addition with it (see RenderArgs::one), rounding u once instead of twice
     const float2 uxy = fma2(qxy, dup2(A.one), dup2(-0.5f));
     const float uz = __fsub_rn(qz, 0.5f);
+    // (floorf is FRND on the XU pipe; the FMA-pipe form — add 1.5*2^23 rounding down, subtract it again, FADD2.RM — was
+    // measured 0.5 % slower: one more issue slot per sample, and the XU pipe is not the limiter)
     const float2 flxy = make_float2(floorf(uxy.x), floorf(uxy.y));
     const float flz = floorf(uz);
     const float2 fxy = sub2(uxy, flxy);
@@ -222,7 +224,7 @@ __device__ __forceinline__ int leap_count(const RenderArgs& A, const LeapRay& L,
 }
 
 template <int MODE, int LAYOUT, int DTYPE, bool SKIP, bool DBG>
-__global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ RenderArgs A) {
+__global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VKRT_LAYOUT_LINEAR ? 12 : 8)) raycast_kernel(const __grid_constant__ RenderArgs A) {
     // ---- which pixel -------------------------------------------------------------------------
     const uint32_t gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y * blockDim.y + threadIdx.y;
     float offx = 0.0f, offy = 0.0f;
@@ -312,6 +314,15 @@ __global__ void __launch_bounds__(256) raycast_kernel(const __grid_constant__ Re
                         t = leap_steps_slow(t, dt, n0, lc);  // up to 10^6 steps: the 64-bit form
                     }
                 }
+            }
+        }
+        if (SKIP && !DBG && lc.eb == 0xffffffffu && t < t_end) {
+            // the increment of the binade the march starts in, computed here at full lane occupancy rather than by the
+            // first leap's slow path (a ray without an entry leap has nothing cached yet)
+            const uint32_t e = __float_as_uint(t) >> 23, inc = binade_inc(e, dt);
+            if (inc < (1u << 19)) {
+                lc.eb = e << 23;
+                lc.inc = inc;
             }
         }
         const float2 exy = make_float2(eye.x, eye.y), dxy = make_float2(dir.x, dir.y), hxy = make_float2(A.hx, A.hy), one2 = dup2(A.one);
