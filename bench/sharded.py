@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--edge5", type=int, default=4096)
     ap.add_argument("--edge34", type=int, default=0)
     ap.add_argument("--tile", type=int, default=120)
-    ap.add_argument("--layout", type=int, default=abi.LAYOUT_GATHER)
+    ap.add_argument("--layout", type=int, default=-1, help="-1 = the layout workloads.py chose per config")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     dist = None
@@ -42,7 +42,7 @@ def main():
                 print(json.dumps({"check": fn.__name__, **r}), flush=True)
     for cid in (3, 4):
         if str(cid) in what:
-            r = workloads.run_sortfirst_tiles(cid, rank, world, local, dist, frames=args.frames, tile=args.tile, layout=args.layout,
+            r = workloads.run_sortfirst_tiles(cid, rank, world, local, dist, frames=args.frames, tile=args.tile, layout=(None if args.layout < 0 else args.layout),
                                               edge=args.edge34 or None, hbm_peak_gbs=peak)
             if rank == 0:
                 print(json.dumps(r), flush=True)

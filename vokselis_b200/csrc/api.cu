@@ -51,6 +51,14 @@ struct VkrtContext {
     int W = 0, H = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaStream_t stream2 = nullptr;  // second render stream: sort-first tiles of consecutive frames alternate streams, so one frame's tail overlaps the next frame's head
+    // Sort-first tile shares of consecutive frames rotate over kSfLanes render streams, each with its own local frame on a
+    // peer: a frame's share on 1/N of the GPUs is a short launch whose duration is its longest rays (config 4 at 4K: 72 of
+    // 576 tiles take 0.30 ms against 0.78 ms for all of them, bench/tiles_subset.py), so several frames must be in flight.
+    static constexpr int kSfLanes = 8;
+    cudaStream_t sf_stream[kSfLanes] = {};
+    uint2* sf_local[kSfLanes] = {};
+    cudaEvent_t sf_ready[kSfLanes] = {}, sf_copied[kSfLanes] = {};
+    int sf_lane = 0;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // recorded on `stream` after a layout (BRICKED / TEXTURE / GATHER) was built there; a render launched on another
     // stream (the sort-first root renders on copy_stream) waits for it before reading the layout
@@ -136,7 +144,32 @@ void free_volume(VkrtContext* c) {
     c->kind = VOL_NONE;
     c->windowed = false;
 }
+int sf_lanes_ensure(VkrtContext* c, bool local_frames) {
+    for (int i = 0; i < VkrtContext::kSfLanes; ++i) {
+        if (!c->sf_stream[i]) CK(cudaStreamCreateWithFlags(&c->sf_stream[i], cudaStreamNonBlocking));
+        if (!c->sf_ready[i]) CK(cudaEventCreateWithFlags(&c->sf_ready[i], cudaEventDisableTiming));
+        if (!c->sf_copied[i]) CK(cudaEventCreateWithFlags(&c->sf_copied[i], cudaEventDisableTiming));
+        if (local_frames && !c->sf_local[i]) CK(cudaMalloc(&c->sf_local[i], (size_t)c->W * c->H * sizeof(uint2)));
+    }
+    return VKRT_OK;
+}
+void sf_lanes_free(VkrtContext* c, bool streams_too) {
+    for (int i = 0; i < VkrtContext::kSfLanes; ++i) {
+        if (c->sf_stream[i]) cudaStreamSynchronize(c->sf_stream[i]);
+        if (c->sf_local[i]) cudaFree(c->sf_local[i]);
+        c->sf_local[i] = nullptr;
+        if (streams_too) {
+            if (c->sf_ready[i]) cudaEventDestroy(c->sf_ready[i]);
+            if (c->sf_copied[i]) cudaEventDestroy(c->sf_copied[i]);
+            if (c->sf_stream[i]) cudaStreamDestroy(c->sf_stream[i]);
+            c->sf_ready[i] = c->sf_copied[i] = nullptr;
+            c->sf_stream[i] = nullptr;
+        }
+    }
+    c->sf_lane = 0;
+}
 void sf_release(VkrtContext* c) {
+    sf_lanes_free(c, false);  // the local frames have the frame's size
     if (!c->sf_base) return;
     if (c->own_frame) c->frame = c->own_frame;
     c->own_frame = nullptr;
@@ -469,6 +502,8 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
         if ((int)c->offsets_cache.size() != n || memcmp(c->offsets_cache.data(), offsets, (size_t)n * sizeof(VkrtOffset)) != 0) {
             c->offsets_cache.assign(offsets, offsets + n);
             CK(cudaStreamSynchronize(c->copy_stream));  // a sort-first push on the copy stream may still be reading the old table
+            CK(cudaStreamSynchronize(c->stream2));
+            for (cudaStream_t ls : c->sf_stream) if (ls) CK(cudaStreamSynchronize(ls));  // ... or a render on one of the lanes
             CK(cudaMemcpyAsync(c->d_offsets, c->offsets_cache.data(), (size_t)n * sizeof(VkrtOffset), cudaMemcpyHostToDevice, c->stream));
             // a launch on another stream (the sort-first root renders on the copy stream) must see the new table
             CK(cudaStreamSynchronize(c->stream));
@@ -610,6 +645,7 @@ int vkrt_destroy(VkrtContext* c) {
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     free_volume(c);
     free_frame(c);
+    sf_lanes_free(c, true);
     if (c->counters) cudaFree(c->counters);
     if (c->d_offsets) cudaFree(c->d_offsets);
     if (c->d_before) cudaFree(c->d_before);
@@ -871,6 +907,7 @@ int vkrt_sync(VkrtContext* c) {
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamSynchronize(c->copy_stream));
     CK(cudaStreamSynchronize(c->stream2));
+    for (cudaStream_t ls : c->sf_stream) if (ls) CK(cudaStreamSynchronize(ls));
     return VKRT_OK;
 }
 
@@ -1073,6 +1110,7 @@ int vkrt_timing_read(VkrtContext* c, float* ms, int n) {
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamSynchronize(c->copy_stream));  // the sort-first root renders (and records its events) on its other streams
     CK(cudaStreamSynchronize(c->stream2));
+    for (cudaStream_t ls : c->sf_stream) if (ls) CK(cudaStreamSynchronize(ls));
     const size_t cap = c->ring_begin.size();
     for (int i = 0; i < n; ++i) {  // oldest of the last n first
         const size_t k = (c->ring_next + cap - (size_t)n + (size_t)i) % cap;
@@ -1165,6 +1203,8 @@ int vkrt_sortfirst_leave(VkrtContext* c) {
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamSynchronize(c->copy_stream));  // group transfers into rank 0's ring may still be in flight
     CK(cudaStreamSynchronize(c->stream2));
+    for (cudaStream_t ls : c->sf_stream) if (ls) CK(cudaStreamSynchronize(ls));
+    CK(cudaStreamSynchronize(c->copy_stream));  // pushes queued behind a lane's render
     sf_release(c);
     return VKRT_OK;
 }
@@ -1205,46 +1245,44 @@ int vkrt_sortfirst_render(VkrtContext* c, const VkrtCameraUniform* cam, const Vk
     // slot reuse: the frame that used this slot last (frame_index - slots) must have been consumed
     const bool must_wait = frame_index >= (uint64_t)c->sf_slots;
     const uint64_t consumed_target = must_wait ? frame_index - (uint64_t)c->sf_slots + 1 : 0;
+    int rc = sf_lanes_ensure(c, c->sf_rank != 0);
+    if (rc) return rc;
+    const int lane = c->sf_lane;
+    c->sf_lane = (c->sf_lane + 1) % VkrtContext::kSfLanes;
+    cudaStream_t ls = c->sf_stream[lane];
     if (c->sf_rank == 0) {
-        // root: its tiles go straight into the ring slot (local memory) — on the SECOND stream: the context's stream
+        // root: its tiles go straight into the ring slot (local memory) — never on the context's own stream: that one
         // carries the in-order waits for every frame, and a render queued behind the wait for the peers' tiles of frame f
-        // would keep the root from starting its share of frame f + 1.
-        // Consecutive frames alternate between two render streams: a frame's tiles on 1/N of the GPUs are a short launch
-        // whose duration is set by its longest rays; the next frame's launch fills the SMs its tail leaves idle.
-        cudaStream_t rs = (frame_index & 1) ? c->stream2 : c->copy_stream;
-        if (must_wait) CK(launch_flag_wait(sf_consumed(c), consumed_target, sf_timeouts(c), rs));
-        if (eb) CK(cudaEventRecord(eb, rs));
-        int rc = do_render(c, cam, un, tiles ? offsets : nullptr, tiles ? n : 0, false, 1, sf_slot(c, slot), nullptr, rs);
+        // would keep the root from starting its share of frame f + 1. Consecutive frames rotate over the lanes: the next
+        // frames' launches fill the SMs that the tail of this one (its longest rays) leaves idle.
+        if (must_wait) CK(launch_flag_wait(sf_consumed(c), consumed_target, sf_timeouts(c), ls));
+        if (eb) CK(cudaEventRecord(eb, ls));
+        rc = do_render(c, cam, un, tiles ? offsets : nullptr, tiles ? n : 0, false, 1, sf_slot(c, slot), nullptr, ls);
         if (rc) return rc;
-        if (ee) CK(cudaEventRecord(ee, rs));
-        CK(launch_flag_add(sf_arrive(c, slot), 1ull, rs));
+        if (ee) CK(cudaEventRecord(ee, ls));
+        CK(launch_flag_add(sf_arrive(c, slot), 1ull, ls));
         return VKRT_OK;
     }
-    // peer: render into a LOCAL frame (two of them, alternating), then ship the tiles (or the whole frame) to rank 0's
-    // ring slot on the copy stream — whole tile rows in 16-byte stores over NVLink — overlapping this rank's next
-    // launch. The slot-reuse wait sits on the copy stream, so rendering runs ahead of rank 0's consumption.
-    int rc = ensure_batch(c, 1);
+    // peer: render into the lane's LOCAL frame, then ship the tiles (or the whole frame) to rank 0's ring slot on the copy
+    // stream — whole tile rows in 16-byte stores over NVLink — overlapping this rank's next launches. The slot-reuse wait
+    // sits on the copy stream, so rendering runs ahead of rank 0's consumption by up to kSfLanes frames.
+    CK(cudaStreamWaitEvent(ls, c->sf_copied[lane], 0));  // the lane's local frame has left (kSfLanes frames back)
+    if (eb) CK(cudaEventRecord(eb, ls));
+    rc = do_render(c, cam, un, tiles ? offsets : nullptr, tiles ? n : 0, false, 1, c->sf_local[lane], nullptr, ls);
     if (rc) return rc;
-    const int b = c->sf_parity;
-    c->sf_parity ^= 1;
-    cudaStream_t ps = b ? c->stream2 : c->stream;  // local frame b is always rendered on stream b (see the root's note)
-    CK(cudaStreamWaitEvent(ps, c->ev_group_copied[b], 0));  // local frame b has left (two frames back)
-    if (eb) CK(cudaEventRecord(eb, ps));
-    rc = do_render(c, cam, un, tiles ? offsets : nullptr, tiles ? n : 0, false, 1, c->batch_frames[b], nullptr, ps);
-    if (rc) return rc;
-    if (ee) CK(cudaEventRecord(ee, ps));
-    CK(cudaEventRecord(c->ev_group_ready[b], ps));
-    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_group_ready[b], 0));
+    if (ee) CK(cudaEventRecord(ee, ls));
+    CK(cudaEventRecord(c->sf_ready[lane], ls));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->sf_ready[lane], 0));
     if (must_wait) CK(launch_flag_wait(sf_consumed(c), consumed_target, sf_timeouts(c), c->copy_stream));
     if (tiles) {
         bool vec16 = (c->W % 2 == 0) && (c->params.tile_size % 2 == 0);
         for (int i = 0; i < n && vec16; ++i) vec16 = ((long long)offsets[i].x % 2) == 0 && offsets[i].x >= 0.0f;
-        CK(launch_push_tiles(c->batch_frames[b], sf_slot(c, slot), c->d_offsets, n, c->params.tile_size, c->W, c->H, vec16, c->copy_stream));
+        CK(launch_push_tiles(c->sf_local[lane], sf_slot(c, slot), c->d_offsets, n, c->params.tile_size, c->W, c->H, vec16, c->copy_stream));
     } else {
-        CK(cudaMemcpyAsync(sf_slot(c, slot), c->batch_frames[b], sf_frame_bytes(c), cudaMemcpyDeviceToDevice, c->copy_stream));
+        CK(cudaMemcpyAsync(sf_slot(c, slot), c->sf_local[lane], sf_frame_bytes(c), cudaMemcpyDeviceToDevice, c->copy_stream));
     }
     CK(launch_flag_add(sf_arrive(c, slot), 1ull, c->copy_stream));  // after the transfer, system scope
-    CK(cudaEventRecord(c->ev_group_copied[b], c->copy_stream));
+    CK(cudaEventRecord(c->sf_copied[lane], c->copy_stream));
     return VKRT_OK;
 }
 

@@ -71,7 +71,7 @@ class SortFirstGroup:
             ctx.set_params(p)
             self.tiles = partition_tiles(ctx.width, ctx.height, tile, rank, world)
         box = [ctx.sortfirst_create_root(world, self.slots) if rank == 0 else None]
-        if world > 1:  # (world == 1: the same pipeline on one GPU — ring, two render streams — without any plumbing)
+        if world > 1:  # (world == 1: the same pipeline on one GPU — ring, rotating render streams — without any plumbing)
             dist.broadcast_object_list(box, src=0)
             if rank != 0:
                 ctx.sortfirst_join(rank, box[0])

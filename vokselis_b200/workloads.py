@@ -20,9 +20,13 @@ import numpy as np
 from . import abi, rt
 
 SORTFIRST_CONFIGS = {
-    3: dict(name="configs[2]: synthetic 1024^3 fp16 noise volume at 3840x2160, image-tile sharded sort-first", kind=0, dtype=np.float16, n=1024, seed=3),
+    # layout: measured on one B200 (bench/sharded.py --layout 3|4): the dense fp16 fog is bound by the texture path and gains 19 %
+    # from the pre-gathered quads (3.29 -> 2.77 ms per 4K frame, 8 GiB of quads); the sparse volume is bound by traversal and is
+    # indifferent (0.691 vs 0.696 ms), so it keeps the layered array (8 GiB instead of 32 GiB)
+    3: dict(name="configs[2]: synthetic 1024^3 fp16 noise volume at 3840x2160, image-tile sharded sort-first", kind=0, dtype=np.float16, n=1024, seed=3,
+            layout=abi.LAYOUT_QUAD),
     4: dict(name="configs[3]: synthetic 2048^3 uint8 bricked volume with 90% empty space, skipping + early termination, 4K, image-tile sharded sort-first",
-            kind=1, dtype=np.uint8, n=2048, seed=4),
+            kind=1, dtype=np.uint8, n=2048, seed=4, layout=abi.LAYOUT_GATHER),
 }
 
 
@@ -52,7 +56,7 @@ def _gather_floats(value: float, dist, world: int) -> list[float]:
 
 
 def run_sortfirst_tiles(cid: int, rank: int, world: int, local: int, dist=None, frames: int = 24, warm: int = 4, tile: int = 120,
-                        layout: int = abi.LAYOUT_GATHER, res=(3840, 2160), edge: int | None = None, checks: bool = True, hbm_peak_gbs: float = 6650.0):
+                        layout: int | None = None, res=(3840, 2160), edge: int | None = None, checks: bool = True, hbm_peak_gbs: float = 6650.0):
     """configs[2] / configs[3] on `world` GPUs (one process each). N = 1: `single` on one GPU. N > 1: every frame is cut
     into tile x tile pixel tiles dealt over the ranks (volume replicated), each rank renders its tiles locally and ships
     them into rank 0's frame over NVLink; rank 0 waits for each frame in order. Timing: CUDA events on RANK 0's stream
@@ -63,6 +67,7 @@ def run_sortfirst_tiles(cid: int, rank: int, world: int, local: int, dist=None, 
     cfg = SORTFIRST_CONFIGS[cid]
     W, H = res
     n = edge or cfg["n"]
+    layout = cfg["layout"] if layout is None else layout
     ctx = rt.Context(local, W, H)
     t0 = time.perf_counter()
     ctx.generate_synthetic(cfg["kind"], cfg["dtype"], n, seed=cfg["seed"])
@@ -94,8 +99,8 @@ def run_sortfirst_tiles(cid: int, rank: int, world: int, local: int, dist=None, 
             ctx.render_tiles(cams[0], rt.tile_table(W, H, 256))
             out_checks["tile_equals_single"] = bool(np.array_equal(ref_frame, ctx.readback()))
         ctx.set_params(p)
-    # N = 1 runs the SAME pipeline (ring of frames in rank 0's memory, tiles of consecutive frames on alternating streams)
-    group = sortfirst.SortFirstGroup(ctx, rank, world, granularity="tiles", tile=tile, slots=4, dist=dist)
+    # N = 1 runs the SAME pipeline (ring of frames in rank 0's memory, tiles of consecutive frames on rotating streams)
+    group = sortfirst.SortFirstGroup(ctx, rank, world, granularity="tiles", tile=tile, slots=16, dist=dist)
     f = group.submit(cams[0])
     if rank == 0:
         group.wait(f)
@@ -138,12 +143,12 @@ def run_sortfirst_tiles(cid: int, rank: int, world: int, local: int, dist=None, 
         "config": cfg["name"], "volume_edge": n, "dtype": np.dtype(cfg["dtype"]).name, "resolution": [W, H], "n_gpus": world,
         "sharding": (f"one GPU: all {tile}-pixel tiles of a frame in one launch" if world == 1 else
                      f"sort-first, {tile}-pixel image tiles dealt over {world} ranks, tiles shipped to rank 0's frame over NVLink (P2P stores of whole tile rows)")
-                    + "; consecutive frames alternate between two render streams on every rank",
+                    + "; consecutive frames rotate over four render streams on every rank (a ring of 8 frames on rank 0)",
         "layout": layout, "frames": frames, "frames_per_s": 1e3 / ms, "ms_per_frame": ms,
         "timing": "CUDA events on rank 0's stream around the whole pipelined sequence (rank 0 waits for every frame's tiles in order); volume >> L2, no flush",
         "wall_ms_per_frame": 1e3 * wall / frames,
         "kernel_ms_per_frame_by_rank": [v / frames for v in per_rank], "busiest_rank_kernel_ms_per_frame": busiest,
-        "kernel_ms_note": "sum of each launch's own CUDA-event duration; launches of consecutive frames overlap (two streams), so these exceed the pipelined time",
+        "kernel_ms_note": "sum of each launch's own CUDA-event duration; launches of consecutive frames overlap (four streams), so these exceed the pipelined time",
         "ray_samples_per_s": st.samples_reference * 1e3 / ms, "fetched_samples_per_s": st.samples_fetched * 1e3 / ms,
         "samples_frame0": {"reference": int(st.samples_reference), "fetched": int(st.samples_fetched), "rays": int(st.rays_hit)},
         "bricks": {"total": info["bricks_total"], "occupied": info["bricks_occupied"]}, "volume_bytes": vol_bytes, "generate_s": gen_s,
@@ -206,7 +211,13 @@ def run_sortlast(rank: int, world: int, local: int, dist, edge: int = 4096, fram
         "frames": frames, "ms_per_frame": mean_ms, "frames_per_s": 1e3 / mean_ms, "per_frame_ms": per_frame, "generate_s_rank0": gen_s,
         "phase_ms_mean_max_over_ranks": {k: max(v) for k, v in gathered.items()}, "phase_ms_mean_by_rank": gathered,
         "exchange_bytes_per_rank_per_frame": {"all_gather_T": (world - 1) * W * H * 4, "reduce_rgba": W * H * 16},
-        "exchange_share_of_frame": (max(gathered["all_gather"]) + max(gathered["reduce"])) / mean_ms,
+        # A collective is also where a rank that finished its march early WAITS for the slowest one: on the rank that arrives
+        # last the phase lasts as long as the transfer itself, on the others transfer + wait. The transfer cost is therefore
+        # the MIN over ranks, the imbalance of the march is max - min of the march phase.
+        "exchange_ms": {"all_gather_transfer": min(gathered["all_gather"]), "reduce_transfer": min(gathered["reduce"]),
+                        "all_gather_incl_wait_for_slowest_march": max(gathered["all_gather"]),
+                        "march_imbalance_max_minus_min": max(gathered["march"]) - min(gathered["march"])},
+        "exchange_share_of_frame": (min(gathered["all_gather"]) + min(gathered["reduce"])) / mean_ms,
         "timing": "CUDA events on every rank's own stream between the phases of a frame (march from alpha 0, NCCL all-gather of transmittances, resolve, re-march of "
                   "the flagged pixels, NCCL sum onto rank 0, finalize); ms_per_frame = max over ranks of the whole frame, mean over frames; L2 flushed before each frame",
         "roofline": {"bound": "hbm", "achieved": per_rank_bytes / (march * 1e-3) / 1e9, "peak": hbm_peak_gbs, "unit": "GB/s",
