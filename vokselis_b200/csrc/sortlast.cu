@@ -71,14 +71,25 @@ template <> struct WinElem<VKRT_F32> { typedef float type; };
 // addresses are 32-bit sums of those strides added to the corner pointer (one IMAD.WIDE each). The first
 // version built six 64-bit per-axis parts and four 64-bit row sums per sample; ncu showed that address
 // arithmetic as 29 % of the kernel's instructions on an ALU-bound kernel (profiles/r01_v3_prof_final_partial.md).
-template <int DTYPE> __device__ __forceinline__ float win_sample(const PartialArgs& A, float qx, float qy, float qz) {
+struct Taps {
+    uint32_t r[8];     // raw taps c000 c100 c010 c110 c001 c101 c011 c111
+    float fx, fy, fz;  // fractional weights
+};
+// WINDOW: also clamp the low corner into the window (a SPECULATIVE fetch of a sample that may turn out not to be this
+// rank's: the address must be valid, the value is thrown away if the sample is not evaluated).
+template <int DTYPE, bool WINDOW> __device__ __forceinline__ void win_fetch(const PartialArgs& A, float qx, float qy, float qz, Taps& T) {
     const float ux = __fsub_rn(qx, 0.5f), uy = __fsub_rn(qy, 0.5f), uz = __fsub_rn(qz, 0.5f);
     const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
-    const float fx = __fsub_rn(ux, flx), fy = __fsub_rn(uy, fly), fz = __fsub_rn(uz, flz);
+    T.fx = __fsub_rn(ux, flx); T.fy = __fsub_rn(uy, fly); T.fz = __fsub_rn(uz, flz);
     const int x0 = (int)flx, y0 = (int)fly, z0 = (int)flz;
     const int xa = min(max(x0, 0), A.gnx - 1), ya = min(max(y0, 0), A.gny - 1), za = min(max(z0, 0), A.gnz - 1);
-    const bool mx = xa != min(max(x0 + 1, 0), A.gnx - 1), my = ya != min(max(y0 + 1, 0), A.gny - 1), mz = za != min(max(z0 + 1, 0), A.gnz - 1);
-    const uint32_t lx = (uint32_t)(xa - A.wx), ly = (uint32_t)(ya - A.wy), lz = (uint32_t)(za - A.wz);
+    bool mx = xa != min(max(x0 + 1, 0), A.gnx - 1), my = ya != min(max(y0 + 1, 0), A.gny - 1), mz = za != min(max(z0 + 1, 0), A.gnz - 1);
+    uint32_t lx = (uint32_t)(xa - A.wx), ly = (uint32_t)(ya - A.wy), lz = (uint32_t)(za - A.wz);
+    if (WINDOW) {  // the high taps of a clamped corner fold onto it (strides 0) unless they are inside the window too
+        const int cx = min(max(xa - A.wx, 0), A.nx - 1), cy = min(max(ya - A.wy, 0), A.ny - 1), cz = min(max(za - A.wz, 0), A.nz - 1);
+        mx = mx && cx + 1 < A.nx; my = my && cy + 1 < A.ny; mz = mz && cz + 1 < A.nz;
+        lx = (uint32_t)cx; ly = (uint32_t)cy; lz = (uint32_t)cz;
+    }
     size_t base;
     uint32_t dx, dy, dz;
     if (A.bricked) {
@@ -98,14 +109,24 @@ template <int DTYPE> __device__ __forceinline__ float win_sample(const PartialAr
     const uint32_t dxy = dx + dy;
     const typename WinElem<DTYPE>::type *p100 = c + dx, *p010 = c + dy, *p110 = c + dxy, *p001 = c + dz, *p101 = c + (dz + dx),
                                         *p011 = c + (dz + dy), *p111 = c + (dz + dxy);
-    const uint32_t r000 = win_raw<DTYPE>(c), r100 = win_raw<DTYPE>(p100), r010 = win_raw<DTYPE>(p010), r110 = win_raw<DTYPE>(p110);
-    const uint32_t r001 = win_raw<DTYPE>(p001), r101 = win_raw<DTYPE>(p101), r011 = win_raw<DTYPE>(p011), r111 = win_raw<DTYPE>(p111);
-    const float c000 = win_cvt<DTYPE>(r000), c100 = win_cvt<DTYPE>(r100), c010 = win_cvt<DTYPE>(r010), c110 = win_cvt<DTYPE>(r110);
-    const float c001 = win_cvt<DTYPE>(r001), c101 = win_cvt<DTYPE>(r101), c011 = win_cvt<DTYPE>(r011), c111 = win_cvt<DTYPE>(r111);
+    T.r[0] = win_raw<DTYPE>(c); T.r[1] = win_raw<DTYPE>(p100); T.r[2] = win_raw<DTYPE>(p010); T.r[3] = win_raw<DTYPE>(p110);
+    T.r[4] = win_raw<DTYPE>(p001); T.r[5] = win_raw<DTYPE>(p101); T.r[6] = win_raw<DTYPE>(p011); T.r[7] = win_raw<DTYPE>(p111);
+}
+template <int DTYPE> __device__ __forceinline__ float win_resolve(const Taps& T) {
+    const float c000 = win_cvt<DTYPE>(T.r[0]), c100 = win_cvt<DTYPE>(T.r[1]), c010 = win_cvt<DTYPE>(T.r[2]), c110 = win_cvt<DTYPE>(T.r[3]);
+    const float c001 = win_cvt<DTYPE>(T.r[4]), c101 = win_cvt<DTYPE>(T.r[5]), c011 = win_cvt<DTYPE>(T.r[6]), c111 = win_cvt<DTYPE>(T.r[7]);
+    const float fx = T.fx, fy = T.fy, fz = T.fz;
     const float c00 = fmaf(fx, __fsub_rn(c100, c000), c000), c10 = fmaf(fx, __fsub_rn(c110, c010), c010);
     const float c01 = fmaf(fx, __fsub_rn(c101, c001), c001), c11 = fmaf(fx, __fsub_rn(c111, c011), c011);
     const float c0 = fmaf(fy, __fsub_rn(c10, c00), c00), c1 = fmaf(fy, __fsub_rn(c11, c01), c01);
     return __fmul_rn(fmaf(fz, __fsub_rn(c1, c0), c0), DTYPE == VKRT_U8 ? 1.0f / 255.0f : 1.0f);
+}
+
+// speculative fetch of the sample at parameter t (exact position arithmetic: the very q the loop computes for that t)
+template <int DTYPE> __device__ __forceinline__ void fetch_at(const PartialArgs& A, f3 eye, f3 dir, float t, Taps& T) {
+    const float qx = xmul(xadd(xadd(eye.x, xmul(t, dir.x)), 1.0f), A.hx), qy = xmul(xadd(xadd(eye.y, xmul(t, dir.y)), 1.0f), A.hy),
+                qz = xmul(xadd(xadd(eye.z, xmul(t, dir.z)), 1.0f), A.hz);
+    win_fetch<DTYPE, true>(A, qx, qy, qz, T);
 }
 
 template <int MODE, int DTYPE, int PASS>
@@ -164,6 +185,8 @@ __global__ void __launch_bounds__(256) partial_kernel(const __grid_constant__ Pa
             const float dqx = dir.x * A.hx * dt, dqy = dir.y * A.hy * dt, dqz = dir.z * A.hz * dt;
             const float rqx = fabsf(dqx) > 1e-12f ? 1.0f / dqx : 1e30f, rqy = fabsf(dqy) > 1e-12f ? 1.0f / dqy : 1e30f,
                         rqz = fabsf(dqz) > 1e-12f ? 1.0f / dqz : 1e30f;
+            Taps cur, pre;
+            float pre_t = -1.0f;  // the t whose taps `pre` holds (t >= 0 always)
             while (t < t1 && t < t_stop) {
                 f3 p = {xadd(eye.x, xmul(t, dir.x)), xadd(eye.y, xmul(t, dir.y)), xadd(eye.z, xmul(t, dir.z))};
                 const float qx = xmul(xadd(p.x, 1.0f), A.hx), qy = xmul(xadd(p.y, 1.0f), A.hy), qz = xmul(xadd(p.z, 1.0f), A.hz);
@@ -210,7 +233,23 @@ __global__ void __launch_bounds__(256) partial_kernel(const __grid_constant__ Pa
                         m0_shade(col, c, nrm, p, A.clear);
                     }
                 } else {
-                    const float s = win_sample<DTYPE>(A, qx, qy, qz);
+                    // Two samples in flight. At 32-128 GiB per rank a sample's taps mostly miss L1 and L2, the march waits
+                    // on that latency (ncu at 32 GiB: issue active 21 %, DRAM 35 %, long-scoreboard stalls 34 of the 41
+                    // cycles between issues; more resident warps make it SLOWER — they evict each other's sectors —
+                    // fewer make it faster, profiles/r02_sortlast_march.md), and the next sample's addresses depend on
+                    // nothing but t. So the taps of t + dt are requested before this sample's are consumed: every second
+                    // wait finds its data already there. A speculative fetch that is not used (leap, other rank's
+                    // voxel, termination) costs its loads and nothing else; the values are those the unpipelined loop reads.
+                    // (Three in flight: 98 registers, faster for some view directions and slower for others; not kept.)
+                    if (!(pre_t == t)) win_fetch<DTYPE, false>(A, qx, qy, qz, cur);
+                    else cur = pre;
+                    const float tn = xadd(t, dt);
+                    pre_t = -1.0f;
+                    if (tn < t1 && tn < t_stop) {
+                        fetch_at<DTYPE>(A, eye, dir, tn, pre);
+                        pre_t = tn;
+                    }
+                    const float s = win_resolve<DTYPE>(cur);
                     if (PASS == PASS_ALPHA) T *= 1.0f - m1_alpha(s);
                     else m1_shade(col, s);
                 }
