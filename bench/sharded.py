@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--edge5", type=int, default=4096)
     ap.add_argument("--edge34", type=int, default=0)
     ap.add_argument("--tile", type=int, default=120)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="sort-last transmittance exchange")
     ap.add_argument("--layout", type=int, default=-1, help="-1 = the layout workloads.py chose per config")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -47,7 +48,7 @@ def main():
             if rank == 0:
                 print(json.dumps(r), flush=True)
     if "5" in what and world > 1:
-        r = workloads.run_sortlast(rank, world, local, dist, edge=args.edge5, frames=max(args.frames // 4, 3), hbm_peak_gbs=peak)
+        r = workloads.run_sortlast(rank, world, local, dist, edge=args.edge5, frames=max(args.frames // 4, 3), hbm_peak_gbs=peak, exchange=args.exchange)
         if rank == 0:
             print(json.dumps(r), flush=True)
     if world > 1:

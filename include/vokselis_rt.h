@@ -313,7 +313,7 @@ VKRT_API int vkrt_sortfirst_timeouts(VkrtContext* ctx, uint64_t* out);
  * one-voxel halo (the "window"). Every rank walks the same global t sequence per ray and evaluates
  * the samples whose voxel index lies in its brick. A frame, with ranks in visibility order:
  *   all   : vkrt_partial_alpha(cam, d_T)            T = per-pixel transmittance of the rank's brick
- *   (all-gather T across ranks — any transport; vokselis_b200/sortlast.py uses NCCL)
+ *   (T of the ranks in front must reach every rank — any transport; vokselis_b200/sortlast.py uses vkrt_exchange_*, or NCCL)
  *   all   : vkrt_partial_ain(d_T_all, ranks in front of me, n, d_ain)
  *   all   : vkrt_partial_color(cam, d_ain, d_rgba)  premultiplied rgb + alpha, early termination exact
  *   (sum d_rgba over ranks onto rank 0 — NCCL reduce)
@@ -335,6 +335,31 @@ VKRT_API int vkrt_partial_color(VkrtContext* ctx, const VkrtCameraUniform* cam, 
 VKRT_API int vkrt_partial_relative(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un, float* d_rgba, float* d_T);
 VKRT_API int vkrt_partial_resolve(VkrtContext* ctx, const float* d_T_all, const int* ranks_before, int n_before, float* d_rgba, float* d_ain);
 VKRT_API int vkrt_partial_finalize(VkrtContext* ctx, const VkrtCameraUniform* cam, const VkrtUniform* un, const float* d_sum_rgba);
+
+/* Direct-send exchange of the transmittance images between the ranks of a sort-last group (one process per GPU), over
+ * NVLink peer memory instead of a collective: every rank owns a double-buffered table T[2][world][W*H] plus a mailbox,
+ * exports it (CUDA IPC) and maps everybody else's. Per frame f, with the ranks in visibility order:
+ *   vkrt_exchange_push(d_T, ranks behind me, n, f)   one kernel reads d_T once and stores it into slot [f&1][my rank] of every
+ *                                                    rank that composites behind me (16-byte stores, full NVLink lines), then
+ *                                                    raises their arrival counters; waits first until they have resolved f-2
+ *   vkrt_exchange_wait(f, arrivals)                  device-side wait until `arrivals` images of frame f have landed here
+ *   vkrt_exchange_table(f)                           the [world][W*H] table of frame f (for vkrt_partial_ain / _resolve)
+ *   vkrt_exchange_done(f)                            after the resolve: the parity of f may be overwritten by frame f+2
+ * Only ranks IN FRONT of a rank send to it, so a rank receives what its resolve reads and nothing else (an all-gather moves
+ * every image to every rank). All calls are asynchronous on the context's stream; waits give up after 10 s
+ * (vkrt_exchange_timeouts). Replaces nothing in the reference (single-device). */
+typedef struct VkrtExchangeHandle {
+    uint8_t ipc[64];
+    int32_t width, height, world, rank;
+} VkrtExchangeHandle;
+VKRT_API int vkrt_exchange_create(VkrtContext* ctx, int rank, int world, VkrtExchangeHandle* out);
+VKRT_API int vkrt_exchange_open(VkrtContext* ctx, const VkrtExchangeHandle* all_ranks /* [world], index = rank */);
+VKRT_API int vkrt_exchange_push(VkrtContext* ctx, const float* d_T, const int* ranks_behind, int n_behind, uint64_t frame);
+VKRT_API int vkrt_exchange_wait(VkrtContext* ctx, uint64_t frame, int arrivals);
+VKRT_API const float* vkrt_exchange_table(VkrtContext* ctx, uint64_t frame);
+VKRT_API int vkrt_exchange_done(VkrtContext* ctx, uint64_t frame);
+VKRT_API int vkrt_exchange_timeouts(VkrtContext* ctx, uint64_t* out);
+VKRT_API int vkrt_exchange_close(VkrtContext* ctx);
 
 /* Eight user events on the context's stream: vkrt_mark records one, vkrt_mark_elapsed returns the
  * device time between two (ms). */

@@ -109,6 +109,13 @@ struct VkrtContext {
     int gn[3] = {0, 0, 0}, win_lo[3] = {0, 0, 0}, own_lo[3] = {0, 0, 0}, own_hi[3] = {0, 0, 0};
     int cell_lo[3] = {0, 0, 0}, cell_n[3] = {0, 0, 0};
     int* d_before = nullptr;
+    // sort-last direct-send exchange (vkrt_exchange_*): own table + mailbox, and the peers' mapped through CUDA IPC
+    static constexpr int kXMaxWorld = 16;
+    static constexpr size_t kXMailbox = 4096;  // u64 [0], [1]: arrivals of the even / odd frames; [2]: frames resolved; [3]: timeouts
+    unsigned char* x_base = nullptr;
+    unsigned char* x_peer[kXMaxWorld] = {};
+    int x_rank = -1, x_world = 0;
+    unsigned long long x_expected[2] = {0, 0};  // cumulative arrivals expected per parity
     // tile offsets
     VkrtOffset* d_offsets = nullptr;
     int offsets_cap = 0;
@@ -143,6 +150,23 @@ void free_volume(VkrtContext* c) {
     c->dist = nullptr;
     c->kind = VOL_NONE;
     c->windowed = false;
+}
+// ---- sort-last direct-send exchange: helpers ----
+size_t x_image_floats(const VkrtContext* c) { return (size_t)c->W * c->H; }
+float* x_table(const VkrtContext* c, unsigned char* base, uint64_t frame) {
+    return reinterpret_cast<float*>(base + VkrtContext::kXMailbox) + (size_t)(frame & 1u) * (size_t)c->x_world * x_image_floats(c);
+}
+unsigned long long* x_flag(unsigned char* base, int i) { return reinterpret_cast<unsigned long long*>(base) + i; }
+void x_release(VkrtContext* c) {
+    for (int r = 0; r < VkrtContext::kXMaxWorld; ++r) {
+        if (c->x_peer[r] && r != c->x_rank) cudaIpcCloseMemHandle(c->x_peer[r]);
+        c->x_peer[r] = nullptr;
+    }
+    if (c->x_base) cudaFree(c->x_base);
+    c->x_base = nullptr;
+    c->x_rank = -1;
+    c->x_world = 0;
+    c->x_expected[0] = c->x_expected[1] = 0;
 }
 int sf_lanes_ensure(VkrtContext* c, bool local_frames) {
     for (int i = 0; i < VkrtContext::kSfLanes; ++i) {
@@ -646,6 +670,7 @@ int vkrt_destroy(VkrtContext* c) {
     free_volume(c);
     free_frame(c);
     sf_lanes_free(c, true);
+    x_release(c);
     if (c->counters) cudaFree(c->counters);
     if (c->d_offsets) cudaFree(c->d_offsets);
     if (c->d_before) cudaFree(c->d_before);
@@ -1566,6 +1591,103 @@ int vkrt_partial_finalize(VkrtContext* c, const VkrtCameraUniform* cam, const Vk
     int rc = fill_partial_args(c, cam, A);
     if (rc) return rc;
     CK(launch_partial_finalize(A, reinterpret_cast<const float4*>(d_sum_rgba), c->frame, c->params.mode, c->params.m1_srgb, c->stream));
+    return VKRT_OK;
+}
+
+// ---- sort-last direct-send exchange (helpers: above, before the extern "C" block) ----
+int vkrt_exchange_create(VkrtContext* c, int rank, int world, VkrtExchangeHandle* out) {
+    if (!c || !out || world < 1 || world > VkrtContext::kXMaxWorld || rank < 0 || rank >= world) return fail(VKRT_ERR_INVALID, "bad exchange arguments (world <= 16)");
+    if ((x_image_floats(c) & 3u) != 0) return fail(VKRT_ERR_UNSUPPORTED, "the exchange moves 16-byte vectors: W*H must be a multiple of 4");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    x_release(c);
+    c->x_world = world;
+    c->x_rank = rank;
+    const size_t bytes = VkrtContext::kXMailbox + 2 * (size_t)world * x_image_floats(c) * sizeof(float);
+    cudaError_t e = cudaMalloc(&c->x_base, bytes);
+    if (e != cudaSuccess) { x_release(c); return cuda_fail(e, "vkrt_exchange_create"); }
+    CK(cudaMemsetAsync(c->x_base, 0, VkrtContext::kXMailbox, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // completed before the handle leaves (see vkrt_sortfirst_create_root)
+    c->x_peer[rank] = c->x_base;
+    memset(out, 0, sizeof *out);
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->x_base));
+    static_assert(sizeof(h) <= sizeof(out->ipc), "IPC handle size");
+    memcpy(out->ipc, &h, sizeof h);
+    out->width = c->W; out->height = c->H; out->world = world; out->rank = rank;
+    return VKRT_OK;
+}
+
+int vkrt_exchange_open(VkrtContext* c, const VkrtExchangeHandle* all) {
+    if (!c || !all || !c->x_base) return fail(VKRT_ERR_INVALID, "vkrt_exchange_create first");
+    CK(cudaSetDevice(c->device));
+    for (int r = 0; r < c->x_world; ++r) {
+        if (r == c->x_rank) continue;
+        if (all[r].width != c->W || all[r].height != c->H || all[r].world != c->x_world || all[r].rank != r)
+            return fail(VKRT_ERR_INVALID, "exchange handle does not match this group (frame size / world / rank)");
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, all[r].ipc, sizeof ih);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+        c->x_peer[r] = (unsigned char*)p;
+    }
+    return VKRT_OK;
+}
+
+int vkrt_exchange_push(VkrtContext* c, const float* d_T, const int* ranks_behind, int n_behind, uint64_t frame) {
+    if (!c || !c->x_base || !d_T || n_behind < 0 || (n_behind > 0 && !ranks_behind) || n_behind > kMaxPushDst) return fail(VKRT_ERR_INVALID, "bad exchange_push arguments");
+    CK(cudaSetDevice(c->device));
+    PushDst tables{}, arrive{}, done{};
+    for (int k = 0; k < n_behind; ++k) {
+        const int r = ranks_behind[k];
+        if (r < 0 || r >= c->x_world || r == c->x_rank || !c->x_peer[r]) return fail(VKRT_ERR_INVALID, "exchange_push: no such peer (vkrt_exchange_open?)");
+        tables.ptr[k] = x_table(c, c->x_peer[r], frame) + (size_t)c->x_rank * x_image_floats(c);
+        arrive.ptr[k] = x_flag(c->x_peer[r], (int)(frame & 1u));
+        done.ptr[k] = x_flag(c->x_peer[r], 2);
+    }
+    tables.n = arrive.n = done.n = n_behind;
+    // the receivers must have resolved frame - 2 (same parity) before its table is overwritten
+    if (frame >= 2) CK(launch_flag_wait_many(done, frame - 1, x_flag(c->x_base, 3), c->stream));
+    CK(launch_push_many(d_T, tables, x_image_floats(c), c->stream));
+    CK(launch_flag_add_many(arrive, 1ull, c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_exchange_wait(VkrtContext* c, uint64_t frame, int arrivals) {
+    if (!c || !c->x_base || arrivals < 0) return fail(VKRT_ERR_INVALID, "bad exchange_wait arguments");
+    CK(cudaSetDevice(c->device));
+    c->x_expected[frame & 1u] += (unsigned long long)arrivals;
+    if (arrivals > 0) CK(launch_flag_wait(x_flag(c->x_base, (int)(frame & 1u)), c->x_expected[frame & 1u], x_flag(c->x_base, 3), c->stream));
+    return VKRT_OK;
+}
+
+const float* vkrt_exchange_table(VkrtContext* c, uint64_t frame) {
+    if (!c || !c->x_base) return nullptr;
+    return x_table(c, c->x_base, frame);
+}
+
+int vkrt_exchange_done(VkrtContext* c, uint64_t frame) {
+    if (!c || !c->x_base) return fail(VKRT_ERR_INVALID, "no exchange");
+    CK(cudaSetDevice(c->device));
+    CK(launch_flag_set(x_flag(c->x_base, 2), (unsigned long long)frame + 1ull, c->stream));
+    return VKRT_OK;
+}
+
+int vkrt_exchange_timeouts(VkrtContext* c, uint64_t* out) {
+    if (!c || !out || !c->x_base) return fail(VKRT_ERR_INVALID, "no exchange");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    unsigned long long v = 0;
+    CK(cudaMemcpy(&v, x_flag(c->x_base, 3), sizeof v, cudaMemcpyDeviceToHost));
+    *out = v;
+    return VKRT_OK;
+}
+
+int vkrt_exchange_close(VkrtContext* c) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    x_release(c);
     return VKRT_OK;
 }
 

@@ -111,6 +111,15 @@ cudaError_t launch_brick_window(const void* lin, void* out, int elem_bytes, int 
 cudaError_t launch_push_tiles(const uint2* src, uint2* dst, const VkrtOffset* d_offsets, int n_tiles, int tile, int W, int H, bool vec16,
                               cudaStream_t s);
 cudaError_t launch_flush_l2(uint4* buf, size_t n16, cudaStream_t s);
+// sort-last direct-send: up to kMaxPushDst destinations (peer memory) per launch
+constexpr int kMaxPushDst = 15;
+struct PushDst {
+    void* ptr[kMaxPushDst];
+    int n;
+};
+cudaError_t launch_push_many(const float* src, const PushDst& d, size_t n_floats, cudaStream_t s);  // n_floats % 4 == 0
+cudaError_t launch_flag_wait_many(const PushDst& d, unsigned long long target, unsigned long long* timeouts, cudaStream_t s);
+cudaError_t launch_flag_add_many(const PushDst& d, unsigned long long v, cudaStream_t s);
 cudaError_t launch_flag_wait(const unsigned long long* flag, unsigned long long target, unsigned long long* timeouts, cudaStream_t s);
 cudaError_t launch_flag_add(unsigned long long* flag, unsigned long long v, cudaStream_t s);
 cudaError_t launch_flag_set(unsigned long long* flag, unsigned long long v, cudaStream_t s);

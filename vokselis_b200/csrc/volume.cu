@@ -440,6 +440,47 @@ cudaError_t launch_flag_set(unsigned long long* flag, unsigned long long v, cuda
     return cudaGetLastError();
 }
 
+// Sort-last direct-send (vkrt_exchange_*): one pass over a W*H float image, stored into up to kMaxPushDst peer tables over
+// NVLink — consecutive lanes write consecutive 16-byte vectors, so the links carry full 128-byte lines; the image is
+// read once however many ranks need it.
+__global__ void __launch_bounds__(256) push_many_kernel(const float4* __restrict__ src, PushDst d, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(src + i);
+        for (int k = 0; k < d.n; ++k) reinterpret_cast<float4*>(d.ptr[k])[i] = v;
+    }
+}
+// spin until every flag >= target (slot reuse: the receivers have resolved the frame that used this parity before)
+__global__ void flag_wait_many_kernel(PushDst d, unsigned long long target, unsigned long long* timeouts) {
+    const unsigned long long t0 = global_timer_ns();
+    for (int k = 0; k < d.n; ++k) {
+        const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(d.ptr[k]);
+        while (*f < target) {
+            __nanosleep(200);
+            if (global_timer_ns() - t0 > 10000000000ull) {
+                atomicAdd_system(timeouts, 1ull);
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+}
+__global__ void flag_add_many_kernel(PushDst d, unsigned long long v) {
+    __threadfence_system();  // (the push kernel before this one in the stream has completed: its peer stores are performed)
+    for (int k = 0; k < d.n; ++k) atomicAdd_system(reinterpret_cast<unsigned long long*>(d.ptr[k]), v);
+}
+cudaError_t launch_push_many(const float* src, const PushDst& d, size_t n, cudaStream_t s) {
+    if (d.n > 0) push_many_kernel<<<148 * 8, 256, 0, s>>>(reinterpret_cast<const float4*>(src), d, n / 4);
+    return cudaGetLastError();
+}
+cudaError_t launch_flag_wait_many(const PushDst& d, unsigned long long target, unsigned long long* timeouts, cudaStream_t s) {
+    if (d.n > 0) flag_wait_many_kernel<<<1, 1, 0, s>>>(d, target, timeouts);
+    return cudaGetLastError();
+}
+cudaError_t launch_flag_add_many(const PushDst& d, unsigned long long v, cudaStream_t s) {
+    if (d.n > 0) flag_add_many_kernel<<<1, 1, 0, s>>>(d, v);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_flush_l2(uint4* buf, size_t n16, cudaStream_t s) {
     static uint32_t tag = 0;
     flush_l2_kernel<<<148 * 8, 256, 0, s>>>(buf, n16, ++tag);

@@ -35,6 +35,8 @@ EXPORTS = [
     "vkrt_alloc_host", "vkrt_free_host", "vkrt_host_register", "vkrt_host_unregister", "vkrt_generate_synthetic", "vkrt_download_scalar", "vkrt_scalar_to_rgba16f",
     "vkrt_upload_window", "vkrt_generate_synthetic_window", "vkrt_window_info", "vkrt_partial_alpha", "vkrt_partial_ain",
     "vkrt_partial_color", "vkrt_partial_finalize", "vkrt_partial_relative", "vkrt_partial_resolve",
+    "vkrt_exchange_create", "vkrt_exchange_open", "vkrt_exchange_push", "vkrt_exchange_wait", "vkrt_exchange_table", "vkrt_exchange_done",
+    "vkrt_exchange_timeouts", "vkrt_exchange_close",
 ]
 
 
@@ -127,6 +129,14 @@ def lib() -> C.CDLL:
         "vkrt_sortfirst_render_batch": (ci, [vp, vp, ci, C.POINTER(Uniform), C.c_uint64, ci]),
         "vkrt_sortfirst_consume": (ci, [vp, C.c_uint64, ci]),
         "vkrt_sortfirst_timeouts": (ci, [vp, C.POINTER(C.c_uint64)]),
+        "vkrt_exchange_create": (ci, [vp, ci, ci, vp]),
+        "vkrt_exchange_open": (ci, [vp, vp]),
+        "vkrt_exchange_push": (ci, [vp, vp, vp, ci, C.c_uint64]),
+        "vkrt_exchange_wait": (ci, [vp, C.c_uint64, ci]),
+        "vkrt_exchange_table": (vp, [vp, C.c_uint64]),
+        "vkrt_exchange_done": (ci, [vp, C.c_uint64]),
+        "vkrt_exchange_timeouts": (ci, [vp, C.POINTER(C.c_uint64)]),
+        "vkrt_exchange_close": (ci, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -520,6 +530,38 @@ class Context:
     def partial_resolve(self, d_T_all: int, ranks_before, d_rgba: int, d_ain: int):
         rb = np.ascontiguousarray(np.asarray(list(ranks_before), np.int32))
         _check(lib().vkrt_partial_resolve(self._h, d_T_all, _vp(rb) if rb.size else None, int(rb.size), d_rgba, d_ain))
+
+    # -- sort-last direct-send exchange of the transmittance images (one process per GPU) -------------------
+    def exchange_create(self, rank: int, world: int) -> bytes:
+        h = (C.c_ubyte * 80)()
+        _check(lib().vkrt_exchange_create(self._h, rank, world, C.byref(h)))
+        return bytes(h)
+
+    def exchange_open(self, handles):
+        """handles: the 80-byte blobs of exchange_create of ALL ranks, indexed by rank."""
+        blob = (C.c_ubyte * (80 * len(handles))).from_buffer_copy(b"".join(handles))
+        _check(lib().vkrt_exchange_open(self._h, C.byref(blob)))
+
+    def exchange_push(self, d_T: int, ranks_behind, frame: int):
+        rb = np.ascontiguousarray(np.asarray(list(ranks_behind), np.int32))
+        _check(lib().vkrt_exchange_push(self._h, d_T, _vp(rb) if rb.size else None, int(rb.size), frame))
+
+    def exchange_wait(self, frame: int, arrivals: int):
+        _check(lib().vkrt_exchange_wait(self._h, frame, int(arrivals)))
+
+    def exchange_table(self, frame: int) -> int:
+        return int(lib().vkrt_exchange_table(self._h, frame) or 0)
+
+    def exchange_done(self, frame: int):
+        _check(lib().vkrt_exchange_done(self._h, frame))
+
+    def exchange_timeouts(self) -> int:
+        v = C.c_uint64(0)
+        _check(lib().vkrt_exchange_timeouts(self._h, C.byref(v)))
+        return int(v.value)
+
+    def exchange_close(self):
+        _check(lib().vkrt_exchange_close(self._h))
 
     def partial_finalize(self, cam: CameraUniform, d_sum: int, uniform: Uniform | None = None):
         un = uniform if uniform is not None else self.global_uniform

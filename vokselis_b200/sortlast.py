@@ -73,7 +73,7 @@ class SortLastGroup:
     """Drives one frame across the ranks. `torch` tensors hold the exchange buffers; collectives run on
     the context's own stream (torch.cuda.ExternalStream), so no host synchronisation is needed."""
 
-    def __init__(self, ctx, rank: int, world: int, gn, dist=None, grid=None, scheme: str = "deferred"):
+    def __init__(self, ctx, rank: int, world: int, gn, dist=None, grid=None, scheme: str = "deferred", exchange: str = "p2p"):
         import torch
 
         if dist is None:
@@ -89,11 +89,35 @@ class SortLastGroup:
         dev = torch.device("cuda", ctx.device)
         self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
         self.T = torch.empty(n, dtype=torch.float32, device=dev)
-        self.T_all = torch.empty(world * n, dtype=torch.float32, device=dev)
+        self.T_all = None  # (nccl transport: allocated below)
         self.ain = torch.empty(n, dtype=torch.float32, device=dev)
         self.rgba = torch.empty(n * 4, dtype=torch.float32, device=dev)
+        # Transmittance exchange. "p2p" (default): direct-send over NVLink peer memory, vkrt_exchange_* — every rank stores its
+        # image straight into the tables of the ranks BEHIND it (the only ones whose resolve reads it), one kernel, no
+        # collective; torch.distributed only ships the IPC handles. "nccl": all-gather of every image to every rank.
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError(exchange)
+        self.exchange = exchange if world > 1 else "nccl"
+        self.frame = 0
+        if self.exchange == "p2p":
+            mine = ctx.exchange_create(rank, world)
+            handles = [None] * world
+            dist.all_gather_object(handles, mine)
+            ctx.exchange_open(handles)
+            dist.barrier()
+        else:
+            self.T_all = torch.empty(world * n, dtype=torch.float32, device=dev)
 
-    PHASES = ("march", "all_gather", "resolve", "remarch", "reduce", "finalize")
+    PHASES = ("march", "all_gather", "resolve", "remarch", "reduce", "finalize")  # "all_gather" = the transmittance exchange, whichever transport
+
+    def close(self):
+        """Release the peer mappings (all ranks; synchronises)."""
+        if self.exchange == "p2p":
+            self.ctx.sync()
+            self.dist.barrier()
+            self.ctx.exchange_close()
+            self.dist.barrier()
+            self.exchange = "closed"
 
     @staticmethod
     def eye_of(cam):
@@ -121,15 +145,25 @@ class SortLastGroup:
             else:  # ONE march from alpha 0 (relative partial); early termination is resolved afterwards
                 ctx.partial_relative(cam, self.rgba.data_ptr(), self.T.data_ptr())
             mark(1)
-            if self.world > 1:
+            f = self.frame
+            self.frame += 1
+            if self.exchange == "p2p":
+                ctx.exchange_push(self.T.data_ptr(), order[order.index(self.rank) + 1:], f)
+                ctx.exchange_wait(f, len(before))
+                t_all = ctx.exchange_table(f)
+            elif self.world > 1:
                 dist.all_gather_into_tensor(self.T_all, self.T)
+                t_all = self.T_all.data_ptr()
             else:
                 self.T_all.copy_(self.T)
+                t_all = self.T_all.data_ptr()
             mark(2)
             if self.scheme == "two-pass":
-                ctx.partial_ain(self.T_all.data_ptr(), before, self.ain.data_ptr())
+                ctx.partial_ain(t_all, before, self.ain.data_ptr())
             else:
-                ctx.partial_resolve(self.T_all.data_ptr(), before, self.rgba.data_ptr(), self.ain.data_ptr())
+                ctx.partial_resolve(t_all, before, self.rgba.data_ptr(), self.ain.data_ptr())
+            if self.exchange == "p2p":
+                ctx.exchange_done(f)
             mark(3)
             ctx.partial_color(cam, self.ain.data_ptr(), self.rgba.data_ptr())  # deferred: only the flagged pixels
             mark(4)

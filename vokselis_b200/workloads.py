@@ -161,7 +161,7 @@ def run_sortfirst_tiles(cid: int, rank: int, world: int, local: int, dist=None, 
 
 
 def run_sortlast(rank: int, world: int, local: int, dist, edge: int = 4096, frames: int = 6, res=(3840, 2160), kind: int = 3,
-                 dtype=np.float32, save_frame0: str | None = None, hbm_peak_gbs: float = 6650.0):
+                 dtype=np.float32, save_frame0: str | None = None, hbm_peak_gbs: float = 6650.0, exchange: str = "p2p"):
     """configs[4]: edge^3 fp32 volume brick-partitioned over `world` ranks (sort-last). Every phase of a frame is timed
     with CUDA events on each rank's stream; the per-frame time is the max over ranks of the whole frame."""
     import torch
@@ -172,7 +172,7 @@ def run_sortlast(rank: int, world: int, local: int, dist, edge: int = 4096, fram
     gn = (edge, edge, edge)
     dtype = np.dtype(dtype)
     ctx = rt.Context(local, W, H)
-    group = sortlast.SortLastGroup(ctx, rank, world, gn, dist=dist)
+    group = sortlast.SortLastGroup(ctx, rank, world, gn, dist=dist, exchange=exchange)
     t0 = time.perf_counter()
     ctx.generate_synthetic_window(kind, dtype, gn, group.own_lo, group.own_hi, seed=5)
     ctx.sync()
@@ -198,6 +198,12 @@ def run_sortlast(rank: int, world: int, local: int, dist, edge: int = 4096, fram
         phases.append(ph)
     mean_phase = {k: float(np.mean([ph[k] for ph in phases])) for k in phases[0]}
     gathered = {k: _gather_floats(v, dist, world) for k, v in mean_phase.items()}
+    # per frame, per rank: [frame][rank] (which rank waits for which changes with the camera, so transfer cost and
+    # imbalance must be separated frame by frame, not on the means)
+    per_frame_rank = {k: np.array([_gather_floats(ph[k], dist, world) for ph in phases]) for k in ("march", "all_gather", "reduce")}
+    exchange = group.exchange
+    timeouts = _max_over_ranks(float(ctx.exchange_timeouts()) if exchange == "p2p" else 0.0, dist, world)
+    group.close()
     ctx.close()
     if rank != 0:
         return None
@@ -210,15 +216,21 @@ def run_sortlast(rank: int, world: int, local: int, dist, edge: int = 4096, fram
         "n_gpus": world, "brick_grid": list(group.grid), "volume_bytes": edge ** 3 * eb, "bytes_per_rank": per_rank_bytes,
         "frames": frames, "ms_per_frame": mean_ms, "frames_per_s": 1e3 / mean_ms, "per_frame_ms": per_frame, "generate_s_rank0": gen_s,
         "phase_ms_mean_max_over_ranks": {k: max(v) for k, v in gathered.items()}, "phase_ms_mean_by_rank": gathered,
-        "exchange_bytes_per_rank_per_frame": {"all_gather_T": (world - 1) * W * H * 4, "reduce_rgba": W * H * 16},
+        "exchange": ("direct-send over NVLink peer memory (vkrt_exchange_*): every rank stores its transmittance image into the tables of the ranks behind it in "
+                     "visibility order; NCCL only sums the partial colours onto rank 0" if exchange == "p2p" else "NCCL all-gather of the transmittance images + NCCL sum"),
+        "exchange_wait_timeouts": int(timeouts),
+        "exchange_bytes_per_rank_per_frame": {"transmittance_sent_mean": (world - 1) / 2 * W * H * 4 if exchange == "p2p" else W * H * 4,
+                                              "transmittance_received_max": (world - 1) * W * H * 4, "reduce_rgba": W * H * 16},
         # A collective is also where a rank that finished its march early WAITS for the slowest one: on the rank that arrives
         # last the phase lasts as long as the transfer itself, on the others transfer + wait. The transfer cost is therefore
         # the MIN over ranks, the imbalance of the march is max - min of the march phase.
-        "exchange_ms": {"all_gather_transfer": min(gathered["all_gather"]), "reduce_transfer": min(gathered["reduce"]),
-                        "all_gather_incl_wait_for_slowest_march": max(gathered["all_gather"]),
-                        "march_imbalance_max_minus_min": max(gathered["march"]) - min(gathered["march"])},
-        "exchange_share_of_frame": (min(gathered["all_gather"]) + min(gathered["reduce"])) / mean_ms,
-        "timing": "CUDA events on every rank's own stream between the phases of a frame (march from alpha 0, NCCL all-gather of transmittances, resolve, re-march of "
+        "exchange_ms": {"transmittance_transfer": float(per_frame_rank["all_gather"].min(axis=1).mean()),
+                        "reduce_transfer": float(per_frame_rank["reduce"].min(axis=1).mean()),
+                        "transmittance_incl_wait_for_slowest_march": float(per_frame_rank["all_gather"].max(axis=1).mean()),
+                        "march_imbalance_max_minus_min": float((per_frame_rank["march"].max(axis=1) - per_frame_rank["march"].min(axis=1)).mean()),
+                        "note": "per frame: min over ranks = the rank that arrived last (no waiting), max = transfer + wait for the slowest march; means over frames"},
+        "exchange_share_of_frame": float(per_frame_rank["all_gather"].min(axis=1).mean() + per_frame_rank["reduce"].min(axis=1).mean()) / mean_ms,
+        "timing": "CUDA events on every rank's own stream between the phases of a frame (march from alpha 0, exchange of transmittances [phase 'all_gather'], resolve, re-march of "
                   "the flagged pixels, NCCL sum onto rank 0, finalize); ms_per_frame = max over ranks of the whole frame, mean over frames; L2 flushed before each frame",
         "roofline": {"bound": "hbm", "achieved": per_rank_bytes / (march * 1e-3) / 1e9, "peak": hbm_peak_gbs, "unit": "GB/s",
                      "frac": per_rank_bytes / (march * 1e-3) / 1e9 / hbm_peak_gbs,
@@ -354,8 +366,11 @@ def check_sortlast(rank: int, world: int, local: int, dist, log=None) -> dict:
             deltas.append(d)
             ok = ok and d <= 2
             say(f"sort-last world {world} cam {i}: max |delta| {d}/255 {'ok' if d <= 2 else 'MISMATCH'}")
-    flag = torch.tensor([0 if ok else 1], device="cuda")
+    timeouts = ctx.exchange_timeouts() if group.exchange == "p2p" else 0
+    flag = torch.tensor([0 if (ok and timeouts == 0) else 1], device="cuda")
     dist.all_reduce(flag)
+    group.close()
     ctx.close()
-    return {"ok": bool(flag.item() == 0), "what": "sort-last frame vs single-GPU frame of the same 256^3 fp32 volume, max |delta| <= 2/255 after present (3 cameras)",
+    return {"ok": bool(flag.item() == 0), "exchange": "p2p direct-send (vkrt_exchange_*), 0 wait timeouts" if timeouts == 0 else f"{timeouts} wait timeouts",
+            "what": "sort-last frame vs single-GPU frame of the same 256^3 fp32 volume, max |delta| <= 2/255 after present (3 cameras)",
             "max_delta_255": deltas}
