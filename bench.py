@@ -490,12 +490,24 @@ def run_gpu(args):
             t0 = time.perf_counter()
             ctx.frame_host(cams[(Wm + i) % ORBIT], pinned1.array)
             tot1 += time.perf_counter() - t0
+        # the PCIe floor, measured here: the same bytes D2H into page-locked memory with no rendering
+        nfl = min(K, 96)
+        pinned_fl = rt.PinnedArray((8, H, W, 4), np.uint8)
+        ctx.sync()
+        t0 = time.perf_counter()
+        for i in range(nfl):
+            ctx.readback_rgba8_async(pinned_fl.array[i % 8])
+        ctx.sync()
+        d2h_floor_fps = nfl / (time.perf_counter() - t0)
+        pinned_fl.close()
         pinned1.close()
         e2e = {"value": e2e_frames, "unit": "frames/s", "h2d_bytes_per_step": 144 + 48, "d2h_bytes_per_step": W * H * 4,
                "how": f"vkrt_frames_host, {PER_CALL} frames per blocking call into page-locked host memory: cameras in (kernel arguments), "
                       f"groups of {min(B, 4)} frames per launch with the present pass fused into the raycast epilogue, RGBA8 D2H of a group overlapping "
                       "the raycast of the next; wall clock per call, L2 flushed before each call (flush untimed)",
                "single_frame_blocking": n1 / tot1,
+               "d2h_floor": {"frames_per_s": d2h_floor_fps, "GBs": d2h_floor_fps * W * H * 4 / 1e9, "of_floor": e2e_frames / d2h_floor_fps,
+                             "note": "measured in this run: the same RGBA8 bytes copied D2H into page-locked memory back to back, no rendering"},
                "note": "single_frame_blocking = vkrt_frame_host, one frame per call (raycast + fused present + D2H, nothing overlapped). "
                        "The PCIe floor for 8.3 MB of RGBA8 per frame is ~0.154 ms (54 GB/s measured) = 6,500 frames/s per link"}
     else:
@@ -528,6 +540,22 @@ def run_gpu(args):
         tt = torch.tensor([my_tot], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         barrier()
+        # What the platform allows: the SAME bytes into the SAME segment with no rendering at all — every rank copies its share of
+        # the sweep (its presented frame, again and again) over its own PCIe link at the same time, 3 passes, slowest rank.
+        floor_tot = 0.0
+        if ids:
+            ctx.frame_host(cams[Wm % ORBIT], seg.array[ids[0] % n_seg])  # something presented in ctx's rgba8 buffer
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            for i in ids:
+                ctx.readback_rgba8_async(seg.array[i % n_seg])
+            ctx.sync()
+            floor_tot += time.perf_counter() - t0
+        ft = torch.tensor([floor_tot / 3.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+        barrier()
+        d2h_floor_fps = K / float(ft.item()) if float(ft.item()) > 0 else None
         # the consumer's check (untimed): the LAST frame of every rank's share, read from the shared segment by rank 0,
         # equals rank 0's own rendering of that camera
         seg_ok = None
@@ -547,6 +575,10 @@ def run_gpu(args):
                       "frames per launch, present fused, D2H overlapping the next group) straight into it over its own PCIe link; K frames over the slowest rank's "
                       "summed call time, L2 flushed before each call (flush untimed)",
                "consumer_sees_every_ranks_frames": seg_ok, "host_ring_frames": n_seg,
+               "d2h_floor": {"frames_per_s": d2h_floor_fps, "GBs": (d2h_floor_fps * W * H * 4 / 1e9) if d2h_floor_fps else None,
+                             "of_floor": (K / float(tt.item()) / d2h_floor_fps) if d2h_floor_fps and float(tt.item()) > 0 else None,
+                             "note": f"measured in this run: the {world} ranks copy the same {K} frames' bytes into the same host segment concurrently, no rendering "
+                                     "(host memory / PCIe root complexes are shared by the GPUs: the links do not add up)"},
                "via_rank0_gpu": funnel}
 
     clock_info = clocks.stop() if rank == 0 else None  # sampled across all timed GPU regions above (value, warm, e2e)

@@ -5,7 +5,7 @@ import sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print('N', d['n_gpus'], 'value', round(d['value'], 1), 'ms', round(d['ms_per_step'], 5), 'fpl', d['config']['frames_per_launch'])
 e = d['e2e']
-print('e2e', round(e['value'], 1), 'via rank0', (e.get('via_rank0_gpu') or {}).get('value'), e.get('consumer_sees_every_ranks_frames'), 'single_blocking', e.get('single_frame_blocking'))
+print('e2e', round(e['value'], 1), 'via rank0', (e.get('via_rank0_gpu') or {}).get('value'), e.get('consumer_sees_every_ranks_frames'), 'single_blocking', e.get('single_frame_blocking'), 'd2h_floor', {k: v for k, v in (e.get('d2h_floor') or {}).items() if k != 'note'})
 r = d['roofline']
 print('roofline frac', r['frac'], 'achieved', r['achieved'], 'peak', r['peak'], 'dense', (d.get('roofline_dense') or {}).get('frac'))
 print('timeline', {k: v for k, v in d['rank0_timeline_ms_per_step'].items() if k != 'note'}, 'timeouts', d.get('sortfirst_wait_timeouts'))

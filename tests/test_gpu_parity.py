@@ -688,3 +688,35 @@ def test_present_stretched_matches_oracle(rt, oracle, noise64, xor_cam):
             got = ctx.present_scaled(ow, oh)
             ref = oracle.present(frame, ow, oh)
             assert np.abs(got.astype(np.int32) - ref.astype(np.int32)).max() <= 1, (ow, oh)
+
+
+@pytest.mark.parametrize("zoom", [900.0, 5000.0, 3.0e6])
+def test_far_camera_m1_skipping_stays_exact(rt, oracle, zoom):
+    """M1's skipping consults a distance field padded by one brick WITHOUT a per-sample bounds test; that is sound while
+    fp32 positions inside the box are exact to a fraction of a brick, i.e. for ray origins within ~1e3 box units
+    (`tame_camera`, api.cu). Beyond that the library must render with skipping off. Cameras at 900 (tame), 5,000 and
+    3e6 box units (not tame: fp32 positions are off by whole voxels / the whole box): skipping on == skipping off bit for
+    bit, hit mask and iteration counts as the oracle's."""
+    W, H, n = 256, 144, 96
+    rng = np.random.default_rng(11)
+    vol = np.zeros((n, n, n), np.uint8)
+    vol[8:40, 50:90, 20:70] = rng.integers(30, 255, size=(32, 40, 50), dtype=np.uint8)
+    vol[n - 9:, n - 9:, n - 9:] = 200  # content touching the far corner: clamp-to-edge samples at q == N matter
+    cam = rt.Camera(zoom, -0.4, 0.8, (0.1, -0.2, 0.3), W / H).get_proj_view_matrix()
+    ref, ref_aux, _ = oracle.render(abi.default_params(abi.MODE_M1), cam, W, H, scalar=vol)
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_scalar(vol)
+        frames, auxes = [], []
+        for skip in (0, 1):
+            for layout in (abi.LAYOUT_LINEAR, abi.LAYOUT_QUAD):
+                q = rt.default_params(abi.MODE_M1)
+                q.skip_empty, q.layout, q.count_samples = skip, layout, 1
+                ctx.set_params(q)
+                ctx.render(cam)
+                frames.append(ctx.readback())
+                auxes.append(ctx.readback_aux())
+        for f, a in zip(frames[1:], auxes[1:]):
+            assert np.array_equal(f, frames[0]) and np.array_equal(a, auxes[0]), zoom
+        assert np.array_equal(auxes[0] >> 31, ref_aux >> 31), zoom
+        d = auxes[0].astype(np.int64) - ref_aux.astype(np.int64)
+        assert (d != 0).mean() <= 1e-3 and np.abs(d).max() <= 1, zoom

@@ -102,6 +102,7 @@ struct VkrtContext {
     cudaArray_t arr_a = nullptr, arr_b = nullptr, arr_g = nullptr, arr_q = nullptr;
     cudaTextureObject_t tex_a = 0, tex_b = 0, tex_g = 0, tex_q = 0;  // tex_g: layered + gather (LAYOUT_GATHER); tex_q: pre-gathered quads (LAYOUT_QUAD)
     uint8_t* dist = nullptr;  // brick distance field (0 = occupied)
+    uint8_t* dist_pad = nullptr;  // scalar volumes: the same, padded by one occupied layer on the high sides (RenderArgs::dist)
     int occ_lo[3] = {0, 0, 0}, occ_hi[3] = {-1, -1, -1};  // bounding box of the occupied bricks (inclusive); hi < lo = none
     // brick-partitioned (sort-last) state: the resident volume is a window of a larger global grid
     bool windowed = false;
@@ -146,8 +147,10 @@ void free_volume(VkrtContext* c) {
     if (c->lin_a) cudaFree(c->lin_a);
     if (c->lin_b) cudaFree(c->lin_b);
     if (c->dist) cudaFree(c->dist);
+    if (c->dist_pad) cudaFree(c->dist_pad);
     c->lin_a = c->lin_b = nullptr;
     c->dist = nullptr;
+    c->dist_pad = nullptr;
     c->kind = VOL_NONE;
     c->windowed = false;
 }
@@ -398,6 +401,10 @@ int build_occupancy(VkrtContext* c) {
     int bounds[6] = {0, 0, 0, -1, -1, -1};
     if (e == cudaSuccess) e = launch_occupied_bounds(c->dist, c->nbx, c->nby, c->nbz, (int*)scratch, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(bounds, scratch, sizeof bounds, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && c->kind == VOL_SCALAR) {
+        e = cudaMalloc(&c->dist_pad, (size_t)(c->nbx + 1) * (c->nby + 1) * (c->nbz + 1));
+        if (e == cudaSuccess) e = launch_pad_dist(c->dist, c->dist_pad, c->nbx, c->nby, c->nbz, c->stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(scratch);
     if (e != cudaSuccess) return cuda_fail(e, "build_occupancy");
@@ -439,6 +446,30 @@ bool params_ok(const VkrtParams* p, std::string& why) {
 // therefore conservative. Anything else (singular or non-finite matrix, a corner with w <= 0, i.e. the
 // camera plane cuts the box) disables culling: the rectangle becomes the whole plane. The kernel's own
 // rounding moves the silhouette by ~1e-6 of the frame; the margin is two pixels.
+// Are the ray origins of this camera close enough to the box for a sample's voxel index to stay within one brick of the
+// grid? The kernel computes p = eye + t*dir in fp32: with |eye| <= 1024 a position inside the box [-1,1]^3 is off by at most
+// a few ulp(1024) ~ 1e-4, i.e. <= 1 voxel at 8192^3, so the index lies in [-1, N] and the padded distance field covers it.
+// Origins are eye(sx,sy) = (inv * (sx,sy,0,1)).xyz / .w, a ratio of affine functions of the screen point: if w keeps its sign
+// at the four frame corners it keeps it inside, and every origin lies in the convex hull of the corner origins. Anything
+// else (far, orthographic-at-infinity, non-finite) renders with skipping off: exact by construction, only slower.
+bool tame_camera(const float inv[16], int W, int H) {
+    double wmin = 1e300, wmax = 0.0;
+    int sign = 0;
+    for (int k = 0; k < 4; ++k) {
+        const double cx = (k & 1) ? (double)W + 1.0 : -1.0, cy = (k & 2) ? (double)H + 1.0 : -1.0;
+        const double sx = 2.0 * cx / W - 1.0, sy = (2.0 * cy / H - 1.0) * (-(double)H / (double)W);
+        double v[4];
+        for (int r = 0; r < 4; ++r) v[r] = (double)inv[r] * sx + (double)inv[4 + r] * sy + (double)inv[12 + r];
+        if (!std::isfinite(v[0]) || !std::isfinite(v[1]) || !std::isfinite(v[2]) || !std::isfinite(v[3]) || v[3] == 0.0) return false;
+        const int sg = v[3] > 0.0 ? 1 : -1;
+        if (sign != 0 && sg != sign) return false;
+        sign = sg;
+        wmin = std::min(wmin, fabs(v[3])); wmax = std::max(wmax, fabs(v[3]));
+        for (int r = 0; r < 3; ++r) if (!(fabs(v[r] / v[3]) <= 1024.0)) return false;
+    }
+    return wmin > 1e-6 * wmax;
+}
+
 void cull_rect(const float inv[16], int W, int H, float cull[4], int* centre_row) {
     const float big = 3.0e38f;
     cull[0] = cull[1] = -big; cull[2] = cull[3] = big;
@@ -504,7 +535,7 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     // clear_color.a == 0 (raycast_compute.wgsl:89,91). And the reference tests `a >= threshold` only after
     // compositing a sample (:92), so with initial_alpha >= alpha_threshold it stops after its FIRST sample, which a
     // leap would pass over. Otherwise fall back to the full march.
-    const bool skip = P.skip_empty && !(P.mode == VKRT_MODE_M0 && P.clear_color[3] != 0.0f) && P.initial_alpha < P.alpha_threshold;
+    bool skip = P.skip_empty && !(P.mode == VKRT_MODE_M0 && P.clear_color[3] != 0.0f) && P.initial_alpha < P.alpha_threshold;
 
     RenderArgs A{};
     A.W = c->W; A.H = c->H;
@@ -513,6 +544,8 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
         memcpy(A.inv[f], cam[f].inv_proj, sizeof A.inv[f]);
         int centre_row;
         cull_rect(A.inv[f], A.W, A.H, A.cull[f], &centre_row);
+        // M1's skipping indexes the padded distance field without a bounds test (RenderArgs::dist)
+        if (P.mode == VKRT_MODE_M1 && skip && !tame_camera(A.inv[f], A.W, A.H)) skip = false;
     }
     A.n_tiles = 0; A.tile_size = P.tile_size; A.offsets = nullptr;
     if (offsets && n > 0) {
@@ -548,7 +581,15 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     A.hx = A.fx / 2.0f; A.hy = A.fy / 2.0f; A.hz = A.fz / 2.0f;
     A.one = 1.0f;
     A.nbx = c->nbx; A.nby = c->nby; A.nbz = c->nbz;
-    A.dist = c->dist;
+    if (P.mode == VKRT_MODE_M1 && c->dist_pad) {
+        A.dist = c->dist_pad;
+        A.dsx = (uint32_t)c->nbx + 1u; A.dsy = (uint32_t)c->nby + 1u;
+        A.dist_last = (uint32_t)((size_t)(c->nbx + 1) * (c->nby + 1) * (c->nbz + 1) - 1);
+    } else {
+        A.dist = c->dist;
+        A.dsx = (uint32_t)c->nbx; A.dsy = (uint32_t)c->nby;
+        A.dist_last = (uint32_t)((size_t)c->nbx * c->nby * c->nbz - 1);
+    }
     // shrink leap regions by ~16 ulp of the largest voxel coordinate (rounding of p and q)
     A.leap_eps = 16.0f * 1.1920929e-07f * (float)(c->nx > c->ny ? (c->nx > c->nz ? c->nx : c->nz) : (c->ny > c->nz ? c->ny : c->nz));
     {

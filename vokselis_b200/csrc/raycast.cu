@@ -334,7 +334,8 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
             const float2 qxy = mul2(add2(pxy, dup2(1.0f)), hxy);
             const float qx = qxy.x, qy = qxy.y, qz = xmul(xadd(pz, 1.0f), A.hz);
             const int ix = __float2int_rz(qx), iy = __float2int_rz(qy), iz = __float2int_rz(qz);
-            const bool inb = (unsigned)ix < (unsigned)A.nx && (unsigned)iy < (unsigned)A.ny && (unsigned)iz < (unsigned)A.nz;
+            // M1 needs no bounds test: the fetch clamps to the edge, and the distance field it consults is padded (below)
+            const bool inb = MODE != VKRT_MODE_M0 || ((unsigned)ix < (unsigned)A.nx && (unsigned)iy < (unsigned)A.ny && (unsigned)iz < (unsigned)A.nz);
             if (SKIP) {
                 // Exact empty-space skipping. A sample in an empty brick (or, in M0,
                 // outside the grid) leaves colour and alpha bit-identical, so only the t sequence
@@ -345,7 +346,11 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
                     n = MODE == VKRT_MODE_M0 ? 1 : 0;
                 } else {
                     const int bx = ix >> 3, by = iy >> 3, bz = iz >> 3;
-                    const uint32_t d = __ldg(A.dist + (((uint32_t)bz * (uint32_t)A.nby + (uint32_t)by) * (uint32_t)A.nbx + (uint32_t)bx));
+                    uint32_t cell = ((uint32_t)bz * A.dsy + (uint32_t)by) * A.dsx + (uint32_t)bx;
+                    // M1: ix == nx (p rounded onto the box face) lands on the pad layer, a slightly negative wrapped index on
+                    // the pad of the previous row / slab or past the end: all "occupied", i.e. the sample is evaluated
+                    if (MODE == VKRT_MODE_M1) cell = min(cell, A.dist_last);
+                    const uint32_t d = __ldg(A.dist + cell);
                     if (d != 0u) n = leap_count<MODE>(A, L, d, bx, by, bz, qxy, qz);
                 }
                 if (n > 0) {

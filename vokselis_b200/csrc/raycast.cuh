@@ -22,8 +22,13 @@ struct RenderArgs {
     float one;
     int nx, ny, nz;
     int nbx;              // 8^3-voxel bricks per axis (occupancy grid and bricked layout)
-    const uint8_t* dist;  // per brick: 0 = occupied, d = bricks within Chebyshev radius d-1 are all empty
+    // per brick: 0 = occupied, d = bricks within Chebyshev radius d-1 are all empty. Row / slab strides dsx, dsy; M0: the
+    // field itself (nbx, nby); M1: the copy padded by one occupied layer on the high side of every axis (nbx + 1, nby + 1),
+    // indexed without a bounds test and clamped to dist_last (memory safety; the host only enables skipping for cameras
+    // whose ray origins are near enough for the voxel index to stay within the pad, see tame_camera in api.cu)
+    const uint8_t* dist;
     int nby, nbz;
+    uint32_t dsx, dsy, dist_last;
     cudaTextureObject_t tex_a, tex_b;
     float alpha_threshold;
     float leap_r0;        // -(4 + leap_eps): exit-plane offset from the brick centre is 8 d + leap_r0
@@ -57,7 +62,6 @@ struct RenderArgs {
     uint32_t* aux;                 // optional W*H: bit31 hit, low bits iterations
     unsigned long long* counters;  // optional [3]: rays_hit, samples_reference, samples_fetched
 };
-static_assert(offsetof(RenderArgs, nx) == 16 && offsetof(RenderArgs, dist) == 32 && offsetof(RenderArgs, tex_a) == 48, "hot block layout");
 
 // One rank's view of a brick-partitioned volume (sortlast.cu): a WINDOW of the global grid.
 struct PartialArgs {
@@ -99,6 +103,7 @@ cudaError_t launch_occupancy_m0(const uint2* color, const uint2* normal, int nx,
 cudaError_t launch_occupancy_m1(const void* scalar, int dtype, int nx, int ny, int nz, int nbx, int nby, int nbz,
                                 uint8_t* dist, cudaStream_t s);
 cudaError_t launch_occupied_bounds(const uint8_t* dist, int nbx, int nby, int nbz, int* d_out6, cudaStream_t s);
+cudaError_t launch_pad_dist(const uint8_t* dist, uint8_t* out, int nbx, int nby, int nbz, cudaStream_t s);
 cudaError_t launch_distance_transform(uint8_t* dist, uint8_t* scratch, int nbx, int nby, int nbz, int border, int max_d, cudaStream_t s);
 cudaError_t launch_pregather_quads(const void* vol, int dtype, void* out_texels, int nx, int ny, int nz, cudaStream_t s);
 cudaError_t launch_generate_xor(uint2* color, uint2* normal, int n, float time, int which, cudaStream_t s);

@@ -554,6 +554,22 @@ cudaError_t launch_occupied_bounds(const uint8_t* dist, int nbx, int nby, int nb
     return cudaGetLastError();
 }
 
+// The distance field with one layer of "occupied" cells appended on the high side of every axis (M1, see RenderArgs::dist):
+// a sample whose voxel index is one past the grid (q == N, reached when p rounds to the box face) or slightly negative in a
+// wrapped index lands on a pad cell and is simply evaluated, so the march needs no per-sample bounds test.
+__global__ void __launch_bounds__(256) pad_dist_kernel(const uint8_t* __restrict__ dist, uint8_t* __restrict__ out, int nbx, int nby, int nbz) {
+    const size_t total = (size_t)(nbx + 1) * (nby + 1) * (nbz + 1);
+    const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= total) return;
+    const int bx = (int)(o % (size_t)(nbx + 1)), by = (int)((o / (size_t)(nbx + 1)) % (size_t)(nby + 1)), bz = (int)(o / ((size_t)(nbx + 1) * (nby + 1)));
+    out[o] = (bx < nbx && by < nby && bz < nbz) ? dist[((size_t)bz * nby + by) * nbx + bx] : (uint8_t)0;
+}
+cudaError_t launch_pad_dist(const uint8_t* dist, uint8_t* out, int nbx, int nby, int nbz, cudaStream_t s) {
+    const size_t total = (size_t)(nbx + 1) * (nby + 1) * (nbz + 1);
+    pad_dist_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dist, out, nbx, nby, nbz);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_occupancy_m1(const void* scalar, int dtype, int nx, int ny, int nz, int nbx, int nby, int nbz, uint8_t* dist,
                                 cudaStream_t s) {
     const size_t cells = (size_t)nbx * nby * nbz;
