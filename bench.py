@@ -5,7 +5,7 @@ Headline workload (BASELINE.json configs[1]): the `xor` procedural volume, 256^3
 over an orbit camera sweep of 360 frames (yaw_i = 1 + 2*pi*i/360, pitch -0.5, zoom 3, the xor example's camera,
 examples/xor/main.rs:273-279) in mode M1 (scalar volume, trilinear, `vertigo` transfer function, early ray
 termination, exact empty-space skipping), LAYOUT_QUAD (two tex3D point fetches per sample, fp32 weights: parity path).
-One STEP = one frame of the orbit; a LAUNCH renders --batch (default 8) consecutive frames of the sweep (grid.z =
+One STEP = one frame of the orbit; a LAUNCH renders --batch (default 16) consecutive frames of the sweep (grid.z =
 frame), because one 1080p frame with a fifth of its pixels on the box cannot fill a B200 (the one-frame-per-launch
 figure is reported beside it as `single_frame_per_launch`). `value` = frames/s with the volume resident in HBM,
 timed per launch with CUDA events on the launching stream, L2 flushed (a 256 MiB write) between timed launches.
@@ -207,21 +207,22 @@ def m0_section(rt, abi, device, K, Wm, no_cpu):
         ms = c.timing_read(n).astype(np.float64)
         out[f"gpu_fps_{w}x{h}_one_frame_per_launch"] = 1e3 / float(ms.mean())
         out[f"gpu_ms_{w}x{h}_one_frame_per_launch"] = float(ms.mean())
-        # 8 frames of the sweep per launch (grid.z = frame), like the headline
-        nb = max(n // 8, 1)
+        # MAX_BATCH frames of the sweep per launch (grid.z = frame), like the headline
+        FB = rt.MAX_BATCH
+        nb = max(n // FB, 2)
         c.timing_enable(nb)
-        c.render_batch(cams[:8])
+        c.render_batch(cams[:FB])
         for j in range(nb):
             c.flush_l2()
-            c.render_batch([cams[(Wm + 8 * j + k) % ORBIT] for k in range(8)])
+            c.render_batch([cams[(Wm + FB * j + k) % ORBIT] for k in range(FB)])
         msb = c.timing_read(nb).astype(np.float64)
-        out[f"gpu_fps_{w}x{h}"] = 8e3 / float(msb.mean())
-        out[f"gpu_ms_{w}x{h}"] = float(msb.mean()) / 8
+        out[f"gpu_fps_{w}x{h}"] = FB * 1e3 / float(msb.mean())
+        out[f"gpu_ms_{w}x{h}"] = float(msb.mean()) / FB
         if (w, h) == (1280, 720) and not no_cpu:
             color, normal = c.download_rgba16f()
             cam0 = cams[0]
         c.close()
-    out["layout"] = "TEXTURE (tex3D point fetches), exact empty-space skipping; gpu_fps_* = 8 frames per launch, L2 flushed between launches"
+    out["layout"] = f"TEXTURE (tex3D point fetches), exact empty-space skipping; gpu_fps_* = {rt.MAX_BATCH} frames per launch, L2 flushed between launches"
     if color is not None:
         try:
             from oracle import ref_binding as rb
@@ -368,12 +369,12 @@ def run_gpu(args):
         samples_ref, samples_fetched = probe_samples(ctx, rt, abi, cams, timed_ids, LAYOUT, 1)
         ctx.set_params(p)
 
-    # frames per launch (grid.z = frame). --batch 0 = choose: 8 on one GPU; for N ranks the group size that leaves no rank
+    # frames per launch (grid.z = frame). --batch 0 = choose: MAX_BATCH = 16 on one GPU (8 -> 12 -> 16 frames: 10,065 -> 10,626 -> 10,765 frames/s); for N ranks the group size that leaves no rank
     # with more frames than necessary (groups are dealt round-robin), larger groups preferred
     if args.batch > 0:
         B = max(1, min(args.batch, rt.MAX_BATCH))
     elif world == 1:
-        B = rt.MAX_BATCH
+        B = -(-K // -(-K // rt.MAX_BATCH))  # the fewest launches of <= MAX_BATCH frames, evenly filled (20 steps: 2 launches of 10)
     else:
         from vokselis_b200.sortfirst import choose_batch
 
@@ -472,7 +473,7 @@ def run_gpu(args):
 
     # ---- e2e through the C ABI with host buffers: presented RGBA8 frames in ONE consumer's page-locked host memory ----------
     e2e = None
-    PER_CALL = 24
+    PER_CALL = 60  # frames per blocking vkrt_frames_host call: a 360-frame sweep in 6 calls (20 driver steps: one call)
     if world == 1:
         # the call a user of a sweep makes: vkrt_frames_host — cameras in, presented RGBA8 frames out in page-locked host memory;
         # groups of frames per launch, present fused into the raycast epilogue, D2H of a group overlapping the next raycast
@@ -664,7 +665,7 @@ def run_gpu(args):
         tfile = ROOT / "profiles" / "traffic_r02.json"
         if tfile.exists():
             try:
-                traffic = json.loads(tfile.read_text()).get("raycast_m1_quad_u8_skip_batch8_dram_bytes_per_launch") if frames_per_launch == 8 else None
+                traffic = json.loads(tfile.read_text()).get(f"raycast_m1_quad_u8_skip_batch{frames_per_launch}_dram_bytes_per_launch")  # ncu capture of this launch shape, or null
             except Exception:
                 pass
         hbm_bytes = min(4 * NVOL ** 3, alg_bytes) + (my_frames / max(len(launch_ms), 1)) * W * H * 8.0
@@ -679,9 +680,10 @@ def run_gpu(args):
                     "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["hbm_source"],
                     "compulsory_bytes_per_launch": hbm_bytes, "note": "quad texture (64 MiB, read at most once per launch) + frames (W*H*8 B each); far below HBM peak by construction"},
             "frames_per_launch": frames_per_launch,
-            "binding_resource": "instruction issue: ncu on this launch shape (8 frames) reports issue active 88 %, sm__throughput 84 % of peak over the launch, l1tex 53 %, "
-                                "DRAM 1 % (profiles/r02_v1_prof_batch8_m1_quad_skip.md); the quad texture is L1/L2-resident, so the texel path is the memory-side bound "
-                                "reported here and HBM (roofline.hbm) is a few % by construction. With skipping off the SAME kernel is bound by the texel path: roofline_dense",
+            "binding_resource": "instruction issue: ncu on the 16-frame launch reports issue active 85 %, sm__throughput 83 % of peak over the launch, l1tex 60 %, "
+                                "DRAM 2 %, 24.6 of 32 lanes active per instruction (profiles/r02_v3_prof_batch16_m1_quad_skip.md); the quad texture is L1/L2-resident, so the texel "
+                                "path is the memory-side bound reported here and HBM (roofline.hbm) is a few % by construction. With skipping off the SAME kernel is bound by the "
+                                "texel path: roofline_dense",
             "note": "achieved = samples actually fetched x 8 B of taps / launch time; with exact empty-space skipping a large share of the kernel's "
                     "time is traversal (instruction issue), not fetching",
         }
@@ -692,7 +694,7 @@ def run_gpu(args):
                               "frames_per_s": 1e3 / dense["ms_per_frame"], "ms_per_frame": dense["ms_per_frame"], "samples_per_frame": dense["samples_per_frame"],
                               "fetches_per_s": 2.0 * dense["samples_per_frame"] * 1e3 / dense["ms_per_frame"],
                               "note": "the same workload with skipping off (every reference sample fetched): ncu l1tex throughput 98 %, tex_throttle the top stall "
-                                      "(profiles/r02_v1_prof_batch8_m1_quad_noskip.md) — the fetch path is the bound here"}
+                                      "(profiles/r02_v3_prof_batch16_m1_quad_noskip.md) — the fetch path is the bound here"}
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -730,7 +732,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
     ap.add_argument("--granularity", default="frames", choices=["frames", "tiles"], help="sort-first granularity for N > 1")
-    ap.add_argument("--batch", type=int, default=0, help="frames per launch (grid.z = frame), 1..8; 0 = choose (8 on one GPU)")
+    ap.add_argument("--batch", type=int, default=0, help="frames per launch (grid.z = frame), 1..16; 0 = choose (16 on one GPU)")
     ap.add_argument("--only-headline", action="store_true", help="skip BASELINE configs[2..4] and the multi-GPU checks (development)")
     ap.add_argument("--config-frames", type=int, default=24, help="frames per timed pass of configs[2]/[3]")
     args = ap.parse_args()

@@ -636,7 +636,7 @@ def test_batched_launch_equals_single_frames(rt, oracle, noise64, mode):
     from vokselis_b200 import volumes
 
     W, H = 320, 180
-    cams = [rt.Camera(3.0 - 0.2 * i, -0.5 + 0.1 * i, 1.0 + 0.7 * i, (0, 0, 0), W / H).get_proj_view_matrix() for i in range(11)]
+    cams = [rt.Camera(3.0 - 0.1 * i, -0.5 + 0.05 * i, 1.0 + 0.7 * i, (0, 0, 0), W / H).get_proj_view_matrix() for i in range(rt.MAX_BATCH + 3)]
     with rt.Context(0, W, H) as ctx:
         if mode == abi.MODE_M0:
             ctx.upload_rgba16f(*noise64)
@@ -659,7 +659,7 @@ def test_batched_launch_equals_single_frames(rt, oracle, noise64, mode):
                 assert np.array_equal(ctx.readback_batch(i), singles[i]), (n, i)
         with pytest.raises(rt.VokselisError):
             ctx.render_batch(cams[:rt.MAX_BATCH + 1])
-        for group in (0, 1, 3, 8):
+        for group in (0, 1, 3, 8, rt.MAX_BATCH):
             got = ctx.frames_host(cams, group=group)
             for i in range(len(cams)):
                 assert np.array_equal(got[i], singles8[i]), (group, i)
