@@ -5,7 +5,7 @@ Headline workload (BASELINE.json configs[1]): the `xor` procedural volume, 256^3
 over an orbit camera sweep of 360 frames (yaw_i = 1 + 2*pi*i/360, pitch -0.5, zoom 3, the xor example's camera,
 examples/xor/main.rs:273-279) in mode M1 (scalar volume, trilinear, `vertigo` transfer function, early ray
 termination, exact empty-space skipping), LAYOUT_QUAD (two tex3D point fetches per sample, fp32 weights: parity path).
-One STEP = one frame of the orbit; a LAUNCH renders --batch (default 16) consecutive frames of the sweep (grid.z =
+One STEP = one frame of the orbit; a LAUNCH renders --batch (default: up to 32) consecutive frames of the sweep (grid.z =
 frame), because one 1080p frame with a fifth of its pixels on the box cannot fill a B200 (the one-frame-per-launch
 figure is reported beside it as `single_frame_per_launch`). `value` = frames/s with the volume resident in HBM,
 timed per launch with CUDA events on the launching stream, L2 flushed (a 256 MiB write) between timed launches.
@@ -369,7 +369,7 @@ def run_gpu(args):
         samples_ref, samples_fetched = probe_samples(ctx, rt, abi, cams, timed_ids, LAYOUT, 1)
         ctx.set_params(p)
 
-    # frames per launch (grid.z = frame). --batch 0 = choose: MAX_BATCH = 16 on one GPU (8 -> 12 -> 16 frames: 10,065 -> 10,626 -> 10,765 frames/s); for N ranks the group size that leaves no rank
+    # frames per launch (grid.z = frame). --batch 0 = choose: the fewest launches of <= MAX_BATCH = 32 frames on one GPU (8 / 16 / 24 / 32 frames per launch: 10,065 / 10,680 / 11,086 / 11,090 frames/s); for N ranks the group size that leaves no rank
     # with more frames than necessary (groups are dealt round-robin), larger groups preferred
     if args.batch > 0:
         B = max(1, min(args.batch, rt.MAX_BATCH))
@@ -732,7 +732,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
     ap.add_argument("--granularity", default="frames", choices=["frames", "tiles"], help="sort-first granularity for N > 1")
-    ap.add_argument("--batch", type=int, default=0, help="frames per launch (grid.z = frame), 1..16; 0 = choose (16 on one GPU)")
+    ap.add_argument("--batch", type=int, default=0, help="frames per launch (grid.z = frame), 1..32; 0 = choose (the fewest, evenly filled launches on one GPU)")
     ap.add_argument("--only-headline", action="store_true", help="skip BASELINE configs[2..4] and the multi-GPU checks (development)")
     ap.add_argument("--config-frames", type=int, default=24, help="frames per timed pass of configs[2]/[3]")
     args = ap.parse_args()

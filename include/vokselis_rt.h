@@ -202,7 +202,7 @@ VKRT_API int vkrt_box_screen_bounds(const VkrtCameraUniform* cam, int width, int
  * bounded by the dependent march of its longest rays; a few frames per launch do fill it. Every frame is
  * bit-identical to what vkrt_render produces for its camera. Frames land in context-owned batch buffers
  * (vkrt_batch_frame_device_ptr / vkrt_readback_batch, valid until the next batch call). */
-#define VKRT_MAX_BATCH 16
+#define VKRT_MAX_BATCH 32
 VKRT_API int vkrt_render_batch(VkrtContext* ctx, const VkrtCameraUniform* cams, int n, const VkrtUniform* un);
 VKRT_API void* vkrt_batch_frame_device_ptr(VkrtContext* ctx, int i); /* W*H rgba16f, frame i of the last vkrt_render_batch */
 VKRT_API int vkrt_readback_batch(VkrtContext* ctx, int i, uint16_t* rgba16f /* W*H*4 halfs */);

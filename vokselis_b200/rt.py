@@ -159,7 +159,7 @@ def dispatch_optimal(length: int, subgroup_size: int) -> int:
     return int(lib().vkrt_dispatch_optimal(length, subgroup_size))
 
 
-MAX_BATCH = 16  # VKRT_MAX_BATCH
+MAX_BATCH = 32  # VKRT_MAX_BATCH
 
 
 def default_params(mode: int = abi.MODE_M0) -> Params:
