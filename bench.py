@@ -541,9 +541,21 @@ def run_gpu(args):
         tt = torch.tensor([my_tot], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         barrier()
+        # the consumer's check (untimed): the LAST frame of every rank's share, read from the shared segment by rank 0,
+        # equals rank 0's own rendering of that camera
+        seg_ok = None
+        if rank == 0:
+            seg_ok = True
+            for r in range(world):
+                last = (r + 1) * K // world - 1
+                if last < r * K // world:
+                    continue
+                mine8 = ctx.frames_host([cams[(Wm + last) % ORBIT]], group=1)[0]
+                seg_ok = seg_ok and bool(np.array_equal(mine8, seg.array[last % n_seg]))
         # What the platform allows: the SAME bytes into the SAME segment with no rendering at all — every rank copies its share of
         # the sweep (its presented frame, again and again) over its own PCIe link at the same time, 3 passes, slowest rank.
         floor_tot = 0.0
+        barrier()  # rank 0 has finished reading the rendered frames: the copies below overwrite them
         if ids:
             ctx.frame_host(cams[Wm % ORBIT], seg.array[ids[0] % n_seg])  # something presented in ctx's rgba8 buffer
         for _ in range(3):
@@ -557,17 +569,6 @@ def run_gpu(args):
         dist.all_reduce(ft, op=dist.ReduceOp.MAX)
         barrier()
         d2h_floor_fps = K / float(ft.item()) if float(ft.item()) > 0 else None
-        # the consumer's check (untimed): the LAST frame of every rank's share, read from the shared segment by rank 0,
-        # equals rank 0's own rendering of that camera
-        seg_ok = None
-        if rank == 0:
-            seg_ok = True
-            for r in range(world):
-                last = (r + 1) * K // world - 1
-                if last < r * K // world:
-                    continue
-                mine8 = ctx.frames_host([cams[(Wm + last) % ORBIT]], group=1)[0]
-                seg_ok = seg_ok and bool(np.array_equal(mine8, seg.array[last % n_seg]))
         seg.close()
         e2e = {"value": K / float(tt.item()) if float(tt.item()) > 0 else 0.0, "unit": "frames/s", "h2d_bytes_per_step": 144 + 48,
                "d2h_bytes_per_step": W * H * 4,
