@@ -162,7 +162,7 @@ def test_group_dealing_covers_every_frame_once_and_fits_the_ring():
         for steps in (360, 100, 50, 16, 8, 3, 1):
             b = sortfirst.choose_batch(steps, world)
             slots = 2 * world * b
-            assert 1 <= b <= 8 and slots <= sortfirst.MAX_SLOTS and slots % b == 0
+            assert 1 <= b <= sortfirst.rt.MAX_BATCH and slots <= sortfirst.MAX_SLOTS and slots % b == 0
             groups = -(-steps // b)
             owners = [sortfirst.frame_owner(g * b, world, b) for g in range(groups)]
             for g in range(groups):
