@@ -195,6 +195,11 @@ VKRT_API int vkrt_tile_table(int width, int height, int tile_size, VkrtOffset* o
  * rect = {x0, y0, x1, y1}, inclusive; +-3e38 when the projection is not trustworthy (camera plane cuts the
  * box, singular matrix): then nothing is culled. */
 VKRT_API int vkrt_box_screen_bounds(const VkrtCameraUniform* cam, int width, int height, float rect[4], int* centre_row);
+/* The same for the box's silhouette: up to six inward half-planes a*cx + b*cy + c >= 0 (unit normals, pixel units, two
+ * pixels of margin) of the convex hull of the eight projected corners; a pixel violating one cannot hit. Unused planes
+ * (and all of them when the projection is not trustworthy) are (0, 0, 1). The launch tests pixels inside the rectangle
+ * against these before building a ray: about half of the rectangle lies outside the silhouette. */
+VKRT_API int vkrt_box_screen_hull(const VkrtCameraUniform* cam, int width, int height, float planes[6][3]);
 
 /* Batched `single`: the cameras of n consecutive frames of a sweep (n consecutive `Demo::render` calls of the
  * event loop, src/lib.rs:178-200; the recorder's frame sequence, src/lib.rs:132-140) rendered by ONE launch,

@@ -135,7 +135,7 @@ def test_box_screen_bounds_contain_every_hit_pixel(rt, oracle):
              (5.0, 1.5, -2.0, (0.5, -0.5, 0.2)), (3.0, 0.0, 0.0, (4.0, 0.0, 0.0)), (50.0, -1.0, 4.0, (0, 0, 0))]
     cases += [(float(rng.uniform(0.3, 8)), float(rng.uniform(-1.5, 1.5)), float(rng.uniform(-6, 6)),
                tuple(rng.uniform(-1.5, 1.5, 3))) for _ in range(40)]
-    culled_some = 0
+    culled_some = hull_culled = 0
     for k, (zoom, pitch, yaw, tgt) in enumerate(cases):
         W, H = [(160, 90), (128, 128), (97, 211)][k % 3]
         ocam = oracle.camera_uniform(zoom, pitch, yaw, tgt, W / H)
@@ -155,7 +155,17 @@ def test_box_screen_bounds_contain_every_hit_pixel(rt, oracle):
                 assert x0 >= cx.min() - 4 and x1 <= cx.max() + 4 and y0 >= cy.min() - 4 and y1 <= cy.max() + 4
             culled_some += int((~inside).any())
             assert row == -1 or 0 <= row < H
-    assert culled_some >= 10
+        # the silhouette's convex hull (tested inside the rectangle by the launch): contains every hit pixel, ...
+        planes = rt.box_screen_hull(_as_rt_cam(rt, ocam), W, H).astype(np.float64)
+        gx, gy = np.meshgrid(np.arange(W) + offx, np.arange(H) + offy)
+        dmin = np.min(planes[:, 0, None, None] * gx[None] + planes[:, 1, None, None] * gy[None] + planes[:, 2, None, None], axis=0)
+        if len(xs):
+            assert dmin[hit].min() >= 0.0, (zoom, pitch, yaw, tgt, dmin[hit].min())
+        if x0 > -1e30 and not np.allclose(planes, [[0, 0, 1]] * 6):
+            # ... is tight (every pixel 4 px or more inside the hull hits), and culls pixels the rectangle keeps
+            assert hit[dmin >= 4.0].all(), (zoom, pitch, yaw, tgt)
+            hull_culled += int(((dmin < 0) & inside).sum() > 0)
+    assert culled_some >= 10 and hull_culled >= 10
     # identity matrices: orthographic rays along +z through (sx, sy, 0); the box covers |sx| <= 1 and |sy| <= 1
     ident = abi.CameraUniform()
     for i in range(4):

@@ -470,10 +470,16 @@ bool tame_camera(const float inv[16], int W, int H) {
     return wmin > 1e-6 * wmax;
 }
 
-void cull_rect(const float inv[16], int W, int H, float cull[4], int* centre_row) {
+// hull (optional): up to kHullEdges inward half-planes a*cx + b*cy + c >= 0 (unit normals, pixel units, 2 px of margin)
+// of the convex hull of the eight projected corners — the box's silhouette; unused edges are (0, 0, 1). A pixel's ray is a
+// line through the eye, and it meets the (convex) box iff the pixel lies in the convex hull of the corner images, so
+// everything outside the hull misses as surely as everything outside the rectangle, and the hull is ~half its area.
+void cull_rect(const float inv[16], int W, int H, float cull[4], int* centre_row, float (*hull)[3] = nullptr) {
     const float big = 3.0e38f;
     cull[0] = cull[1] = -big; cull[2] = cull[3] = big;
     *centre_row = -1;
+    if (hull) for (int k = 0; k < kHullEdges; ++k) { hull[k][0] = 0.0f; hull[k][1] = 0.0f; hull[k][2] = 1.0f; }
+    double px[8], py[8];
     double a[4][8];
     for (int r = 0; r < 4; ++r)
         for (int k = 0; k < 4; ++k) { a[r][k] = (double)inv[4 * k + r]; a[r][4 + k] = r == k ? 1.0 : 0.0; }  // column-major in
@@ -502,6 +508,7 @@ void cull_rect(const float inv[16], int W, int H, float cull[4], int* centre_row
         // sx = 2*cx/W - 1 ; sy = (2*cy/H - 1) * (-H/W)     (raycast_compute.wgsl:103-105)
         const double cx = (sx + 1.0) * 0.5 * W, cy = (1.0 - sy * (double)W / (double)H) * 0.5 * H;
         x0 = std::min(x0, cx); x1 = std::max(x1, cx); y0 = std::min(y0, cy); y1 = std::max(y1, cy);
+        px[cidx] = cx; py[cidx] = cy;
     }
     if (!(wmin > 1e-6 * wmax)) return;  // a corner (almost) on the camera plane: its image is unreliable
     if (!std::isfinite(x0) || !std::isfinite(x1) || !std::isfinite(y0) || !std::isfinite(y1)) return;
@@ -511,6 +518,31 @@ void cull_rect(const float inv[16], int W, int H, float cull[4], int* centre_row
     cull[2] = (float)std::min(lim, ceil(x1 + margin));   cull[3] = (float)std::min(lim, ceil(y1 + margin));
     const double cyc = 0.5 * (std::max(y0, 0.0) + std::min(y1, (double)H - 1.0));
     if (cyc >= 0.0 && cyc <= (double)H - 1.0) *centre_row = (int)cyc;
+    if (hull) {
+        // Andrew's monotone chain over the eight corner images; collinear points dropped. A box's silhouette has at most
+        // six edges; anything else (degenerate, numerically odd) leaves the hull unused: the rectangle still culls.
+        int idx[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+        std::sort(idx, idx + 8, [&](int a, int b) { return px[a] < px[b] || (px[a] == px[b] && py[a] < py[b]); });
+        auto cross = [&](int o, int a, int b) { return (px[a] - px[o]) * (py[b] - py[o]) - (py[a] - py[o]) * (px[b] - px[o]); };
+        int hv[16], m = 0;
+        for (int i = 0; i < 8; ++i) { while (m >= 2 && cross(hv[m - 2], hv[m - 1], idx[i]) <= 0.0) --m; hv[m++] = idx[i]; }
+        for (int i = 6, lo = m + 1; i >= 0; --i) { while (m >= lo && cross(hv[m - 2], hv[m - 1], idx[i]) <= 0.0) --m; hv[m++] = idx[i]; }
+        --m;  // the last point repeats the first
+        if (m >= 3 && m <= kHullEdges) {
+            bool ok = true;
+            float planes[kHullEdges][3];
+            for (int e = 0; e < m && ok; ++e) {
+                const int a = hv[e], b = hv[(e + 1) % m];  // counter-clockwise: the interior is on the left of a -> b
+                const double ex = px[b] - px[a], ey = py[b] - py[a], len = sqrt(ex * ex + ey * ey);
+                if (!(len > 1e-9) || !std::isfinite(len)) { ok = false; break; }
+                const double nx = -ey / len, ny = ex / len;  // inward normal
+                const double cc = -(nx * px[a] + ny * py[a]) + margin;
+                if (!std::isfinite(nx) || !std::isfinite(ny) || !std::isfinite(cc) || fabs(cc) > 1e9) { ok = false; break; }
+                planes[e][0] = (float)nx; planes[e][1] = (float)ny; planes[e][2] = (float)cc;
+            }
+            if (ok) for (int e = 0; e < m; ++e) { hull[e][0] = planes[e][0]; hull[e][1] = planes[e][1]; hull[e][2] = planes[e][2]; }
+        }
+    }
 }
 
 // n_frames > 1 (with frames_out): the `single` entry for n_frames cameras in ONE launch, frame f stored at
@@ -543,7 +575,7 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     for (int f = 0; f < n_frames; ++f) {
         memcpy(A.inv[f], cam[f].inv_proj, sizeof A.inv[f]);
         int centre_row;
-        cull_rect(A.inv[f], A.W, A.H, A.cull[f], &centre_row);
+        cull_rect(A.inv[f], A.W, A.H, A.cull[f], &centre_row, A.hull[f]);
         // M1's skipping indexes the padded distance field without a bounds test (RenderArgs::dist)
         if (P.mode == VKRT_MODE_M1 && skip && !tame_camera(A.inv[f], A.W, A.H)) skip = false;
     }
@@ -897,6 +929,15 @@ int vkrt_box_screen_bounds(const VkrtCameraUniform* cam, int width, int height, 
     int row = -1;
     cull_rect(cam->inv_proj, width, height, rect, &row);
     if (centre_row) *centre_row = row;
+    return VKRT_OK;
+}
+
+int vkrt_box_screen_hull(const VkrtCameraUniform* cam, int width, int height, float planes[6][3]) {
+    if (!cam || !planes || width <= 0 || height <= 0) return fail(VKRT_ERR_INVALID, "bad box_screen_hull arguments");
+    static_assert(kHullEdges == 6, "vkrt_box_screen_hull returns six half-planes");
+    float rect[4];
+    int row = -1;
+    cull_rect(cam->inv_proj, width, height, rect, &row, planes);
     return VKRT_OK;
 }
 

@@ -249,7 +249,15 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
     {
         const float cx = (float)gx + offx, cy = (float)gy + offy;
         const float* cull = A.cull[fr];
-        if (valid && cx >= cull[0] && cy >= cull[1] && cx <= cull[2] && cy <= cull[3]) {
+        bool may_hit = valid && cx >= cull[0] && cy >= cull[1] && cx <= cull[2] && cy <= cull[3];
+        if (may_hit) {  // inside the rectangle: inside the silhouette's convex hull as well? (half of the rectangle is not)
+            const float(*hp)[3] = A.hull[fr];
+            const float d0 = fmaf(hp[0][0], cx, fmaf(hp[0][1], cy, hp[0][2])), d1 = fmaf(hp[1][0], cx, fmaf(hp[1][1], cy, hp[1][2]));
+            const float d2 = fmaf(hp[2][0], cx, fmaf(hp[2][1], cy, hp[2][2])), d3 = fmaf(hp[3][0], cx, fmaf(hp[3][1], cy, hp[3][2]));
+            const float d4 = fmaf(hp[4][0], cx, fmaf(hp[4][1], cy, hp[4][2])), d5 = fmaf(hp[5][0], cx, fmaf(hp[5][1], cy, hp[5][2]));
+            may_hit = fminf(fminf(fminf(d0, d1), fminf(d2, d3)), fminf(d4, d5)) >= 0.0f;
+        }
+        if (may_hit) {
             gen_ray(A.inv[fr], (float)gx, (float)gy, offx, offy, (float)A.W, (float)A.H, eye, dir);
             intersect_box(eye, dir, t0, t1, inv_dir);
         }

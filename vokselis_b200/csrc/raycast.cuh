@@ -11,6 +11,7 @@ namespace vkrt {
 // Everything one raycast launch reads; passed by value as a __grid_constant__ kernel parameter
 // (lives in the constant bank, no global loads for the camera or the parameters).
 constexpr int kMaxBatch = VKRT_MAX_BATCH;
+constexpr int kHullEdges = 6;
 struct RenderArgs {
     // ---- what every iteration of the march reads, kept together at the front (ptxas re-reads kernel parameters with
     // LDCU inside the loop rather than keeping them in registers; tried and rejected: forcing them into registers through
@@ -42,6 +43,7 @@ struct RenderArgs {
     // the dependent march of its longest rays; several frames of a sweep in one grid do (measured 1.85x).
     float inv[kMaxBatch][16];  // per frame: CameraUniform.inv_proj, column-major (src/camera.rs:10)
     float cull[kMaxBatch][4];  // per frame: x0, y0, x1, y1 (ray coordinates = gid + offset): pixels outside cannot hit the box
+    float hull[kMaxBatch][kHullEdges][3];  // per frame: inward half-planes a*cx + b*cy + c >= 0 of the box's silhouette (api.cu cull_rect)
     int n_frames;
     int W, H;
     // tiles: n_tiles == 0 -> `single`; else grid.z indexes `offsets` (device memory)

@@ -25,7 +25,7 @@ _SO = Path(os.environ.get("VKRT_LIB") or (Path(__file__).resolve().parent / "lib
 EXPORTS = [
     "vkrt_create", "vkrt_destroy", "vkrt_resize", "vkrt_last_error", "vkrt_default_params", "vkrt_set_params",
     "vkrt_get_params", "vkrt_upload_rgba16f", "vkrt_upload_scalar", "vkrt_generate_xor", "vkrt_download_rgba16f",
-    "vkrt_render", "vkrt_render_tiles", "vkrt_tile_table", "vkrt_box_screen_bounds",
+    "vkrt_render", "vkrt_render_tiles", "vkrt_tile_table", "vkrt_box_screen_bounds", "vkrt_box_screen_hull",
     "vkrt_render_batch", "vkrt_batch_frame_device_ptr", "vkrt_readback_batch", "vkrt_frames_host", "vkrt_present", "vkrt_present_scaled", "vkrt_readback", "vkrt_readback_rgba8", "vkrt_readback_rgba8_async",
     "vkrt_readback_aux", "vkrt_sync", "vkrt_frame_host", "vkrt_frame_host_async", "vkrt_frame_host_wait",
     "vkrt_frame_host_slot_ptr", "vkrt_frame_device_ptr", "vkrt_frame_rgba8_device_ptr", "vkrt_stream", "vkrt_stats",
@@ -75,6 +75,7 @@ def lib() -> C.CDLL:
         "vkrt_render_tiles": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp, ci]),
         "vkrt_tile_table": (ci, [ci, ci, ci, vp, ci]),
         "vkrt_box_screen_bounds": (ci, [C.POINTER(CameraUniform), ci, ci, C.POINTER(C.c_float * 4), C.POINTER(ci)]),
+        "vkrt_box_screen_hull": (ci, [C.POINTER(CameraUniform), ci, ci, vp]),
         "vkrt_render_batch": (ci, [vp, vp, ci, C.POINTER(Uniform)]),
         "vkrt_batch_frame_device_ptr": (vp, [vp, ci]),
         "vkrt_readback_batch": (ci, [vp, ci, vp]),
@@ -659,6 +660,13 @@ def sortfirst_partition(width: int, height: int, tile_size: int, rank: int, worl
     out = np.zeros((n, 2), np.float32)
     lib().vkrt_sortfirst_partition(width, height, tile_size, rank, world, _vp(out), n)
     return out
+
+
+def box_screen_hull(cam: CameraUniform, width: int, height: int) -> np.ndarray:
+    """Six inward half-planes [a, b, c] (a*cx + b*cy + c >= 0 inside) of the box's silhouette, 2 px of margin (host-only)."""
+    planes = np.zeros((6, 3), np.float32)
+    _check(lib().vkrt_box_screen_hull(C.byref(cam), width, height, _vp(planes)))
+    return planes
 
 
 class RaycastPipeline:
