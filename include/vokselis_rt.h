@@ -308,6 +308,11 @@ VKRT_API int vkrt_sortfirst_render(VkrtContext* ctx, const VkrtCameraUniform* ca
 #define VKRT_SF_FLUSH_L2 1 /* flags: write an L2-sized buffer before the launch, on the stream the launch uses (benchmarks) */
 VKRT_API int vkrt_sortfirst_render_batch(VkrtContext* ctx, const VkrtCameraUniform* cams, int n, const VkrtUniform* un, uint64_t first_frame,
                                          int flags);
+/* "tiles" granularity, batched: this rank's tiles (offsets, n) of n_frames <= 15 consecutive frames in ONE launch
+ * (grid.z = frame x tile) into n_frames consecutive ring slots; every rank calls it with its own tile table. A frame's
+ * share on 1/N of the GPUs is a short launch bounded by its longest rays, so shares are batched like whole frames. */
+VKRT_API int vkrt_sortfirst_render_tiles_batch(VkrtContext* ctx, const VkrtCameraUniform* cams, int n_frames, const VkrtUniform* un,
+                                               const VkrtOffset* offsets, int n, uint64_t first_frame);
 VKRT_API int vkrt_sortfirst_wait(VkrtContext* ctx, uint64_t frame_index, uint64_t arrivals_target);
 VKRT_API int vkrt_sortfirst_consume(VkrtContext* ctx, uint64_t frame_index, int do_present);
 /* Number of device-side waits that gave up after 10 s (a peer died); 0 on a healthy group. Synchronises. */

@@ -59,6 +59,7 @@ struct VkrtContext {
     uint2* sf_local[kSfLanes] = {};
     cudaEvent_t sf_ready[kSfLanes] = {}, sf_copied[kSfLanes] = {};
     int sf_lane = 0;
+    int sf_local_cap = 0;  // frames each sf_local buffer holds
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // recorded on `stream` after a layout (BRICKED / TEXTURE / GATHER) was built there; a render launched on another
     // stream (the sort-first root renders on copy_stream) waits for it before reading the layout
@@ -171,13 +172,23 @@ void x_release(VkrtContext* c) {
     c->x_world = 0;
     c->x_expected[0] = c->x_expected[1] = 0;
 }
-int sf_lanes_ensure(VkrtContext* c, bool local_frames) {
+int sf_lanes_ensure(VkrtContext* c, bool local_frames, int frames = 1) {
+    if (local_frames && frames > c->sf_local_cap) {  // a lane's local buffer holds the shares of `frames` consecutive frames
+        for (int i = 0; i < VkrtContext::kSfLanes; ++i) {
+            if (c->sf_stream[i]) CK(cudaStreamSynchronize(c->sf_stream[i]));
+            if (c->sf_local[i]) cudaFree(c->sf_local[i]);
+            c->sf_local[i] = nullptr;
+        }
+        CK(cudaStreamSynchronize(c->copy_stream));
+        c->sf_local_cap = 0;
+    }
     for (int i = 0; i < VkrtContext::kSfLanes; ++i) {
         if (!c->sf_stream[i]) CK(cudaStreamCreateWithFlags(&c->sf_stream[i], cudaStreamNonBlocking));
         if (!c->sf_ready[i]) CK(cudaEventCreateWithFlags(&c->sf_ready[i], cudaEventDisableTiming));
         if (!c->sf_copied[i]) CK(cudaEventCreateWithFlags(&c->sf_copied[i], cudaEventDisableTiming));
-        if (local_frames && !c->sf_local[i]) CK(cudaMalloc(&c->sf_local[i], (size_t)c->W * c->H * sizeof(uint2)));
+        if (local_frames && !c->sf_local[i]) CK(cudaMalloc(&c->sf_local[i], (size_t)c->W * c->H * sizeof(uint2) * (size_t)frames));
     }
+    if (local_frames && frames > c->sf_local_cap) c->sf_local_cap = frames;
     return VKRT_OK;
 }
 void sf_lanes_free(VkrtContext* c, bool streams_too) {
@@ -185,6 +196,7 @@ void sf_lanes_free(VkrtContext* c, bool streams_too) {
         if (c->sf_stream[i]) cudaStreamSynchronize(c->sf_stream[i]);
         if (c->sf_local[i]) cudaFree(c->sf_local[i]);
         c->sf_local[i] = nullptr;
+        c->sf_local_cap = 0;
         if (streams_too) {
             if (c->sf_ready[i]) cudaEventDestroy(c->sf_ready[i]);
             if (c->sf_copied[i]) cudaEventDestroy(c->sf_copied[i]);
@@ -644,7 +656,7 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     A.rgba8 = rgba8_out;
     const bool dbg = P.count_samples != 0;
     if (dbg && n_frames > 1) return fail(VKRT_ERR_INVALID, "params.count_samples needs single-frame renders (the counters are per frame)");
-    if (n_frames > 1 && (offsets && n > 0)) return fail(VKRT_ERR_INVALID, "a batch renders whole frames (`single`), not tiles");
+    if (n_frames > 1 && (offsets && n > 0) && (size_t)n * n_frames > 65535) return fail(VKRT_ERR_INVALID, "tiles x frames exceed one launch (65535)");
     if (dbg && !c->aux) {
         CK(cudaMalloc(&c->aux, (size_t)c->W * c->H * 4));
         CK(cudaMemsetAsync(c->aux, 0, (size_t)c->W * c->H * 4, c->stream));
@@ -1392,6 +1404,61 @@ int vkrt_sortfirst_render(VkrtContext* c, const VkrtCameraUniform* cam, const Vk
         CK(cudaMemcpyAsync(sf_slot(c, slot), c->sf_local[lane], sf_frame_bytes(c), cudaMemcpyDeviceToDevice, c->copy_stream));
     }
     CK(launch_flag_add(sf_arrive(c, slot), 1ull, c->copy_stream));  // after the transfer, system scope
+    CK(cudaEventRecord(c->sf_copied[lane], c->copy_stream));
+    return VKRT_OK;
+}
+
+int vkrt_sortfirst_render_tiles_batch(VkrtContext* c, const VkrtCameraUniform* cams, int n_frames, const VkrtUniform* un, const VkrtOffset* offsets, int n,
+                                      uint64_t first_frame) {
+    if (!c || !c->sf_base) return fail(VKRT_ERR_INVALID, "context is not in a sort-first group");
+    if (!cams || !offsets || n < 1 || n_frames < 1 || n_frames > kMaxPushDst || n_frames > VKRT_MAX_BATCH)
+        return fail(VKRT_ERR_INVALID, "tile batch needs 1..15 cameras and this rank's tiles");
+    const int slot0 = (int)(first_frame % (uint64_t)c->sf_slots);
+    if (slot0 + n_frames > c->sf_slots) return fail(VKRT_ERR_INVALID, "a batch must occupy consecutive ring slots (slots % batch == 0, first_frame % batch == 0)");
+    CK(cudaSetDevice(c->device));
+    cudaEvent_t eb = nullptr, ee = nullptr;
+    if (!c->ring_begin.empty()) {
+        eb = c->ring_begin[c->ring_next];
+        ee = c->ring_end[c->ring_next];
+        c->ring_next = (c->ring_next + 1) % c->ring_begin.size();
+        if (c->ring_count < c->ring_begin.size()) ++c->ring_count;
+    }
+    // slot reuse: the frame that used the LAST of these slots before must have been consumed (frames are consumed in order)
+    const uint64_t last = first_frame + (uint64_t)n_frames - 1;
+    const bool must_wait = last >= (uint64_t)c->sf_slots;
+    const uint64_t consumed_target = must_wait ? last - (uint64_t)c->sf_slots + 1 : 0;
+    int rc = sf_lanes_ensure(c, c->sf_rank != 0, n_frames);
+    if (rc) return rc;
+    const int lane = c->sf_lane;
+    c->sf_lane = (c->sf_lane + 1) % VkrtContext::kSfLanes;
+    cudaStream_t ls = c->sf_stream[lane];
+    PushDst arrive{};
+    for (int f = 0; f < n_frames; ++f) arrive.ptr[f] = sf_arrive(c, slot0 + f);
+    arrive.n = n_frames;
+    // ONE launch for this rank's tiles of n_frames consecutive frames (grid.z = frame x tile): a single frame's share on
+    // 1/N of the GPUs lasts as long as its longest rays whatever its pixel count (config 4: 72 of 576 tiles take 0.30 ms
+    // where 576 take 0.78 ms), so the shares of several frames are batched exactly like whole frames are.
+    if (c->sf_rank == 0) {
+        if (must_wait) CK(launch_flag_wait(sf_consumed(c), consumed_target, sf_timeouts(c), ls));
+        if (eb) CK(cudaEventRecord(eb, ls));
+        rc = do_render(c, cams, un, offsets, n, false, n_frames, sf_slot(c, slot0), nullptr, ls);
+        if (rc) return rc;
+        if (ee) CK(cudaEventRecord(ee, ls));
+        CK(launch_flag_add_many(arrive, 1ull, ls));
+        return VKRT_OK;
+    }
+    CK(cudaStreamWaitEvent(ls, c->sf_copied[lane], 0));  // the lane's local frames have left
+    if (eb) CK(cudaEventRecord(eb, ls));
+    rc = do_render(c, cams, un, offsets, n, false, n_frames, c->sf_local[lane], nullptr, ls);
+    if (rc) return rc;
+    if (ee) CK(cudaEventRecord(ee, ls));
+    CK(cudaEventRecord(c->sf_ready[lane], ls));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->sf_ready[lane], 0));
+    if (must_wait) CK(launch_flag_wait(sf_consumed(c), consumed_target, sf_timeouts(c), c->copy_stream));
+    bool vec16 = (c->W % 2 == 0) && (c->params.tile_size % 2 == 0);
+    for (int i = 0; i < n && vec16; ++i) vec16 = ((long long)offsets[i].x % 2) == 0 && offsets[i].x >= 0.0f;
+    CK(launch_push_tiles(c->sf_local[lane], sf_slot(c, slot0), c->d_offsets, n, c->params.tile_size, c->W, c->H, vec16, c->copy_stream, n_frames));
+    CK(launch_flag_add_many(arrive, 1ull, c->copy_stream));  // after the transfer, system scope
     CK(cudaEventRecord(c->sf_copied[lane], c->copy_stream));
     return VKRT_OK;
 }

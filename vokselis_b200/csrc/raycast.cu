@@ -230,9 +230,10 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
     float offx = 0.0f, offy = 0.0f;
     uint32_t px = gx, py = gy;
     bool valid = true;
-    const uint32_t fr = A.n_tiles > 0 ? 0u : blockIdx.z;  // `single`: grid.z = frame of the batch
+    // `single`: grid.z = frame of the batch; `tile`: grid.z = frame * n_tiles + tile (the tile shares of several frames in one launch)
+    const uint32_t fr = A.n_tiles > 0 ? blockIdx.z / (uint32_t)A.n_tiles : blockIdx.z;
     if (A.n_tiles > 0) {  // `tile` entry: coord = gid + offset; store at gid + u32(offset)
-        const VkrtOffset o = A.offsets[blockIdx.z];
+        const VkrtOffset o = A.offsets[blockIdx.z - fr * (uint32_t)A.n_tiles];
         offx = o.x;
         offy = o.y;
         px = gx + __float2uint_rz(offx);  // vec2<u32>(f32) saturates: a negative offset stores at gid + 0
@@ -450,7 +451,8 @@ cudaError_t launch_raycast(const RenderArgs& A, int mode, int layout, int dtype,
     const dim3 block((unsigned)bw, (unsigned)bh, 1);
     dim3 grid;
     if (A.n_tiles > 0) {
-        grid = dim3((unsigned)((A.tile_size + bw - 1) / bw), (unsigned)((A.tile_size + bh - 1) / bh), (unsigned)A.n_tiles);
+        grid = dim3((unsigned)((A.tile_size + bw - 1) / bw), (unsigned)((A.tile_size + bh - 1) / bh),
+                    (unsigned)A.n_tiles * (unsigned)(A.n_frames > 0 ? A.n_frames : 1));
     } else {
         grid = dim3((unsigned)((A.W + bw - 1) / bw), (unsigned)((A.H + bh - 1) / bh), (unsigned)(A.n_frames > 0 ? A.n_frames : 1));
     }

@@ -116,7 +116,7 @@ cudaError_t launch_synth(void* out, int kind, int dtype, int nx, int ny, int nz,
 cudaError_t launch_brick_window(const void* lin, void* out, int elem_bytes, int nx, int ny, int nz, cudaStream_t s);
 // vec16: every tile origin x and W are even (16-byte aligned rows): two pixels per store
 cudaError_t launch_push_tiles(const uint2* src, uint2* dst, const VkrtOffset* d_offsets, int n_tiles, int tile, int W, int H, bool vec16,
-                              cudaStream_t s);
+                              cudaStream_t s, int n_frames = 1);  // n_frames consecutive frames of W*H texels on both sides
 cudaError_t launch_flush_l2(uint4* buf, size_t n16, cudaStream_t s);
 // sort-last direct-send: up to kMaxPushDst destinations (peer memory) per launch
 constexpr int kMaxPushDst = 15;

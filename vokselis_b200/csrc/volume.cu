@@ -353,6 +353,8 @@ __global__ void __launch_bounds__(256) push_tiles_kernel(const uint2* __restrict
     const VkrtOffset o = offsets[blockIdx.x];
     const uint32_t x0 = __float2uint_rz(o.x), y0 = __float2uint_rz(o.y);
     if (x0 >= (uint32_t)W || y0 >= (uint32_t)H) return;
+    src += (size_t)blockIdx.z * W * H;  // grid.z = frame of a batched tile share: consecutive local frames -> consecutive ring slots
+    dst += (size_t)blockIdx.z * W * H;
     const int cols = min(tile, W - (int)x0) / PX;  // vectors per row (PX pixels each)
     const int r0 = (int)blockIdx.y * 16, r1 = min(min(r0 + 16, tile), H - (int)y0);
     for (int i = (int)threadIdx.x; i < (r1 - r0) * cols; i += (int)blockDim.x) {
@@ -372,9 +374,9 @@ __global__ void __launch_bounds__(256) push_tiles_kernel(const uint2* __restrict
 }  // namespace
 
 cudaError_t launch_push_tiles(const uint2* src, uint2* dst, const VkrtOffset* d_offsets, int n_tiles, int tile, int W, int H, bool vec16,
-                              cudaStream_t s) {
+                              cudaStream_t s, int n_frames) {
     if (n_tiles <= 0) return cudaSuccess;
-    const dim3 grid((unsigned)n_tiles, (unsigned)((tile + 15) / 16));
+    const dim3 grid((unsigned)n_tiles, (unsigned)((tile + 15) / 16), (unsigned)(n_frames > 0 ? n_frames : 1));
     if (vec16) push_tiles_kernel<uint4, 2><<<grid, 256, 0, s>>>(src, dst, d_offsets, tile, W, H);
     else push_tiles_kernel<uint2, 1><<<grid, 256, 0, s>>>(src, dst, d_offsets, tile, W, H);
     return cudaGetLastError();

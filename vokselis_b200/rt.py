@@ -30,7 +30,7 @@ EXPORTS = [
     "vkrt_readback_aux", "vkrt_sync", "vkrt_frame_host", "vkrt_frame_host_async", "vkrt_frame_host_wait",
     "vkrt_frame_host_slot_ptr", "vkrt_frame_device_ptr", "vkrt_frame_rgba8_device_ptr", "vkrt_stream", "vkrt_stats",
     "vkrt_reset_stats", "vkrt_timing_enable", "vkrt_timing_read", "vkrt_flush_l2", "vkrt_volume_info", "vkrt_camera_uniform", "vkrt_dispatch_optimal",
-    "vkrt_sortfirst_create_root", "vkrt_sortfirst_join", "vkrt_sortfirst_leave", "vkrt_sortfirst_partition", "vkrt_sortfirst_render", "vkrt_sortfirst_render_batch",
+    "vkrt_sortfirst_create_root", "vkrt_sortfirst_join", "vkrt_sortfirst_leave", "vkrt_sortfirst_partition", "vkrt_sortfirst_render", "vkrt_sortfirst_render_batch", "vkrt_sortfirst_render_tiles_batch",
     "vkrt_sortfirst_consume", "vkrt_sortfirst_timeouts", "vkrt_sortfirst_wait", "vkrt_mark", "vkrt_mark_elapsed",
     "vkrt_alloc_host", "vkrt_free_host", "vkrt_host_register", "vkrt_host_unregister", "vkrt_generate_synthetic", "vkrt_download_scalar", "vkrt_scalar_to_rgba16f",
     "vkrt_upload_window", "vkrt_generate_synthetic_window", "vkrt_window_info", "vkrt_partial_alpha", "vkrt_partial_ain",
@@ -128,6 +128,7 @@ def lib() -> C.CDLL:
         "vkrt_sortfirst_partition": (ci, [ci, ci, ci, ci, ci, vp, ci]),
         "vkrt_sortfirst_render": (ci, [vp, C.POINTER(CameraUniform), C.POINTER(Uniform), vp, ci, C.c_uint64]),
         "vkrt_sortfirst_render_batch": (ci, [vp, vp, ci, C.POINTER(Uniform), C.c_uint64, ci]),
+        "vkrt_sortfirst_render_tiles_batch": (ci, [vp, vp, ci, C.POINTER(Uniform), vp, ci, C.c_uint64]),
         "vkrt_sortfirst_consume": (ci, [vp, C.c_uint64, ci]),
         "vkrt_sortfirst_timeouts": (ci, [vp, C.POINTER(C.c_uint64)]),
         "vkrt_exchange_create": (ci, [vp, ci, ci, vp]),
@@ -484,6 +485,11 @@ class Context:
         un = uniform if uniform is not None else self.global_uniform
         arr = self._cam_array(cams)
         _check(lib().vkrt_sortfirst_render_batch(self._h, C.cast(arr, C.c_void_p), len(cams), C.byref(un), first_frame, 1 if flush_l2 else 0))
+
+    def sortfirst_render_tiles_batch(self, cams, offsets: np.ndarray, first_frame: int, uniform: Uniform | None = None):
+        un = uniform if uniform is not None else self.global_uniform
+        arr = self._cam_array(cams)
+        _check(lib().vkrt_sortfirst_render_tiles_batch(self._h, C.cast(arr, C.c_void_p), len(cams), C.byref(un), _vp(offsets), offsets.shape[0], first_frame))
 
     def sortfirst_consume(self, frame_index: int, present: bool = False):
         _check(lib().vkrt_sortfirst_consume(self._h, frame_index, 1 if present else 0))

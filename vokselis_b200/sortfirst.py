@@ -58,10 +58,10 @@ class SortFirstGroup:
         if granularity not in ("tiles", "frames"):
             raise ValueError(granularity)
         self.ctx, self.rank, self.world, self.dist, self.granularity = ctx, rank, world, dist, granularity
-        self.batch = batch if granularity == "frames" else 1
-        if not 1 <= self.batch <= rt.MAX_BATCH:
-            raise ValueError(f"batch must be 1..{rt.MAX_BATCH}")
-        self.slots = slots if slots is not None else (2 if granularity == "tiles" else 2 * world * self.batch)
+        self.batch = batch  # frames per launch: groups of whole frames ("frames") or of every rank's tile shares ("tiles")
+        if not 1 <= self.batch <= (rt.MAX_BATCH if granularity == "frames" else 15):
+            raise ValueError(f"batch must be 1..{rt.MAX_BATCH} (frames) / 1..15 (tiles)")
+        self.slots = slots if slots is not None else (2 * self.batch if granularity == "tiles" else 2 * world * self.batch)
         if self.slots % self.batch or not 2 <= self.slots <= MAX_SLOTS:
             raise ValueError(f"slots must be a multiple of batch in 2..{MAX_SLOTS}")
         self.tiles = None
@@ -90,6 +90,8 @@ class SortFirstGroup:
         """Every rank calls this once per frame, in the same order. Asynchronous. Returns the frame index."""
         f = self.frame
         self.frame += 1
+        if self.batch > 1 and self.granularity == "tiles":
+            raise RuntimeError("with batch > 1 use submit_tiles_batch")
         if self.granularity == "tiles":
             self.ctx.sortfirst_render(cam, self.tiles, f)
         elif self.batch > 1:
@@ -108,6 +110,25 @@ class SortFirstGroup:
         self.frame += self.batch
         if frame_owner(f, self.world, self.batch) == self.rank:
             self.ctx.sortfirst_render_batch(cams, f, flush_l2=flush_l2)
+        return f
+
+    def submit_tiles_batch(self, cams) -> int:
+        """'tiles' granularity with batch > 1: every rank calls this once per group of len(cams) <= batch consecutive
+        frames, in the same order, and renders ITS tiles of all of them in one launch. Returns the group's first frame."""
+        assert self.granularity == "tiles" and 1 <= len(cams) <= self.batch and self.frame % self.batch == 0
+        cams = list(cams) + [cams[-1]] * (self.batch - len(cams))  # a short last group is padded: every slot gets its arrivals
+        f = self.frame
+        self.frame += self.batch
+        self.ctx.sortfirst_render_tiles_batch(cams, self.tiles, f)
+        return f
+
+    def render_tiles_batch(self, cams, present: bool = False) -> int:
+        """submit_tiles_batch + (root) wait + consume of every frame of the group, in order. Asynchronous."""
+        f = self.submit_tiles_batch(cams)
+        if self.rank == 0:
+            for k in range(self.batch):
+                self.wait(f + k)
+                self.consume(f + k, present)
         return f
 
     def render_batch(self, cams, present: bool = False, flush_l2: bool = False) -> int:
