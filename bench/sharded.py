@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--tile", type=int, default=120)
     ap.add_argument("--tbatch", type=int, default=1, help="frames per launch of a rank's tile share (configs 3/4)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="sort-last transmittance exchange")
+    ap.add_argument("--brick", type=int, default=0, help="occupancy brick edge (configs 3/4); 0 = automatic")
     ap.add_argument("--layout", type=int, default=-1, help="-1 = the layout workloads.py chose per config")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -45,7 +46,7 @@ def main():
     for cid in (3, 4):
         if str(cid) in what:
             r = workloads.run_sortfirst_tiles(cid, rank, world, local, dist, frames=args.frames, tile=args.tile, layout=(None if args.layout < 0 else args.layout),
-                                              edge=args.edge34 or None, hbm_peak_gbs=peak, batch=args.tbatch)
+                                              edge=args.edge34 or None, hbm_peak_gbs=peak, batch=args.tbatch, brick=args.brick)
             if rank == 0:
                 print(json.dumps(r), flush=True)
     if "5" in what and world > 1:

@@ -376,7 +376,12 @@ VKRT_API int vkrt_exchange_close(VkrtContext* ctx);
 VKRT_API int vkrt_mark(VkrtContext* ctx, int idx);
 VKRT_API int vkrt_mark_elapsed(VkrtContext* ctx, int from, int to, float* ms);
 
-/* kind: 0 none, 1 rgba16f pair, 2 scalar. bricks = 8^3-voxel cells of the occupancy grid. */
+/* Edge, in voxels, of the bricks of the raycast's occupancy grid (exact empty-space skipping) for the volumes uploaded or
+ * generated AFTER this call: 0 = automatic (the finest of 2..32 whose eight directional distance tables fit a fixed cache
+ * budget), else 2, 4, 8, 16 or 32. A tuning knob: frames are bit-identical for every value. No reference counterpart (the
+ * reference marches every sample, shaders/raycast_compute.wgsl:70-96). */
+VKRT_API int vkrt_set_occupancy_brick(VkrtContext* ctx, int edge);
+/* kind: 0 none, 1 rgba16f pair, 2 scalar. bricks = cells of the occupancy grid (see above; sort-last windows: 8^3 voxels). */
 VKRT_API int vkrt_volume_info(VkrtContext* ctx, int* kind, int* dtype, int dims[3], uint64_t* bricks_total,
                               uint64_t* bricks_occupied);
 

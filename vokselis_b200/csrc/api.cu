@@ -43,6 +43,14 @@ enum VolKind { VOL_NONE = 0, VOL_RGBA16F = 1, VOL_SCALAR = 2 };
 // Leaps are capped at this many bricks (8 voxels each): bounds the drift of the repeated addition that a
 // leap replays and the number of relaxation passes at upload.
 constexpr int kMaxLeapBricks = 16;
+// The raycast's occupancy grid: a distance field may see at most kMaxLeapVoxels ahead, and the brick edge is the smallest
+// power of two whose eight padded tables fit kOctTableBudget bytes (and 32-bit cell indices). Finer bricks hug the occupied
+// voxels more tightly — fewer samples evaluated, longer leaps in voxels (bench/leap_model.py) — and measured faster down to
+// 2-voxel bricks even when the tables are 1 GB (2048^3 at edge 4: 2,059 frames/s, edge 8: 1,824, edge 16: 1,456;
+// 256^3 at edge 2 / 4 / 8 / 16: 14,838 / 13,812 / 11,960 / 9,569; profiles/r02_octant_ab.md).
+constexpr int kMaxLeapVoxels = 128;
+constexpr size_t kOctTableBudget = (size_t)5 << 28;  // 1.25 GiB: 2048^3 at edge 4
+constexpr int kMinAutoBrickShift = 1;
 
 }  // namespace
 
@@ -96,14 +104,19 @@ struct VkrtContext {
     uint2* own_frame = nullptr;        // the context's private frame while c->frame points into the ring
     // volume resources
     int kind = VOL_NONE, dtype = 0;
-    int nx = 0, ny = 0, nz = 0, nbx = 0, nby = 0, nbz = 0;
+    int nx = 0, ny = 0, nz = 0, nbx = 0, nby = 0, nbz = 0;  // nb*: 8^3-voxel bricks (BRICKED layout, sort-last windows)
+    // occupancy grid of the raycast: bricks of 2^obs voxels per edge (occupancy_brick_shift); obs_request: -1 = automatic
+    int obs = 3, obx = 0, oby = 0, obz = 0, obs_request = -1;
+    bool occ_full = false;  // every brick is occupied: there is nothing to skip
     void* lin_a = nullptr;  // rgba16f colour | scalar grid (upload layout)
     void* lin_b = nullptr;  // rgba16f normal
     uint4* bricked = nullptr;
     cudaArray_t arr_a = nullptr, arr_b = nullptr, arr_g = nullptr, arr_q = nullptr;
     cudaTextureObject_t tex_a = 0, tex_b = 0, tex_g = 0, tex_q = 0;  // tex_g: layered + gather (LAYOUT_GATHER); tex_q: pre-gathered quads (LAYOUT_QUAD)
-    uint8_t* dist = nullptr;  // brick distance field (0 = occupied)
-    uint8_t* dist_pad = nullptr;  // scalar volumes: the same, padded by one occupied layer on the high sides (RenderArgs::dist)
+    uint8_t* dist = nullptr;  // brick occupancy (0 = occupied, 255 = empty); sort-last windows: the Chebyshev distance field
+    // the 8 directional distance fields of the ray octants, back to back (RenderArgs::dist); scalar volumes: each padded by
+    // one occupied layer on the high sides
+    uint8_t* dist_oct = nullptr;
     int occ_lo[3] = {0, 0, 0}, occ_hi[3] = {-1, -1, -1};  // bounding box of the occupied bricks (inclusive); hi < lo = none
     // brick-partitioned (sort-last) state: the resident volume is a window of a larger global grid
     bool windowed = false;
@@ -148,10 +161,10 @@ void free_volume(VkrtContext* c) {
     if (c->lin_a) cudaFree(c->lin_a);
     if (c->lin_b) cudaFree(c->lin_b);
     if (c->dist) cudaFree(c->dist);
-    if (c->dist_pad) cudaFree(c->dist_pad);
+    if (c->dist_oct) cudaFree(c->dist_oct);
     c->lin_a = c->lin_b = nullptr;
     c->dist = nullptr;
-    c->dist_pad = nullptr;
+    c->dist_oct = nullptr;
     c->kind = VOL_NONE;
     c->windowed = false;
 }
@@ -399,28 +412,59 @@ int set_dims(VkrtContext* c, int nx, int ny, int nz) {
     return VKRT_OK;
 }
 
+int occupancy_brick_shift(const VkrtContext* c) {
+    if (c->obs_request >= 0) return c->obs_request;
+    for (int bs = kMinAutoBrickShift; bs < 5; ++bs) {
+        const size_t B = (size_t)1 << bs;
+        const size_t cells = ((c->nx + B - 1) / B + 1) * ((c->ny + B - 1) / B + 1) * ((c->nz + B - 1) / B + 1);
+        if (8 * cells <= kOctTableBudget) return bs;
+    }
+    return 5;
+}
+
 int build_occupancy(VkrtContext* c) {
-    const size_t cells = (size_t)c->nbx * c->nby * c->nbz;
-    uint8_t* scratch = nullptr;
+    c->obs = occupancy_brick_shift(c);
+    const int B = 1 << c->obs;
+    c->obx = (c->nx + B - 1) / B; c->oby = (c->ny + B - 1) / B; c->obz = (c->nz + B - 1) / B;
+    const int max_d = std::min(255, std::max(4, kMaxLeapVoxels / B));
+    const size_t cells = (size_t)c->obx * c->oby * c->obz;
+    const bool scalar = c->kind == VOL_SCALAR;
+    const size_t padded = (size_t)(c->obx + 1) * (c->oby + 1) * (c->obz + 1);
+    uint8_t *scratch = nullptr, *oct = nullptr;
+    int* d_bounds = nullptr;
     CK(cudaMalloc(&c->dist, cells));
-    CK(cudaMalloc(&scratch, cells < 64 ? 64 : cells));
+    CK(cudaMalloc(&d_bounds, 64));
     cudaError_t e;
-    if (c->kind == VOL_RGBA16F) e = launch_occupancy_m0((const uint2*)c->lin_a, (const uint2*)c->lin_b, c->nx, c->ny, c->nz, c->nbx, c->nby, c->nbz, c->dist, c->stream);
-    else e = launch_occupancy_m1(c->lin_a, c->dtype, c->nx, c->ny, c->nz, c->nbx, c->nby, c->nbz, c->dist, c->stream);
+    if (!scalar) e = launch_occupancy_m0((const uint2*)c->lin_a, (const uint2*)c->lin_b, c->nx, c->ny, c->nz, c->obx, c->oby, c->obz, c->obs, c->dist, c->stream);
+    else e = launch_occupancy_m1(c->lin_a, c->dtype, c->nx, c->ny, c->nz, c->obx, c->oby, c->obz, c->obs, c->dist, c->stream);
+    // bounding box of the occupied bricks (the raycast clips every ray to it) and the number of empty ones
+    int bounds[7] = {0, 0, 0, -1, -1, -1, 0};
+    if (e == cudaSuccess) e = launch_occupied_bounds(c->dist, c->obx, c->oby, c->obz, d_bounds, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bounds, d_bounds, sizeof bounds, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_bounds);
+    if (e != cudaSuccess) return cuda_fail(e, "build_occupancy");
+    for (int k = 0; k < 3; ++k) { c->occ_lo[k] = bounds[k]; c->occ_hi[k] = bounds[3 + k]; }
+    c->occ_full = bounds[6] == 0;
+    // (the kernel indexes the tables with 32 bits: a grid with more than 2^29 bricks renders without skipping; so does
+    // a volume without a single empty brick — every iteration would consult the tables for nothing)
+    if (c->occ_full || 8 * (scalar ? padded : cells) > 0xffffffffull) return VKRT_OK;
+    e = cudaMalloc(&scratch, 8 * cells);
+    if (e == cudaSuccess) e = cudaMalloc(&oct, 8 * cells);
     // bricks outside the grid: empty for M0 (out-of-range texels read 0), occupied for M1 (clamp-to-edge)
-    if (e == cudaSuccess) e = launch_distance_transform(c->dist, scratch, c->nbx, c->nby, c->nbz, c->kind == VOL_RGBA16F ? 255 : 0, kMaxLeapBricks, c->stream);
-    // bounding box of the occupied bricks (the raycast clips every ray to it); reuses the scratch buffer
-    int bounds[6] = {0, 0, 0, -1, -1, -1};
-    if (e == cudaSuccess) e = launch_occupied_bounds(c->dist, c->nbx, c->nby, c->nbz, (int*)scratch, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(bounds, scratch, sizeof bounds, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess && c->kind == VOL_SCALAR) {
-        e = cudaMalloc(&c->dist_pad, (size_t)(c->nbx + 1) * (c->nby + 1) * (c->nbz + 1));
-        if (e == cudaSuccess) e = launch_pad_dist(c->dist, c->dist_pad, c->nbx, c->nby, c->nbz, c->stream);
+    if (e == cudaSuccess) e = launch_octant_distance(c->dist, oct, scratch, c->obx, c->oby, c->obz, scalar ? 0 : 255, max_d, c->stream);
+    if (e == cudaSuccess && scalar) {
+        e = cudaMalloc(&c->dist_oct, 8 * padded);
+        if (e == cudaSuccess) e = launch_pad_dist(oct, c->dist_oct, c->obx, c->oby, c->obz, 8, c->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(scratch);
+    if (e == cudaSuccess && !scalar) {
+        c->dist_oct = oct;
+        oct = nullptr;
+    }
+    cudaFree(oct);
     if (e != cudaSuccess) return cuda_fail(e, "build_occupancy");
-    for (int k = 0; k < 3; ++k) { c->occ_lo[k] = bounds[k]; c->occ_hi[k] = bounds[3 + k]; }
     return VKRT_OK;
 }
 
@@ -579,7 +623,7 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     // clear_color.a == 0 (raycast_compute.wgsl:89,91). And the reference tests `a >= threshold` only after
     // compositing a sample (:92), so with initial_alpha >= alpha_threshold it stops after its FIRST sample, which a
     // leap would pass over. Otherwise fall back to the full march.
-    bool skip = P.skip_empty && !(P.mode == VKRT_MODE_M0 && P.clear_color[3] != 0.0f) && P.initial_alpha < P.alpha_threshold;
+    bool skip = P.skip_empty && c->dist_oct && !(P.mode == VKRT_MODE_M0 && P.clear_color[3] != 0.0f) && P.initial_alpha < P.alpha_threshold;
 
     RenderArgs A{};
     A.W = c->W; A.H = c->H;
@@ -625,15 +669,21 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     A.hx = A.fx / 2.0f; A.hy = A.fy / 2.0f; A.hz = A.fz / 2.0f;
     A.one = 1.0f;
     A.nbx = c->nbx; A.nby = c->nby; A.nbz = c->nbz;
-    if (P.mode == VKRT_MODE_M1 && c->dist_pad) {
-        A.dist = c->dist_pad;
-        A.dsx = (uint32_t)c->nbx + 1u; A.dsy = (uint32_t)c->nby + 1u;
-        A.dist_last = (uint32_t)((size_t)(c->nbx + 1) * (c->nby + 1) * (c->nbz + 1) - 1);
+    A.dist = c->dist_oct;
+    if (c->kind == VOL_SCALAR) {  // padded tables (M1)
+        A.dsx = (uint32_t)c->obx + 1u; A.dsy = (uint32_t)c->oby + 1u;
+        A.dist_tab = (uint32_t)((size_t)(c->obx + 1) * (c->oby + 1) * (c->obz + 1));
+        A.dsz_f = (float)(c->obz + 1);
     } else {
-        A.dist = c->dist;
-        A.dsx = (uint32_t)c->nbx; A.dsy = (uint32_t)c->nby;
-        A.dist_last = (uint32_t)((size_t)c->nbx * c->nby * c->nbz - 1);
+        A.dsx = (uint32_t)c->obx; A.dsy = (uint32_t)c->oby;
+        A.dist_tab = (uint32_t)((size_t)c->obx * c->oby * c->obz);
+        A.dsz_f = (float)c->obz;
     }
+    A.obs = c->obs;
+    A.brick = (float)(1 << c->obs); A.half_brick = 0.5f * A.brick; A.inv_brick = 1.0f / A.brick;
+    A.dist_last = 8u * A.dist_tab - 1u;
+    // M1 takes the brick coordinates as the bit patterns of 1.5 * 2^23 + b (raycast.cu): their common offset, mod 2^32
+    A.dist_bias = 0x4B400000u * (A.dsy * A.dsx + A.dsx + 1u);
     // shrink leap regions by ~16 ulp of the largest voxel coordinate (rounding of p and q)
     A.leap_eps = 16.0f * 1.1920929e-07f * (float)(c->nx > c->ny ? (c->nx > c->nz ? c->nx : c->nz) : (c->ny > c->nz ? c->ny : c->nz));
     {
@@ -641,13 +691,13 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
         for (int k = 0; k < 3; ++k) {
             if (c->occ_hi[0] < c->occ_lo[0]) { A.bb_lo[k] = 1.0f; A.bb_hi[k] = -1.0f; continue; }
             // voxel q = (p + 1) * n/2  ->  p = 2q/n - 1; one voxel of margin (float rounding is ~1e-4 of that)
-            const double lo = (double)c->occ_lo[k] * 8.0 - 1.0, hi = std::min((double)(c->occ_hi[k] + 1) * 8.0, (double)n3[k]) + 1.0;
+            const double lo = (double)c->occ_lo[k] * A.brick - 1.0, hi = std::min((double)(c->occ_hi[k] + 1) * A.brick, (double)n3[k]) + 1.0;
             A.bb_lo[k] = (float)(2.0 * lo / n3[k] - 1.0);
             A.bb_hi[k] = (float)(2.0 * hi / n3[k] - 1.0);
         }
     }
-    A.leap_r0 = -(4.0f + A.leap_eps);
-    A.leap_clip = ((c->nx | c->ny | c->nz) & 7) != 0;
+    A.leap_r0 = -(A.half_brick + A.leap_eps);
+    A.leap_clip = ((c->nx | c->ny | c->nz) & ((1 << c->obs) - 1)) != 0;
     A.leap_lim[0] = A.fx - A.leap_eps; A.leap_lim[1] = A.fy - A.leap_eps; A.leap_lim[2] = A.fz - A.leap_eps;
     A.dt_scale = P.dt_scale; A.dt_floor = P.dt_floor; A.alpha_threshold = P.alpha_threshold; A.initial_alpha = P.initial_alpha;
     memcpy(A.clear, P.clear_color, sizeof A.clear);
@@ -1859,12 +1909,23 @@ int vkrt_mark_elapsed(VkrtContext* c, int from, int to, float* ms) {
     return VKRT_OK;
 }
 
+int vkrt_set_occupancy_brick(VkrtContext* c, int edge) {
+    if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
+    int bs = -1;
+    if (edge != 0) {
+        for (bs = 0; bs <= 5 && (1 << bs) != edge; ++bs) {}
+        if (bs > 5) return fail(VKRT_ERR_INVALID, "occupancy brick edge must be 0 (automatic), 1, 2, 4, 8, 16 or 32");
+    }
+    c->obs_request = bs;
+    return VKRT_OK;
+}
+
 int vkrt_volume_info(VkrtContext* c, int* kind, int* dtype, int dims[3], uint64_t* bricks_total, uint64_t* bricks_occupied) {
     if (!c) return fail(VKRT_ERR_INVALID, "ctx is NULL");
     if (kind) *kind = c->kind;
     if (dtype) *dtype = c->dtype;
     if (dims) { dims[0] = c->nx; dims[1] = c->ny; dims[2] = c->nz; }
-    const size_t cells = (size_t)c->nbx * c->nby * c->nbz;
+    const size_t cells = c->windowed ? (size_t)c->cell_n[0] * c->cell_n[1] * c->cell_n[2] : (size_t)c->obx * c->oby * c->obz;  // the grid c->dist covers
     if (bricks_total) *bricks_total = cells;
     if (bricks_occupied) {
         *bricks_occupied = 0;

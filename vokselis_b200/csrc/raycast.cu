@@ -107,7 +107,19 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
         : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
     return r;
 }
+// the same, rounded towards -infinity (FFMA2.RM)
+__device__ __forceinline__ float2 fma2_rm(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rm.f32x2 rd, ra, rb, rc; "
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
 __device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
+// 1.5 * 2^23: RD(x + kMagic) = kMagic + floor(x) for |x| < 2^22, an integer-valued float whose bit pattern is
+// 0x4B400000 + floor(x) (two's complement for negative floors) — floor and float-to-int on the FMA pipe, no F2I / I2F
+constexpr float kMagic = 12582912.0f;
 
 // a + f*(b - a), every operation spelled out (see the determinism note in vkrt_device.cuh). Order: z, then y, then x —
 // the order in which the pre-gathered quads pair up for the packed form; every layout uses it, so all layouts
@@ -198,19 +210,19 @@ struct LeapRay {
 // so after n <= s steps the model is off by at most s * drift_per_step steps (+ a fixed 0.02). The result is
 // >= 1: the current sample's emptiness was read from its exact index.
 //
-// Written around the brick centre 8b + 4 (b = brick coordinate, already computed for the distance lookup): the exit
+// Written around the brick centre 8b + 4 (b = brick coordinate as a float, already computed for the distance lookup): the exit
 // plane on an axis is centre + sg * R with R = 8d - 4 - eps, so the distance to it is w = 8b + (sg*R + (4 - q)) and
 // s = w * rq. (Not u*rq + R*|rq|: for a ray almost parallel to a face rq is huge and that sum cancels.) x and y go
 // through the packed FADD2 / FFMA2 / FMUL2: 11 floating-point instructions for the three axes. In M1 the region is
 // also clipped to the grid when a partial last brick sticks out of it (A.leap_clip; clamp-to-edge sampling: outside is
 // NOT empty; the distance field's border is "occupied", so whole bricks never stick out).
 template <int MODE>
-__device__ __forceinline__ int leap_count(const RenderArgs& A, const LeapRay& L, uint32_t d, int bx, int by, int bz, float2 qxy, float qz) {
-    const float R = fmaf(8.0f, (float)d, A.leap_r0);  // 8d - (4 + eps)
-    const float2 hxy = fma2(make_float2(L.sgx, L.sgy), dup2(R), add2(make_float2(-qxy.x, -qxy.y), dup2(4.0f)));
-    const float hz = fmaf(L.sgz, R, __fsub_rn(4.0f, qz));
-    const float2 wxy = fma2(dup2(8.0f), make_float2((float)bx, (float)by), hxy);
-    const float wz = fmaf(8.0f, (float)bz, hz);
+__device__ __forceinline__ int leap_count(const RenderArgs& A, const LeapRay& L, uint32_t d, float2 bxy, float bz, float2 qxy, float qz) {
+    const float R = fmaf(A.brick, (float)d, A.leap_r0);  // B d - (B / 2 + eps)
+    const float2 hxy = fma2(make_float2(L.sgx, L.sgy), dup2(R), add2(make_float2(-qxy.x, -qxy.y), dup2(A.half_brick)));
+    const float hz = fmaf(L.sgz, R, __fsub_rn(A.half_brick, qz));
+    const float2 wxy = fma2(dup2(A.brick), bxy, hxy);
+    const float wz = fmaf(A.brick, bz, hz);
     const float2 sxy = mul2(wxy, make_float2(L.rqx, L.rqy));
     float sx = sxy.x, sy = sxy.y, sz = __fmul_rn(wz, L.rqz);
     if (MODE == VKRT_MODE_M1 && A.leap_clip) {  // uniform; only grids whose dims are not multiples of 8
@@ -224,7 +236,10 @@ __device__ __forceinline__ int leap_count(const RenderArgs& A, const LeapRay& L,
 }
 
 template <int MODE, int LAYOUT, int DTYPE, bool SKIP, bool DBG>
-__global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VKRT_LAYOUT_LINEAR ? 12 : 8)) raycast_kernel(const __grid_constant__ RenderArgs A) {
+#ifndef VKRT_M1_BLOCKS
+#define VKRT_M1_BLOCKS 12
+#endif
+__global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VKRT_LAYOUT_LINEAR ? VKRT_M1_BLOCKS : 8)) raycast_kernel(const __grid_constant__ RenderArgs A) {
     // ---- which pixel -------------------------------------------------------------------------
     const uint32_t gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y * blockDim.y + threadIdx.y;
     float offx = 0.0f, offy = 0.0f;
@@ -289,6 +304,11 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
             drift_per_step = (t1 * 5.9604645e-08f) / dt * 2.0f;  // x2 safety
             L.keep = 1.0f - drift_per_step;
         }
+        // The ray's octant selects its directional distance field (RenderArgs::dist); the signs are the ones the leap
+        // length model uses. M1 folds the table into the z brick coordinate (kMagic + octant * slabs per table + bz).
+        const uint32_t oct = SKIP ? ((L.sgx > 0.0f ? 1u : 0u) | (L.sgy > 0.0f ? 2u : 0u) | (L.sgz > 0.0f ? 4u : 0u)) : 0u;
+        const float magic_z = fmaf((float)oct, A.dsz_f, kMagic);
+        const uint32_t oct_off = oct * A.dist_tab;
         // (Two traversal restructurings were measured and rejected on B200. While-while — every lane first
         // advances to its next non-empty sample on its own, then the warp shades together: 1.9x slower,
         // profiles/r01_whilewhile_ab.md. Warp-uniform leaps — leap only when every live lane sits in empty
@@ -351,16 +371,24 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
                 // advances — landing on exactly the floats the reference's `t = t + dt` visits. n = how
                 // many consecutive samples (this one included) provably stay inside the empty region.
                 int n = 0;
-                if (!inb) {
-                    n = MODE == VKRT_MODE_M0 ? 1 : 0;
-                } else {
-                    const int bx = ix >> 3, by = iy >> 3, bz = iz >> 3;
-                    uint32_t cell = ((uint32_t)bz * A.dsy + (uint32_t)by) * A.dsx + (uint32_t)bx;
-                    // M1: ix == nx (p rounded onto the box face) lands on the pad layer, a slightly negative wrapped index on
-                    // the pad of the previous row / slab or past the end: all "occupied", i.e. the sample is evaluated
-                    if (MODE == VKRT_MODE_M1) cell = min(cell, A.dist_last);
+                if (MODE == VKRT_MODE_M1) {
+                    // brick coordinates floor(q / 8) as magic floats (FFMA.RM): their bit patterns index the padded tables
+                    // directly. q == N (p rounded onto the box face) lands on the pad layer, a slightly negative q on the
+                    // pad of the previous row / slab / table or past the end (clamped): all "occupied", i.e. the sample is
+                    // evaluated. (floor, not the truncation of the voxel index: differs for -1 < q < 0 only, towards the pad)
+                    const float2 bxy = fma2_rm(qxy, dup2(A.inv_brick), dup2(kMagic));
+                    const float bzm = __fmaf_rd(qz, A.inv_brick, magic_z);
+                    uint32_t cell = (__float_as_uint(bzm) * A.dsy + __float_as_uint(bxy.y)) * A.dsx + __float_as_uint(bxy.x) - A.dist_bias;
+                    cell = min(cell, A.dist_last);
                     const uint32_t d = __ldg(A.dist + cell);
-                    if (d != 0u) n = leap_count<MODE>(A, L, d, bx, by, bz, qxy, qz);
+                    if (d != 0u) n = leap_count<MODE>(A, L, d, add2(bxy, dup2(-kMagic)), __fsub_rn(bzm, magic_z), qxy, qz);
+                } else if (!inb) {
+                    n = 1;
+                } else {
+                    const int bx = ix >> A.obs, by = iy >> A.obs, bz = iz >> A.obs;
+                    const uint32_t cell = ((uint32_t)bz * A.dsy + (uint32_t)by) * A.dsx + (uint32_t)bx + oct_off;
+                    const uint32_t d = __ldg(A.dist + cell);
+                    if (d != 0u) n = leap_count<MODE>(A, L, d, make_float2((float)bx, (float)by), (float)bz, qxy, qz);
                 }
                 if (n > 0) {
                     if (DBG) {

@@ -22,18 +22,25 @@ struct RenderArgs {
     // packed addition is therefore written fma(m, one, e) = RN(m * 1 + e) = RN(m + e): exact, and not fusable.
     float one;
     int nx, ny, nz;
-    int nbx;              // 8^3-voxel bricks per axis (occupancy grid and bricked layout)
-    // per brick: 0 = occupied, d = bricks within Chebyshev radius d-1 are all empty. Row / slab strides dsx, dsy; M0: the
-    // field itself (nbx, nby); M1: the copy padded by one occupied layer on the high side of every axis (nbx + 1, nby + 1),
-    // indexed without a bounds test and clamped to dist_last (memory safety; the host only enables skipping for cameras
-    // whose ray origins are near enough for the voxel index to stay within the pad, see tame_camera in api.cu)
+    int nbx;              // 8^3-voxel bricks per axis of the BRICKED layout (M0)
+    // Directional distance fields over the bricks, one table per ray octant (bit 0 / 1 / 2 = travelling towards +x / +y / +z),
+    // back to back, dist_tab cells each: 0 = occupied, d = the d^3 bricks [b, b + s d) in the direction of travel are all
+    // empty (volume.cu octant_step_kernel). Row / slab strides dsx, dsy. M0: nbx, nby, indexed after the bounds test; M1:
+    // every table padded by one occupied layer on the high side of every axis (nbx + 1, nby + 1, dsz_f = nbz + 1), indexed
+    // without a bounds test and clamped to dist_last (memory safety; the host only enables skipping for cameras whose ray
+    // origins are near enough for the voxel index to stay within the pad, see tame_camera in api.cu). dist_bias: see api.cu.
     const uint8_t* dist;
+    cudaTextureObject_t tex_d;
     int nby, nbz;
-    uint32_t dsx, dsy, dist_last;
+    uint32_t dsx, dsy, dist_last, dist_tab, dist_bias;
+    float dsz_f;
+    // the occupancy brick: edge B = 2^obs voxels (chosen per volume by api.cu occupancy_brick_shift), as floats B, B / 2, 1 / B
+    int obs;
+    float brick, half_brick, inv_brick;
     cudaTextureObject_t tex_a, tex_b;
     float alpha_threshold;
-    float leap_r0;        // -(4 + leap_eps): exit-plane offset from the brick centre is 8 d + leap_r0
-    int leap_clip;        // M1: some dim is not a multiple of 8, the partial last brick sticks out: clip regions to the grid
+    float leap_r0;        // -(B / 2 + leap_eps): exit-plane offset from the brick centre is B d + leap_r0
+    int leap_clip;        // M1: some dim is not a multiple of B, the partial last brick sticks out: clip regions to the grid
     float leap_eps;       // safety shrink of leap regions, in voxels
     float leap_lim[3];    // M1: dims - leap_eps (the clip)
     float dt_scale, dt_floor, initial_alpha;
@@ -100,12 +107,17 @@ cudaError_t launch_raycast(const RenderArgs& A, int mode, int layout, int dtype,
 cudaError_t launch_interleave_bricked(const uint2* color, const uint2* normal, uint4* out, int nx, int ny, int nz,
                                       int nbx, int nby, int nbz, cudaStream_t s);
 // dist: one byte per brick, built in two steps: occupancy (0 / 255) then the Chebyshev distance transform
-cudaError_t launch_occupancy_m0(const uint2* color, const uint2* normal, int nx, int ny, int nz, int nbx, int nby, int nbz, uint8_t* dist,
+// (nbx, nby, nbz = the occupancy grid: bricks of 2^bs voxels per edge)
+cudaError_t launch_occupancy_m0(const uint2* color, const uint2* normal, int nx, int ny, int nz, int nbx, int nby, int nbz, int bs, uint8_t* dist,
                                 cudaStream_t s);
-cudaError_t launch_occupancy_m1(const void* scalar, int dtype, int nx, int ny, int nz, int nbx, int nby, int nbz,
+cudaError_t launch_occupancy_m1(const void* scalar, int dtype, int nx, int ny, int nz, int nbx, int nby, int nbz, int bs,
                                 uint8_t* dist, cudaStream_t s);
-cudaError_t launch_occupied_bounds(const uint8_t* dist, int nbx, int nby, int nbz, int* d_out6, cudaStream_t s);
-cudaError_t launch_pad_dist(const uint8_t* dist, uint8_t* out, int nbx, int nby, int nbz, cudaStream_t s);
+// d_out7: min x, y, z, max x, y, z of the occupied cells and the number of empty cells
+cudaError_t launch_occupied_bounds(const uint8_t* dist, int nbx, int nby, int nbz, int* d_out7, cudaStream_t s);
+cudaError_t launch_pad_dist(const uint8_t* dist, uint8_t* out, int nbx, int nby, int nbz, int tables, cudaStream_t s);
+// the 8 directional distance fields of the ray octants (volume.cu), back to back
+cudaError_t launch_octant_distance(const uint8_t* occ, uint8_t* oct, uint8_t* scratch, int nbx, int nby, int nbz, int border, int max_d,
+                                   cudaStream_t s);
 cudaError_t launch_distance_transform(uint8_t* dist, uint8_t* scratch, int nbx, int nby, int nbz, int border, int max_d, cudaStream_t s);
 cudaError_t launch_pregather_quads(const void* vol, int dtype, void* out_texels, int nx, int ny, int nz, cudaStream_t s);
 cudaError_t launch_generate_xor(uint2* color, uint2* normal, int n, float time, int which, cudaStream_t s);

@@ -36,16 +36,17 @@ __global__ void __launch_bounds__(256) interleave_bricked_kernel(const uint2* __
     out[o] = v;
 }
 
-// one warp per brick
+// one warp per brick (edge 2^bs voxels)
 __global__ void __launch_bounds__(256) occupancy_m0_kernel(const uint2* __restrict__ color, const uint2* __restrict__ normal, int nx, int ny, int nz, int nbx, int nby,
-                                                           int nbz, uint8_t* __restrict__ dist) {
-    const uint32_t cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                                                           int nbz, int bs, uint8_t* __restrict__ dist) {
+    const size_t cell = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t lane = threadIdx.x & 31u;
-    if (cell >= (uint32_t)nbx * nby * nbz) return;
-    const int bx = (int)(cell % (uint32_t)nbx), by = (int)((cell / (uint32_t)nbx) % (uint32_t)nby), bz = (int)(cell / ((uint32_t)nbx * nby));
+    if (cell >= (size_t)nbx * nby * nbz) return;
+    const int bx = (int)(cell % (size_t)nbx), by = (int)((cell / (size_t)nbx) % (size_t)nby), bz = (int)(cell / ((size_t)nbx * nby));
+    const int m = (1 << bs) - 1;
     bool any = false;
-    for (int k = (int)lane; k < 512; k += 32) {
-        const int ix = bx * 8 + (k & 7), iy = by * 8 + ((k >> 3) & 7), iz = bz * 8 + (k >> 6);
+    for (int k = (int)lane; k < (1 << (3 * bs)); k += 32) {
+        const int ix = (bx << bs) + (k & m), iy = (by << bs) + ((k >> bs) & m), iz = (bz << bs) + (k >> (2 * bs));
         if (ix < nx && iy < ny && iz < nz) {
             const size_t i = ((size_t)iz * ny + iy) * nx + ix;
             any = any || !m0_texel_skippable(__ldg(color + i), __ldg(normal + i));  // alpha through the very function the march uses
@@ -62,19 +63,20 @@ template <> __device__ __forceinline__ float load_scalar<VKRT_F16>(const void* p
 }
 template <> __device__ __forceinline__ float load_scalar<VKRT_F32>(const void* p, size_t i) { return __ldg((const float*)p + i); }
 
-// A sample whose index floor((p+1)*N/2) lies in brick b touches voxels [8b-1, 8b+8] per axis
+// A sample whose index floor((p+1)*N/2) lies in brick b (edge B = 2^bs voxels) touches voxels [B b - 1, B b + B] per axis
 // (clamped to the grid). The brick is empty iff all of them are <= M1_EMPTY_MAX.
 #define M1_EMPTY_MAX 0.0999999f
 template <int DTYPE>
-__global__ void __launch_bounds__(256) occupancy_m1_kernel(const void* __restrict__ vol, int nx, int ny, int nz, int nbx, int nby, int nbz,
+__global__ void __launch_bounds__(256) occupancy_m1_kernel(const void* __restrict__ vol, int nx, int ny, int nz, int nbx, int nby, int nbz, int bs,
                                                            uint8_t* __restrict__ dist) {
-    const uint32_t cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const size_t cell = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t lane = threadIdx.x & 31u;
-    if (cell >= (uint32_t)nbx * nby * nbz) return;
-    const int bx = (int)(cell % (uint32_t)nbx), by = (int)((cell / (uint32_t)nbx) % (uint32_t)nby), bz = (int)(cell / ((uint32_t)nbx * nby));
-    const int x0 = max(bx * 8 - 1, 0), x1 = min(bx * 8 + 8, nx - 1);
-    const int y0 = max(by * 8 - 1, 0), y1 = min(by * 8 + 8, ny - 1);
-    const int z0 = max(bz * 8 - 1, 0), z1 = min(bz * 8 + 8, nz - 1);
+    if (cell >= (size_t)nbx * nby * nbz) return;
+    const int bx = (int)(cell % (size_t)nbx), by = (int)((cell / (size_t)nbx) % (size_t)nby), bz = (int)(cell / ((size_t)nbx * nby));
+    const int B = 1 << bs;
+    const int x0 = max(bx * B - 1, 0), x1 = min(bx * B + B, nx - 1);
+    const int y0 = max(by * B - 1, 0), y1 = min(by * B + B, ny - 1);
+    const int z0 = max(bz * B - 1, 0), z1 = min(bz * B + B, nz - 1);
     const int wy = y1 - y0 + 1, wz = z1 - z0 + 1;
     bool any = false;
     for (int r = (int)lane; r < wy * wz; r += 32) {
@@ -112,11 +114,54 @@ __global__ void __launch_bounds__(256) distance_step_kernel(const uint8_t* __res
     out[c] = (uint8_t)d;
 }
 
+// Directional distance fields, one per ray octant k (bit 0 / 1 / 2 set = the ray travels towards +x / +y / +z): table k holds,
+// per brick b, the largest d such that the d^3 bricks [b, b + s d) (s = the octant's sign on each axis) are all empty; 0 =
+// occupied. A ray only ever moves forward, so the cube BEHIND a sample (which the isotropic Chebyshev distance also
+// requires to be empty) does not limit its leap: on the bench volume the mean distance over empty bricks grows from 1.6 to
+// 2.7 bricks and a ray needs half as many leaps (bench/leap_model.py). The forward extent of the region is the same
+// 8 d - 4 voxels from the brick centre as before, so the kernel's leap length model is unchanged.
+// One relaxation step: d = min(d, 1 + min over the 7 forward neighbours); tables are initialised with the occupancy
+// (0 / 255). `in` / `out` hold the 8 tables back to back.
+__global__ void __launch_bounds__(256) octant_step_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int nbx, int nby,
+                                                          int nbz, int border, int cap) {
+    const size_t cells = (size_t)nbx * nby * nbz;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= 8 * cells) return;
+    const int k = (int)(g / cells);
+    const size_t c = g - (size_t)k * cells;
+    const uint8_t* tab = in + (size_t)k * cells;
+    int d = tab[c];
+    if (d != 0) {
+        const int bx = (int)(c % (size_t)nbx), by = (int)((c / (size_t)nbx) % (size_t)nby), bz = (int)(c / ((size_t)nbx * nby));
+        const int sx = (k & 1) ? 1 : -1, sy = (k & 2) ? 1 : -1, sz = (k & 4) ? 1 : -1;
+        int m = 255;
+        for (int j = 1; j < 8; ++j) {
+            const int x = bx + ((j & 1) ? sx : 0), y = by + ((j & 2) ? sy : 0), z = bz + ((j & 4) ? sz : 0);
+            const int v = (x < 0 || y < 0 || z < 0 || x >= nbx || y >= nby || z >= nbz) ? border : (int)tab[((size_t)z * nby + y) * nbx + x];
+            m = min(m, v);
+        }
+        d = min(min(d, m + 1), cap);
+    }
+    out[g] = (uint8_t)d;
+}
+
+__global__ void __launch_bounds__(256) replicate8_kernel(const uint8_t* __restrict__ occ, uint8_t* __restrict__ out, size_t cells) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < 8 * cells) out[g] = occ[g % cells];
+}
+
 // Bounding box, in bricks, of the occupied cells (dist == 0) of the finished distance field:
-// out = {min x, min y, min z, max x, max y, max z}, initialised to {INT_MAX x3, -1 x3} by the launcher.
+// out = {min x, min y, min z, max x, max y, max z, number of EMPTY cells (saturating at INT_MAX)}, initialised to
+// {INT_MAX x3, -1 x3, 0} by the launcher.
 __global__ void __launch_bounds__(256) occupied_bounds_kernel(const uint8_t* __restrict__ dist, int nbx, int nby, int nbz, int* __restrict__ out) {
     const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool occ = c < (size_t)nbx * nby * nbz && dist[c] == 0;
+    const bool in = c < (size_t)nbx * nby * nbz;
+    const bool occ = in && dist[c] == 0;
+    const int n_empty = __popc(__ballot_sync(0xffffffffu, in && !occ));
+    if ((threadIdx.x & 31u) == 0u && n_empty) {
+        const int old = atomicAdd(out + 6, n_empty);
+        if (old < 0 || old + n_empty < 0) atomicExch(out + 6, 0x7fffffff);
+    }
     const int bx = (int)(c % (size_t)nbx), by = (int)((c / (size_t)nbx) % (size_t)nby), bz = (int)(c / ((size_t)nbx * nby));
     const int big = 0x7fffffff;
     const int lx = __reduce_min_sync(0xffffffffu, occ ? bx : big), ly = __reduce_min_sync(0xffffffffu, occ ? by : big);
@@ -525,9 +570,10 @@ cudaError_t launch_interleave_bricked(const uint2* color, const uint2* normal, u
     return cudaGetLastError();
 }
 
-cudaError_t launch_occupancy_m0(const uint2* color, const uint2* normal, int nx, int ny, int nz, int nbx, int nby, int nbz, uint8_t* dist, cudaStream_t s) {
+cudaError_t launch_occupancy_m0(const uint2* color, const uint2* normal, int nx, int ny, int nz, int nbx, int nby, int nbz, int bs, uint8_t* dist,
+                                cudaStream_t s) {
     const size_t cells = (size_t)nbx * nby * nbz;
-    occupancy_m0_kernel<<<(unsigned)((cells + 7) / 8), 256, 0, s>>>(color, normal, nx, ny, nz, nbx, nby, nbz, dist);
+    occupancy_m0_kernel<<<(unsigned)((cells + 7) / 8), 256, 0, s>>>(color, normal, nx, ny, nz, nbx, nby, nbz, bs, dist);
     return cudaGetLastError();
 }
 
@@ -547,39 +593,60 @@ cudaError_t launch_distance_transform(uint8_t* dist, uint8_t* scratch, int nbx, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_occupied_bounds(const uint8_t* dist, int nbx, int nby, int nbz, int* d_out6, cudaStream_t s) {
-    static const int init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1};
-    cudaError_t e = cudaMemcpyAsync(d_out6, init, sizeof init, cudaMemcpyHostToDevice, s);
+// occ: occupancy (0 / 255), cells bytes. oct, scratch: 8 * cells bytes each. After max_d relaxation steps every table holds
+// min(true directional distance, max_d); the result is left in `oct`.
+cudaError_t launch_octant_distance(const uint8_t* occ, uint8_t* oct, uint8_t* scratch, int nbx, int nby, int nbz, int border, int max_d,
+                                   cudaStream_t s) {
+    const size_t cells = (size_t)nbx * nby * nbz;
+    const unsigned blocks = (unsigned)((8 * cells + 255) / 256);
+    replicate8_kernel<<<blocks, 256, 0, s>>>(occ, oct, cells);
+    uint8_t *a = oct, *b = scratch;
+    for (int i = 0; i < max_d; ++i) {
+        octant_step_kernel<<<blocks, 256, 0, s>>>(a, b, nbx, nby, nbz, border, max_d);
+        uint8_t* t = a; a = b; b = t;
+    }
+    if (a != oct) {
+        cudaError_t e = cudaMemcpyAsync(oct, a, 8 * cells, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_occupied_bounds(const uint8_t* dist, int nbx, int nby, int nbz, int* d_out7, cudaStream_t s) {
+    static const int init[7] = {0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1, 0};
+    cudaError_t e = cudaMemcpyAsync(d_out7, init, sizeof init, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return e;
     const size_t cells = (size_t)nbx * nby * nbz;
-    occupied_bounds_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(dist, nbx, nby, nbz, d_out6);
+    occupied_bounds_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(dist, nbx, nby, nbz, d_out7);
     return cudaGetLastError();
 }
 
 // The distance field with one layer of "occupied" cells appended on the high side of every axis (M1, see RenderArgs::dist):
 // a sample whose voxel index is one past the grid (q == N, reached when p rounds to the box face) or slightly negative in a
 // wrapped index lands on a pad cell and is simply evaluated, so the march needs no per-sample bounds test.
-__global__ void __launch_bounds__(256) pad_dist_kernel(const uint8_t* __restrict__ dist, uint8_t* __restrict__ out, int nbx, int nby, int nbz) {
-    const size_t total = (size_t)(nbx + 1) * (nby + 1) * (nbz + 1);
-    const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= total) return;
+__global__ void __launch_bounds__(256) pad_dist_kernel(const uint8_t* __restrict__ dist, uint8_t* __restrict__ out, int nbx, int nby, int nbz, int tables) {
+    const size_t padded = (size_t)(nbx + 1) * (nby + 1) * (nbz + 1), cells = (size_t)nbx * nby * nbz;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= padded * (size_t)tables) return;
+    const size_t k = g / padded, o = g - k * padded;
     const int bx = (int)(o % (size_t)(nbx + 1)), by = (int)((o / (size_t)(nbx + 1)) % (size_t)(nby + 1)), bz = (int)(o / ((size_t)(nbx + 1) * (nby + 1)));
-    out[o] = (bx < nbx && by < nby && bz < nbz) ? dist[((size_t)bz * nby + by) * nbx + bx] : (uint8_t)0;
+    out[g] = (bx < nbx && by < nby && bz < nbz) ? dist[k * cells + ((size_t)bz * nby + by) * nbx + bx] : (uint8_t)0;
 }
-cudaError_t launch_pad_dist(const uint8_t* dist, uint8_t* out, int nbx, int nby, int nbz, cudaStream_t s) {
-    const size_t total = (size_t)(nbx + 1) * (nby + 1) * (nbz + 1);
-    pad_dist_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dist, out, nbx, nby, nbz);
+// `tables` fields back to back on both sides
+cudaError_t launch_pad_dist(const uint8_t* dist, uint8_t* out, int nbx, int nby, int nbz, int tables, cudaStream_t s) {
+    const size_t total = (size_t)(nbx + 1) * (nby + 1) * (nbz + 1) * (size_t)tables;
+    pad_dist_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dist, out, nbx, nby, nbz, tables);
     return cudaGetLastError();
 }
 
-cudaError_t launch_occupancy_m1(const void* scalar, int dtype, int nx, int ny, int nz, int nbx, int nby, int nbz, uint8_t* dist,
+cudaError_t launch_occupancy_m1(const void* scalar, int dtype, int nx, int ny, int nz, int nbx, int nby, int nbz, int bs, uint8_t* dist,
                                 cudaStream_t s) {
     const size_t cells = (size_t)nbx * nby * nbz;
     const unsigned blocks = (unsigned)((cells + 7) / 8);
     switch (dtype) {
-        case VKRT_U8: occupancy_m1_kernel<VKRT_U8><<<blocks, 256, 0, s>>>(scalar, nx, ny, nz, nbx, nby, nbz, dist); break;
-        case VKRT_F16: occupancy_m1_kernel<VKRT_F16><<<blocks, 256, 0, s>>>(scalar, nx, ny, nz, nbx, nby, nbz, dist); break;
-        case VKRT_F32: occupancy_m1_kernel<VKRT_F32><<<blocks, 256, 0, s>>>(scalar, nx, ny, nz, nbx, nby, nbz, dist); break;
+        case VKRT_U8: occupancy_m1_kernel<VKRT_U8><<<blocks, 256, 0, s>>>(scalar, nx, ny, nz, nbx, nby, nbz, bs, dist); break;
+        case VKRT_F16: occupancy_m1_kernel<VKRT_F16><<<blocks, 256, 0, s>>>(scalar, nx, ny, nz, nbx, nby, nbz, bs, dist); break;
+        case VKRT_F32: occupancy_m1_kernel<VKRT_F32><<<blocks, 256, 0, s>>>(scalar, nx, ny, nz, nbx, nby, nbz, bs, dist); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

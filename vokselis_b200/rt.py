@@ -29,7 +29,7 @@ EXPORTS = [
     "vkrt_render_batch", "vkrt_batch_frame_device_ptr", "vkrt_readback_batch", "vkrt_frames_host", "vkrt_present", "vkrt_present_scaled", "vkrt_readback", "vkrt_readback_rgba8", "vkrt_readback_rgba8_async",
     "vkrt_readback_aux", "vkrt_sync", "vkrt_frame_host", "vkrt_frame_host_async", "vkrt_frame_host_wait",
     "vkrt_frame_host_slot_ptr", "vkrt_frame_device_ptr", "vkrt_frame_rgba8_device_ptr", "vkrt_stream", "vkrt_stats",
-    "vkrt_reset_stats", "vkrt_timing_enable", "vkrt_timing_read", "vkrt_flush_l2", "vkrt_volume_info", "vkrt_camera_uniform", "vkrt_dispatch_optimal",
+    "vkrt_reset_stats", "vkrt_timing_enable", "vkrt_timing_read", "vkrt_flush_l2", "vkrt_set_occupancy_brick", "vkrt_volume_info", "vkrt_camera_uniform", "vkrt_dispatch_optimal",
     "vkrt_sortfirst_create_root", "vkrt_sortfirst_join", "vkrt_sortfirst_leave", "vkrt_sortfirst_partition", "vkrt_sortfirst_render", "vkrt_sortfirst_render_batch", "vkrt_sortfirst_render_tiles_batch",
     "vkrt_sortfirst_consume", "vkrt_sortfirst_timeouts", "vkrt_sortfirst_wait", "vkrt_mark", "vkrt_mark_elapsed",
     "vkrt_alloc_host", "vkrt_free_host", "vkrt_host_register", "vkrt_host_unregister", "vkrt_generate_synthetic", "vkrt_download_scalar", "vkrt_scalar_to_rgba16f",
@@ -99,6 +99,7 @@ def lib() -> C.CDLL:
         "vkrt_timing_enable": (ci, [vp, ci]),
         "vkrt_timing_read": (ci, [vp, vp, ci]),
         "vkrt_flush_l2": (ci, [vp]),
+        "vkrt_set_occupancy_brick": (ci, [vp, ci]),
         "vkrt_volume_info": (ci, [vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci * 3), C.POINTER(C.c_uint64),
                                   C.POINTER(C.c_uint64)]),
         "vkrt_camera_uniform": (ci, [cf, cf, cf, C.POINTER(cf * 3), cf, C.POINTER(CameraUniform)]),
@@ -341,6 +342,10 @@ class Context:
         normal = np.empty((nz, ny, nx, 4), np.uint16)
         _check(lib().vkrt_download_rgba16f(self._h, _vp(color), _vp(normal)))
         return color, normal
+
+    def set_occupancy_brick(self, edge: int = 0):
+        """Brick edge (voxels) of the occupancy grid for volumes uploaded after this call; 0 = automatic. Frames do not depend on it."""
+        _check(lib().vkrt_set_occupancy_brick(self._h, int(edge)))
 
     def volume_info(self) -> dict:
         kind, dtype, dims = C.c_int(), C.c_int(), (C.c_int * 3)()

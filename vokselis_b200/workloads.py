@@ -57,7 +57,7 @@ def _gather_floats(value: float, dist, world: int) -> list[float]:
 
 def run_sortfirst_tiles(cid: int, rank: int, world: int, local: int, dist=None, frames: int = 24, warm: int = 4, tile: int = 120,
                         layout: int | None = None, res=(3840, 2160), edge: int | None = None, checks: bool = True, hbm_peak_gbs: float = 6650.0,
-                        batch: int = 1):
+                        batch: int = 1, brick: int = 0):
     """configs[2] / configs[3] on `world` GPUs (one process each). N = 1: `single` on one GPU. N > 1: every frame is cut
     into tile x tile pixel tiles dealt over the ranks (volume replicated), each rank renders its tiles locally and ships
     them into rank 0's frame over NVLink; rank 0 waits for each frame in order. Timing: CUDA events on RANK 0's stream
@@ -71,6 +71,7 @@ def run_sortfirst_tiles(cid: int, rank: int, world: int, local: int, dist=None, 
     layout = cfg["layout"] if layout is None else layout
     ctx = rt.Context(local, W, H)
     t0 = time.perf_counter()
+    ctx.set_occupancy_brick(brick)  # 0 = the library's choice
     ctx.generate_synthetic(cfg["kind"], cfg["dtype"], n, seed=cfg["seed"])
     ctx.sync()
     gen_s = time.perf_counter() - t0
