@@ -627,6 +627,7 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
 
     RenderArgs A{};
     A.W = c->W; A.H = c->H;
+    A.aspect_hw = (float)c->H / (float)c->W;
     A.n_frames = n_frames;
     for (int f = 0; f < n_frames; ++f) {
         memcpy(A.inv[f], cam[f].inv_proj, sizeof A.inv[f]);

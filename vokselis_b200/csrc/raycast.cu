@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
             may_hit = fminf(fminf(fminf(d0, d1), fminf(d2, d3)), fminf(d4, d5)) >= 0.0f;
         }
         if (may_hit) {
-            gen_ray(A.inv[fr], (float)gx, (float)gy, offx, offy, (float)A.W, (float)A.H, eye, dir);
+            gen_ray(A.inv[fr], (float)gx, (float)gy, offx, offy, (float)A.W, (float)A.H, A.aspect_hw, eye, dir);
             intersect_box(eye, dir, t0, t1, inv_dir);
         }
     }
@@ -296,12 +296,14 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
         float drift_per_step = 0.0f;
         if (SKIP) {
             const float dqx = dir.x * A.hx * dt, dqy = dir.y * A.hy * dt, dqz = dir.z * A.hz * dt;  // voxels per step
-            L.rqx = fabsf(dqx) > 1e-12f ? 1.0f / dqx : 1e30f;
-            L.rqy = fabsf(dqy) > 1e-12f ? 1.0f / dqy : 1e30f;
-            L.rqz = fabsf(dqz) > 1e-12f ? 1.0f / dqz : 1e30f;
+            // (approximate reciprocals, MUFU.RCP: the leap length model carries a margin of 0.02 steps + the drift, a relative
+            // error of 2^-22 in rq moves a 4095-step leap by 0.001)
+            L.rqx = fabsf(dqx) > 1e-12f ? __fdividef(1.0f, dqx) : 1e30f;
+            L.rqy = fabsf(dqy) > 1e-12f ? __fdividef(1.0f, dqy) : 1e30f;
+            L.rqz = fabsf(dqz) > 1e-12f ? __fdividef(1.0f, dqz) : 1e30f;
             L.sgx = copysignf(1.0f, L.rqx); L.sgy = copysignf(1.0f, L.rqy); L.sgz = copysignf(1.0f, L.rqz);
             // one replayed addition moves t off the exact line by <= ulp(t)/2 <= t1 * 2^-24; in units of a step:
-            drift_per_step = (t1 * 5.9604645e-08f) / dt * 2.0f;  // x2 safety
+            drift_per_step = __fdividef(t1 * 5.9604645e-08f, dt) * 2.0f;  // x2 safety
             L.keep = 1.0f - drift_per_step;
         }
         // The ray's octant selects its directional distance field (RenderArgs::dist); the signs are the ones the leap

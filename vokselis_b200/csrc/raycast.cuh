@@ -53,6 +53,7 @@ struct RenderArgs {
     float hull[kMaxBatch][kHullEdges][3];  // per frame: inward half-planes a*cx + b*cy + c >= 0 of the box's silhouette (api.cu cull_rect)
     int n_frames;
     int W, H;
+    float aspect_hw;  // (float)H / (float)W, IEEE: raycast_compute.wgsl:105, computed once on the host
     // tiles: n_tiles == 0 -> `single`; else grid.z indexes `offsets` (device memory)
     const VkrtOffset* offsets;
     int n_tiles, tile_size;

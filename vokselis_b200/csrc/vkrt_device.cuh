@@ -31,11 +31,11 @@ __device__ __forceinline__ float xrow(const float* m, int r, float x, float y, f
     return xadd(xadd(xadd(xmul(m[r], x), xmul(m[4 + r], y)), xmul(m[8 + r], z)), xmul(m[12 + r], w));
 }
 
-// shaders/raycast_compute.wgsl:102-116 — ray generation (`render`). gx, gy = global_invocation_id.
-__device__ __forceinline__ void gen_ray(const float* inv, float gx, float gy, float offx, float offy, float W, float H,
+// shaders/raycast_compute.wgsl:102-116 — ray generation (`render`). gx, gy = global_invocation_id. aspect_ratio = the
+// IEEE quotient H / W (:105), the same for every pixel: the raycast kernel takes it from the host (RenderArgs::aspect_hw).
+__device__ __forceinline__ void gen_ray(const float* inv, float gx, float gy, float offx, float offy, float W, float H, float aspect_ratio,
                                         f3& eye, f3& dir) {
     const float cx = xadd(gx, offx), cy = xadd(gy, offy);
-    const float aspect_ratio = xdiv(H, W);
     const float sx = xsub(xdiv(xmul(2.0f, cx), W), 1.0f);
     float sy = xsub(xdiv(xmul(2.0f, cy), H), 1.0f);
     sy = xmul(sy, -aspect_ratio);
@@ -49,6 +49,10 @@ __device__ __forceinline__ void gen_ray(const float* inv, float gx, float gy, fl
     f3 d = {xsub(xdiv(vt.x, vtw), eye.x), xsub(xdiv(vt.y, vtw), eye.y), xsub(xdiv(vt.z, vtw), eye.z)};
     const float len = __fsqrt_rn(xdot3(d, d));
     dir.x = xdiv(d.x, len); dir.y = xdiv(d.y, len); dir.z = xdiv(d.z, len);
+}
+
+__device__ __forceinline__ void gen_ray(const float* inv, float gx, float gy, float offx, float offy, float W, float H, f3& eye, f3& dir) {
+    gen_ray(inv, gx, gy, offx, offy, W, H, xdiv(H, W), eye, dir);
 }
 
 // shaders/raycast_compute.wgsl:42-53 — slab test against [-1,1]^3 (fminf/fmaxf = WGSL min/max on NVIDIA).
@@ -75,12 +79,12 @@ __device__ __forceinline__ void slab_box(f3 o, f3 inv, const float* lo, const fl
     t1 = fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz)));
 }
 
-// shaders/raycast_compute.wgsl:65-68 — step length.
+// shaders/raycast_compute.wgsl:65-68 — step length: dt_scale * max(min_i 1 / (n_i |dir_i|), dt_floor). Correctly rounded
+// division is monotone, so the minimum of the three quotients IS the quotient by the largest divisor, bit for bit — one
+// IEEE division instead of three (fminf / fmaxf both drop a NaN operand; an axis with |dir_i| = 0 gives +inf either way).
 __device__ __forceinline__ float step_dt(f3 dir, float nx, float ny, float nz, float dt_scale, float dt_floor) {
-    const float dx = xdiv(1.0f, xmul(nx, fabsf(dir.x)));
-    const float dy = xdiv(1.0f, xmul(ny, fabsf(dir.y)));
-    const float dz = xdiv(1.0f, xmul(nz, fabsf(dir.z)));
-    return xmul(dt_scale, fmaxf(fminf(dx, fminf(dy, dz)), dt_floor));
+    const float a = fmaxf(xmul(nx, fabsf(dir.x)), fmaxf(xmul(ny, fabsf(dir.y)), xmul(nz, fabsf(dir.z))));
+    return xmul(dt_scale, fmaxf(xdiv(1.0f, a), dt_floor));
 }
 
 // Exact result of `n` repeated additions t = fl(t + dt) (round-to-nearest-even), without executing them
