@@ -1402,6 +1402,34 @@ int vkrt_sortfirst_partition(int width, int height, int tile_size, int rank, int
     return k;
 }
 
+namespace {
+// Sort-first tiles: the pixel rectangle of frame f of a push that can hold anything but the clear colour — the kernel's
+// own cull rectangle (cull_rect: ray coordinates gid + offset; a fractional offset stores up to one pixel to the left /
+// above, hence 2 pixels of margin), clamped to the frame, x0 even and x1 odd so that 16-byte stores stay aligned. The
+// peers ship only these pixels of their tiles; rank 0 writes the clear colour everywhere else (sf_fill_outside).
+void push_clip(const VkrtContext* c, const VkrtCameraUniform* cam, int f, PushClip& clip) {
+    float r[4];
+    int row;
+    cull_rect(cam->inv_proj, c->W, c->H, r, &row);
+    const double W1 = c->W - 1, H1 = c->H - 1;
+    int x0 = (int)std::max(0.0, std::min(W1 + 1.0, std::floor((double)r[0]) - 2.0)), x1 = (int)std::min(W1, std::max(-1.0, std::ceil((double)r[2]) + 2.0));
+    int y0 = (int)std::max(0.0, std::min(H1 + 1.0, std::floor((double)r[1]) - 2.0)), y1 = (int)std::min(H1, std::max(-1.0, std::ceil((double)r[3]) + 2.0));
+    x0 &= ~1;
+    if (!(x1 & 1) && x1 < c->W - 1) ++x1;
+    if (x0 > x1 || y0 > y1) { x0 = 0; y0 = 0; x1 = -1; y1 = -1; }  // the box is off screen: nothing to ship
+    clip.x0[f] = x0; clip.y0[f] = y0; clip.x1[f] = x1; clip.y1[f] = y1;
+}
+int sf_fill_outside(VkrtContext* c, uint2* frame, const PushClip& clip, int f, cudaStream_t s) {
+    const float* cc = c->params.clear_color;
+    const __half2 lo = __floats2half2_rn(cc[0], cc[1]), hi = __floats2half2_rn(cc[2], 1.0f);  // what the kernel stores for a miss
+    uint2 texel;
+    memcpy(&texel.x, &lo, 4);
+    memcpy(&texel.y, &hi, 4);
+    CK(launch_fill_outside(frame, c->W, c->H, clip.x0[f], clip.y0[f], clip.x1[f], clip.y1[f], texel, s));
+    return VKRT_OK;
+}
+}  // namespace
+
 int vkrt_sortfirst_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* un, const VkrtOffset* offsets, int n,
                           uint64_t frame_index) {
     if (!c || !c->sf_base) return fail(VKRT_ERR_INVALID, "context is not in a sort-first group");
@@ -1429,6 +1457,12 @@ int vkrt_sortfirst_render(VkrtContext* c, const VkrtCameraUniform* cam, const Vk
         // would keep the root from starting its share of frame f + 1. Consecutive frames rotate over the lanes: the next
         // frames' launches fill the SMs that the tail of this one (its longest rays) leaves idle.
         if (must_wait) CK(launch_flag_wait(sf_consumed(c), consumed_target, sf_timeouts(c), ls));
+        if (tiles && c->sf_world > 1) {  // the peers do not ship what lies outside the cull rectangle
+            PushClip clip;
+            push_clip(c, cam, 0, clip);
+            rc = sf_fill_outside(c, sf_slot(c, slot), clip, 0, ls);
+            if (rc) return rc;
+        }
         if (eb) CK(cudaEventRecord(eb, ls));
         rc = do_render(c, cam, un, tiles ? offsets : nullptr, tiles ? n : 0, false, 1, sf_slot(c, slot), nullptr, ls);
         if (rc) return rc;
@@ -1450,7 +1484,9 @@ int vkrt_sortfirst_render(VkrtContext* c, const VkrtCameraUniform* cam, const Vk
     if (tiles) {
         bool vec16 = (c->W % 2 == 0) && (c->params.tile_size % 2 == 0);
         for (int i = 0; i < n && vec16; ++i) vec16 = ((long long)offsets[i].x % 2) == 0 && offsets[i].x >= 0.0f;
-        CK(launch_push_tiles(c->sf_local[lane], sf_slot(c, slot), c->d_offsets, n, c->params.tile_size, c->W, c->H, vec16, c->copy_stream));
+        PushClip clip;
+        push_clip(c, cam, 0, clip);
+        CK(launch_push_tiles(c->sf_local[lane], sf_slot(c, slot), c->d_offsets, n, c->params.tile_size, c->W, c->H, vec16, c->copy_stream, 1, &clip));
     } else {
         CK(cudaMemcpyAsync(sf_slot(c, slot), c->sf_local[lane], sf_frame_bytes(c), cudaMemcpyDeviceToDevice, c->copy_stream));
     }
@@ -1491,6 +1527,14 @@ int vkrt_sortfirst_render_tiles_batch(VkrtContext* c, const VkrtCameraUniform* c
     // where 576 take 0.78 ms), so the shares of several frames are batched exactly like whole frames are.
     if (c->sf_rank == 0) {
         if (must_wait) CK(launch_flag_wait(sf_consumed(c), consumed_target, sf_timeouts(c), ls));
+        if (c->sf_world > 1) {
+            PushClip clip;
+            for (int f = 0; f < n_frames; ++f) {
+                push_clip(c, cams + f, f, clip);
+                rc = sf_fill_outside(c, sf_slot(c, slot0 + f), clip, f, ls);
+                if (rc) return rc;
+            }
+        }
         if (eb) CK(cudaEventRecord(eb, ls));
         rc = do_render(c, cams, un, offsets, n, false, n_frames, sf_slot(c, slot0), nullptr, ls);
         if (rc) return rc;
@@ -1508,7 +1552,9 @@ int vkrt_sortfirst_render_tiles_batch(VkrtContext* c, const VkrtCameraUniform* c
     if (must_wait) CK(launch_flag_wait(sf_consumed(c), consumed_target, sf_timeouts(c), c->copy_stream));
     bool vec16 = (c->W % 2 == 0) && (c->params.tile_size % 2 == 0);
     for (int i = 0; i < n && vec16; ++i) vec16 = ((long long)offsets[i].x % 2) == 0 && offsets[i].x >= 0.0f;
-    CK(launch_push_tiles(c->sf_local[lane], sf_slot(c, slot0), c->d_offsets, n, c->params.tile_size, c->W, c->H, vec16, c->copy_stream, n_frames));
+    PushClip clip;
+    for (int f = 0; f < n_frames; ++f) push_clip(c, cams + f, f, clip);
+    CK(launch_push_tiles(c->sf_local[lane], sf_slot(c, slot0), c->d_offsets, n, c->params.tile_size, c->W, c->H, vec16, c->copy_stream, n_frames, &clip));
     CK(launch_flag_add_many(arrive, 1ull, c->copy_stream));  // after the transfer, system scope
     CK(cudaEventRecord(c->sf_copied[lane], c->copy_stream));
     return VKRT_OK;

@@ -127,12 +127,18 @@ cudaError_t launch_scalar_to_rgba16f(const void* vol, int dtype, uint2* color, u
 cudaError_t launch_synth(void* out, int kind, int dtype, int nx, int ny, int nz, int ox, int oy, int oz, int gnx, int gny, int gnz,
                          uint32_t seed, cudaStream_t s, int bricked = 0);
 cudaError_t launch_brick_window(const void* lin, void* out, int elem_bytes, int nx, int ny, int nz, cudaStream_t s);
-// vec16: every tile origin x and W are even (16-byte aligned rows): two pixels per store
+// sort-first direct-send: up to kMaxPushDst destinations (peer memory) / frames per launch
+constexpr int kMaxPushDst = 15;
+// per frame of a tile push: the pixel rectangle (inclusive) that is shipped; everything outside holds the clear colour
+struct PushClip {
+    int x0[kMaxPushDst + 1], y0[kMaxPushDst + 1], x1[kMaxPushDst + 1], y1[kMaxPushDst + 1];
+};
+// vec16: every tile origin x, clip x0 and W are even (16-byte aligned rows): two pixels per store. clip == nullptr: whole tiles
 cudaError_t launch_push_tiles(const uint2* src, uint2* dst, const VkrtOffset* d_offsets, int n_tiles, int tile, int W, int H, bool vec16,
-                              cudaStream_t s, int n_frames = 1);  // n_frames consecutive frames of W*H texels on both sides
+                              cudaStream_t s, int n_frames = 1, const PushClip* clip = nullptr);  // n_frames consecutive frames of W*H texels on both sides
+cudaError_t launch_fill_outside(uint2* frame, int W, int H, int x0, int y0, int x1, int y1, uint2 texel, cudaStream_t s);
 cudaError_t launch_flush_l2(uint4* buf, size_t n16, cudaStream_t s);
 // sort-last direct-send: up to kMaxPushDst destinations (peer memory) per launch
-constexpr int kMaxPushDst = 15;
 struct PushDst {
     void* ptr[kMaxPushDst];
     int n;

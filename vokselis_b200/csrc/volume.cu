@@ -8,6 +8,8 @@
 //    function's 0.1f threshold so that fp32 rounding inside any trilinear formula cannot cross it.
 //  * generate_xor: shaders/xor.wgsl `cs_main` (:69-78) with `noise_volume` (:55-61) or the dead
 //    bit-pattern `volume` (:46-53), writing both rgba16f volumes on the device ("next" row N1).
+#include <algorithm>
+
 #include "raycast.cuh"
 #include "vkrt_device.cuh"
 
@@ -392,38 +394,64 @@ __global__ void flag_set_kernel(unsigned long long* flag, unsigned long long v) 
 // (a CUDA-IPC mapping: the stores go out over NVLink). Whole tile rows with 16-byte stores by consecutive lanes, so the
 // link carries full 128-byte lines — the raycast kernel's own 8-byte stores of 8x4-pixel warps (64-byte row segments)
 // cost its launch 20-30 % (profiles/scaling_r01.md). grid = (tile, group of 16 rows).
+// clip: per frame of the launch, the pixel rectangle (inclusive; x0 even, x1 odd) outside of which every pixel holds the
+// clear colour — the cull rectangle around the projected box, api.cu push_clip — and is NOT shipped: rank 0 fills those
+// pixels of the slot itself (fill_outside_kernel). At zoom 3 the box covers about a quarter of a 16:9 frame, so the
+// gather moves a quarter of the bytes.
 template <class V, int PX>
 __global__ void __launch_bounds__(256) push_tiles_kernel(const uint2* __restrict__ src, uint2* __restrict__ dst, const VkrtOffset* __restrict__ offsets,
-                                                         int tile, int W, int H) {
+                                                         int tile, int W, int H, const PushClip clip) {
     const VkrtOffset o = offsets[blockIdx.x];
     const uint32_t x0 = __float2uint_rz(o.x), y0 = __float2uint_rz(o.y);
     if (x0 >= (uint32_t)W || y0 >= (uint32_t)H) return;
     src += (size_t)blockIdx.z * W * H;  // grid.z = frame of a batched tile share: consecutive local frames -> consecutive ring slots
     dst += (size_t)blockIdx.z * W * H;
-    const int cols = min(tile, W - (int)x0) / PX;  // vectors per row (PX pixels each)
-    const int r0 = (int)blockIdx.y * 16, r1 = min(min(r0 + 16, tile), H - (int)y0);
+    // the tile's pixels inside the clip rectangle: columns [xs, xe), rows [r0, r1) of this block's 16-row group
+    const int xs = max((int)x0, clip.x0[blockIdx.z]), xe = min(min((int)x0 + tile, W), clip.x1[blockIdx.z] + 1);
+    const int r0 = max((int)blockIdx.y * 16, clip.y0[blockIdx.z] - (int)y0);
+    const int r1 = min(min(min((int)blockIdx.y * 16 + 16, tile), H - (int)y0), clip.y1[blockIdx.z] + 1 - (int)y0);
+    if (xs >= xe || r0 >= r1) return;
+    const int cols = (xe - xs) / PX;  // vectors per row (PX pixels each)
     for (int i = (int)threadIdx.x; i < (r1 - r0) * cols; i += (int)blockDim.x) {
         const int r = r0 + i / cols, cidx = i % cols;
-        const size_t px = ((size_t)(y0 + r) * W + x0) + (size_t)cidx * PX;
+        const size_t px = ((size_t)(y0 + r) * W + xs) + (size_t)cidx * PX;
         *reinterpret_cast<V*>(dst + px) = *reinterpret_cast<const V*>(src + px);
     }
-    if (PX == 2 && ((min(tile, W - (int)x0)) & 1)) {  // odd clipped width: the last pixel of each row
-        const int c = min(tile, W - (int)x0) - 1;
+    if (PX == 2 && ((xe - xs) & 1)) {  // odd width (the frame's last column): the last pixel of each row
         for (int r = r0 + (int)threadIdx.x; r < r1; r += (int)blockDim.x) {
-            const size_t px = ((size_t)(y0 + r) * W + x0) + (size_t)c;
+            const size_t px = ((size_t)(y0 + r) * W + xe - 1);
             dst[px] = src[px];
         }
     }
 }
 
+// rank 0: every pixel of `frame` outside the rectangle (inclusive bounds; an empty rectangle = the whole frame) := texel
+__global__ void __launch_bounds__(256) fill_outside_kernel(uint2* __restrict__ frame, int W, int H, int x0, int y0, int x1, int y1, uint2 texel) {
+    const int y = (int)blockIdx.y;
+    const bool row_inside = y >= y0 && y <= y1;
+    for (int x = (int)(blockIdx.x * blockDim.x + threadIdx.x); x < W; x += (int)(gridDim.x * blockDim.x))
+        if (!row_inside || x < x0 || x > x1) frame[(size_t)y * W + x] = texel;
+}
+
 }  // namespace
 
 cudaError_t launch_push_tiles(const uint2* src, uint2* dst, const VkrtOffset* d_offsets, int n_tiles, int tile, int W, int H, bool vec16,
-                              cudaStream_t s, int n_frames) {
+                              cudaStream_t s, int n_frames, const PushClip* clip) {
     if (n_tiles <= 0) return cudaSuccess;
+    PushClip all;
+    if (!clip) {
+        for (int f = 0; f < kMaxPushDst + 1; ++f) { all.x0[f] = 0; all.y0[f] = 0; all.x1[f] = W - 1; all.y1[f] = H - 1; }
+        clip = &all;
+    }
     const dim3 grid((unsigned)n_tiles, (unsigned)((tile + 15) / 16), (unsigned)(n_frames > 0 ? n_frames : 1));
-    if (vec16) push_tiles_kernel<uint4, 2><<<grid, 256, 0, s>>>(src, dst, d_offsets, tile, W, H);
-    else push_tiles_kernel<uint2, 1><<<grid, 256, 0, s>>>(src, dst, d_offsets, tile, W, H);
+    if (vec16) push_tiles_kernel<uint4, 2><<<grid, 256, 0, s>>>(src, dst, d_offsets, tile, W, H, *clip);
+    else push_tiles_kernel<uint2, 1><<<grid, 256, 0, s>>>(src, dst, d_offsets, tile, W, H, *clip);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_outside(uint2* frame, int W, int H, int x0, int y0, int x1, int y1, uint2 texel, cudaStream_t s) {
+    const dim3 grid((unsigned)std::min((W + 255) / 256, 64), (unsigned)H);
+    fill_outside_kernel<<<grid, 256, 0, s>>>(frame, W, H, x0, y0, x1, y1, texel);
     return cudaGetLastError();
 }
 
