@@ -681,12 +681,14 @@ def run_gpu(args):
                     "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["hbm_source"],
                     "compulsory_bytes_per_launch": hbm_bytes, "note": "quad texture (64 MiB, read at most once per launch) + frames (W*H*8 B each); far below HBM peak by construction"},
             "frames_per_launch": frames_per_launch,
-            "binding_resource": "instruction issue: ncu on the 16-frame launch reports issue active 85 %, sm__throughput 83 % of peak over the launch, l1tex 60 %, "
-                                "DRAM 2 %, 24.6 of 32 lanes active per instruction (profiles/r02_v3_prof_batch16_m1_quad_skip.md); the quad texture is L1/L2-resident, so the texel "
-                                "path is the memory-side bound reported here and HBM (roofline.hbm) is a few % by construction. With skipping off the SAME kernel is bound by the "
-                                "texel path: roofline_dense",
-            "note": "achieved = samples actually fetched x 8 B of taps / launch time; with exact empty-space skipping a large share of the kernel's "
-                    "time is traversal (instruction issue), not fetching",
+            "binding_resource": "instruction issue: ncu on the 16-frame launch reports issue active 82 %, sm__throughput 79 % of peak over the launch, l1tex 52 %, "
+                                "DRAM 2.5 %, 24.5 of 32 lanes active per instruction, 65 M warp instructions per frame (profiles/r02_v4_prof_batch16_m1_quad_skip_octant.md); the quad "
+                                "texture is L1/L2-resident, so the texel path is the memory-side bound reported here and HBM (roofline.hbm) is a few % by construction. With skipping "
+                                "off the SAME kernel is bound by the texel path: roofline_dense",
+            "note": "achieved = samples actually fetched x 8 B of taps / launch time. Exact empty-space skipping over 2-voxel occupancy bricks with one distance field per ray "
+                    "octant fetches 11.3 M of the frame's 90 M reference samples (8-voxel bricks, isotropic field: 17.7 M): the kernel got 1.33x faster (11,215 -> 14,950 frames/s) "
+                    "by NOT fetching transparent samples, which lowers this fraction (0.37 -> 0.33) while frames/s rise; what remains per frame is traversal + shading, bound by "
+                    "instruction issue (profiles/r02_octant_ab.md)",
         }
         roofline_dense = None
         if dense and l1_peak:
@@ -695,7 +697,7 @@ def run_gpu(args):
                               "frames_per_s": 1e3 / dense["ms_per_frame"], "ms_per_frame": dense["ms_per_frame"], "samples_per_frame": dense["samples_per_frame"],
                               "fetches_per_s": 2.0 * dense["samples_per_frame"] * 1e3 / dense["ms_per_frame"],
                               "note": "the same workload with skipping off (every reference sample fetched): ncu l1tex throughput 98 %, tex_throttle the top stall "
-                                      "(profiles/r02_v3_prof_batch16_m1_quad_noskip.md) — the fetch path is the bound here"}
+                                      "(profiles/r02_v4_prof_batch16_m1_quad_noskip.md) — the fetch path is the bound here"}
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

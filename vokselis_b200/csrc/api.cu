@@ -442,23 +442,23 @@ int build_occupancy(VkrtContext* c) {
     if (e == cudaSuccess) e = launch_occupied_bounds(c->dist, c->obx, c->oby, c->obz, d_bounds, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(bounds, d_bounds, sizeof bounds, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_bounds);
-    if (e != cudaSuccess) return cuda_fail(e, "build_occupancy");
+    if (e != cudaSuccess) { cudaFree(d_bounds); return cuda_fail(e, "build_occupancy"); }
     for (int k = 0; k < 3; ++k) { c->occ_lo[k] = bounds[k]; c->occ_hi[k] = bounds[3 + k]; }
     c->occ_full = bounds[6] == 0;
     // (the kernel indexes the tables with 32 bits: a grid with more than 2^29 bricks renders without skipping; so does
     // a volume without a single empty brick — every iteration would consult the tables for nothing)
-    if (c->occ_full || 8 * (scalar ? padded : cells) > 0xffffffffull) return VKRT_OK;
+    if (c->occ_full || 8 * (scalar ? padded : cells) > 0xffffffffull) { cudaFree(d_bounds); return VKRT_OK; }
     e = cudaMalloc(&scratch, 8 * cells);
     if (e == cudaSuccess) e = cudaMalloc(&oct, 8 * cells);
     // bricks outside the grid: empty for M0 (out-of-range texels read 0), occupied for M1 (clamp-to-edge)
-    if (e == cudaSuccess) e = launch_octant_distance(c->dist, oct, scratch, c->obx, c->oby, c->obz, scalar ? 0 : 255, max_d, c->stream);
+    if (e == cudaSuccess) e = launch_octant_distance(c->dist, oct, scratch, d_bounds, c->obx, c->oby, c->obz, scalar ? 0 : 255, max_d, c->stream);
     if (e == cudaSuccess && scalar) {
         e = cudaMalloc(&c->dist_oct, 8 * padded);
         if (e == cudaSuccess) e = launch_pad_dist(oct, c->dist_oct, c->obx, c->oby, c->obz, 8, c->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(scratch);
+    cudaFree(d_bounds);
     if (e == cudaSuccess && !scalar) {
         c->dist_oct = oct;
         oct = nullptr;

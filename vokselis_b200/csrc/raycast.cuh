@@ -117,8 +117,8 @@ cudaError_t launch_occupancy_m1(const void* scalar, int dtype, int nx, int ny, i
 cudaError_t launch_occupied_bounds(const uint8_t* dist, int nbx, int nby, int nbz, int* d_out7, cudaStream_t s);
 cudaError_t launch_pad_dist(const uint8_t* dist, uint8_t* out, int nbx, int nby, int nbz, int tables, cudaStream_t s);
 // the 8 directional distance fields of the ray octants (volume.cu), back to back
-cudaError_t launch_octant_distance(const uint8_t* occ, uint8_t* oct, uint8_t* scratch, int nbx, int nby, int nbz, int border, int max_d,
-                                   cudaStream_t s);
+cudaError_t launch_octant_distance(const uint8_t* occ, uint8_t* oct, uint8_t* scratch, int* d_flag, int nbx, int nby, int nbz, int border,
+                                   int max_d, cudaStream_t s);
 cudaError_t launch_distance_transform(uint8_t* dist, uint8_t* scratch, int nbx, int nby, int nbz, int border, int max_d, cudaStream_t s);
 cudaError_t launch_pregather_quads(const void* vol, int dtype, void* out_texels, int nx, int ny, int nz, cudaStream_t s);
 cudaError_t launch_generate_xor(uint2* color, uint2* normal, int n, float time, int which, cudaStream_t s);

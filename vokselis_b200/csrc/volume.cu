@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) distance_step_kernel(const uint8_t* __res
 // One relaxation step: d = min(d, 1 + min over the 7 forward neighbours); tables are initialised with the occupancy
 // (0 / 255). `in` / `out` hold the 8 tables back to back.
 __global__ void __launch_bounds__(256) octant_step_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int nbx, int nby,
-                                                          int nbz, int border, int cap) {
+                                                          int nbz, int border, int cap, int* __restrict__ changed) {
     const size_t cells = (size_t)nbx * nby * nbz;
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= 8 * cells) return;
@@ -142,7 +142,9 @@ __global__ void __launch_bounds__(256) octant_step_kernel(const uint8_t* __restr
             const int v = (x < 0 || y < 0 || z < 0 || x >= nbx || y >= nby || z >= nbz) ? border : (int)tab[((size_t)z * nby + y) * nbx + x];
             m = min(m, v);
         }
-        d = min(min(d, m + 1), cap);
+        const int nd = min(min(d, m + 1), cap);
+        if (nd != d && changed) *changed = 1;  // (benign race: every writer stores 1)
+        d = nd;
     }
     out[g] = (uint8_t)d;
 }
@@ -621,17 +623,29 @@ cudaError_t launch_distance_transform(uint8_t* dist, uint8_t* scratch, int nbx, 
     return cudaGetLastError();
 }
 
-// occ: occupancy (0 / 255), cells bytes. oct, scratch: 8 * cells bytes each. After max_d relaxation steps every table holds
-// min(true directional distance, max_d); the result is left in `oct`.
-cudaError_t launch_octant_distance(const uint8_t* occ, uint8_t* oct, uint8_t* scratch, int nbx, int nby, int nbz, int border, int max_d,
+// occ: occupancy (0 / 255), cells bytes. oct, scratch: 8 * cells bytes each; d_flag: one int. After k relaxation steps every
+// table holds min(true directional distance, k) (255 where nothing within k is occupied); the loop stops at max_d steps or,
+// checked every 8 steps, as soon as a step changes nothing (then every value is final, and min(value, max_d) is applied by
+// the step's own cap). Synchronises the stream. The result is left in `oct`.
+cudaError_t launch_octant_distance(const uint8_t* occ, uint8_t* oct, uint8_t* scratch, int* d_flag, int nbx, int nby, int nbz, int border, int max_d,
                                    cudaStream_t s) {
     const size_t cells = (size_t)nbx * nby * nbz;
     const unsigned blocks = (unsigned)((8 * cells + 255) / 256);
     replicate8_kernel<<<blocks, 256, 0, s>>>(occ, oct, cells);
     uint8_t *a = oct, *b = scratch;
     for (int i = 0; i < max_d; ++i) {
-        octant_step_kernel<<<blocks, 256, 0, s>>>(a, b, nbx, nby, nbz, border, max_d);
+        const bool probe = (i % 8) == 7 && i + 1 < max_d;
+        cudaError_t e = probe ? cudaMemsetAsync(d_flag, 0, sizeof(int), s) : cudaSuccess;
+        if (e != cudaSuccess) return e;
+        octant_step_kernel<<<blocks, 256, 0, s>>>(a, b, nbx, nby, nbz, border, max_d, probe ? d_flag : nullptr);
         uint8_t* t = a; a = b; b = t;
+        if (probe) {
+            int changed = 1;
+            e = cudaMemcpyAsync(&changed, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) return e;
+            if (!changed) break;
+        }
     }
     if (a != oct) {
         cudaError_t e = cudaMemcpyAsync(oct, a, 8 * cells, cudaMemcpyDeviceToDevice, s);
