@@ -607,6 +607,86 @@ def test_cull_rectangle_and_bounds_clip_are_bit_exact(rt, oracle, mode):
         assert long_gap  # some rays march > 200 reference steps, so entry gaps beyond 64 steps occur
 
 
+@pytest.mark.parametrize("mode", [abi.MODE_M0, abi.MODE_M1])
+def test_every_occupancy_brick_edge_is_bit_exact(rt, oracle, mode):
+    """The occupancy grid's brick edge (vkrt_set_occupancy_brick: 1, 2, 4, 8, 16, 32 voxels, 0 = the library's choice) and the
+    eight per-octant distance fields built over it only decide WHICH samples are leapt over: frames and reference-semantics
+    iteration counts are identical for every edge and identical to the full march, on a grid whose dimensions are multiples
+    of none of them (partial last bricks, the leap clip), for cameras in all eight octants' worth of directions, inside the
+    box and grazing a face. Finer bricks must not fetch more samples than coarser ones."""
+    W, H = 320, 180
+    nx, ny, nz = 100, 60, 77
+    scalar, color, normal = _corner_content(nx, ny, nz)
+    cams = [(3.0, -0.5, 1.0, (0, 0, 0)), (3.0, 0.6, 4.1, (0, 0, 0)), (2.4, -0.9, 2.6, (0, 0, 0)), (2.4, 0.9, 5.7, (0, 0, 0)),
+            (0.5, 0.2, 2.5, (-0.4, 0.3, -0.3)), (1.45, 0.0, 0.0, (0, 0.99, 0))]
+    cams = [rt.Camera(z, p_, y, t, W / H).get_proj_view_matrix() for z, p_, y, t in cams]
+    with rt.Context(0, W, H) as ctx:
+        ref_frames, ref_aux, fetched = None, None, {}
+        for edge in (8, 1, 2, 4, 16, 32, 0):
+            ctx.set_occupancy_brick(edge)
+            if mode == abi.MODE_M0:
+                ctx.upload_rgba16f(color.view(np.uint16), normal.view(np.uint16))
+            else:
+                ctx.upload_scalar(scalar)
+            info = ctx.volume_info()
+            assert 0 < info["bricks_occupied"] < info["bricks_total"]
+            if edge:
+                assert info["bricks_total"] == -(-nx // edge) * -(-ny // edge) * -(-nz // edge)
+            q = rt.default_params(mode)
+            q.layout = abi.LAYOUT_TEXTURE if mode == abi.MODE_M0 else abi.LAYOUT_QUAD
+            if ref_frames is None:  # the full march
+                q.skip_empty, q.count_samples = 0, 1
+                ctx.set_params(q)
+                ref_frames, ref_aux = [], []
+                for cam in cams:
+                    ctx.render(cam)
+                    ref_frames.append(ctx.readback())
+                    ref_aux.append(ctx.readback_aux())
+            total = 0
+            for count in (0, 1):
+                q.skip_empty, q.count_samples = 1, count
+                ctx.set_params(q)
+                ctx.reset_stats()
+                for i, cam in enumerate(cams):
+                    ctx.render(cam)
+                    assert np.array_equal(ctx.readback(), ref_frames[i]), (edge, count, i)
+                    if count:
+                        assert np.array_equal(ctx.readback_aux(), ref_aux[i]), (edge, i)
+                if count:
+                    total = int(ctx.stats().samples_fetched)
+            fetched[edge] = total
+        ctx.set_occupancy_brick(0)
+        assert fetched[1] <= fetched[2] <= fetched[4] <= fetched[8] <= fetched[16] <= fetched[32], fetched
+        assert fetched[0] == fetched[2]  # a small grid gets 2-voxel bricks
+        with pytest.raises(rt.VokselisError):
+            ctx.set_occupancy_brick(3)
+
+
+def test_volume_without_an_empty_brick_renders_without_skipping(rt, oracle, xor_cam):
+    """Every brick occupied (BASELINE config 3's fog): no distance tables are built and skip_empty = 1 runs the full march."""
+    W, H = 256, 144
+    rng = np.random.default_rng(5)
+    scalar = rng.integers(60, 255, size=(32, 32, 32), dtype=np.uint8)
+    ref, aux, st = oracle.render(abi.default_params(1), xor_cam, W, H, scalar=scalar)
+    with rt.Context(0, W, H) as ctx:
+        ctx.upload_scalar(scalar)
+        info = ctx.volume_info()
+        assert info["bricks_occupied"] == info["bricks_total"]
+        out = []
+        for skip in (0, 1):
+            q = rt.default_params(abi.MODE_M1)
+            q.skip_empty, q.count_samples, q.layout = skip, 1, abi.LAYOUT_QUAD
+            ctx.set_params(q)
+            ctx.reset_stats()
+            ctx.render(xor_cam)
+            out.append((ctx.readback(), ctx.readback_aux(), ctx.stats()))
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+        assert out[1][2].samples_fetched == out[1][2].samples_reference  # nothing was skipped
+        assert np.array_equal(out[1][1] >> 31, aux >> 31)
+        ctx.present()
+        check_images(ctx.readback_rgba8(), oracle.present(ref))
+
+
 def test_all_empty_volume_with_skipping(rt, oracle, xor_cam):
     """Nothing occupied: no ray marches; every hit pixel keeps the initial colour, like the full march."""
     W, H = 256, 144
