@@ -11,8 +11,11 @@ Checked for every ray:
     after t_end lie outside the occupied bricks;
   * sortlast.cu pre-leap (`n_pre`) and `t_stop`: no sample whose voxel index falls in the rank's own brick is
     skipped.
-The distance field is analytic (a few occupied boxes of bricks, Chebyshev distance, cap 16; for M1 the outside of
-the grid counts as occupied, as in volume.cu `distance_step_kernel`).
+The distance fields are analytic: a few occupied boxes of bricks (edge B = 2, 8 or 32 voxels); the raycast's field is
+DIRECTIONAL, one per ray octant — the largest d such that the d^3 bricks ahead of the brick in the ray's direction of travel
+are empty, capped at 128 voxels, as built by volume.cu `octant_step_kernel` — and for M1 the outside of the grid counts as
+occupied. The brick coordinate is floor(q / B) taken on the float (the kernel's FFMA.RM), not a shift of the truncated
+index; the approximate reciprocals of the leap model (MUFU.RCP) are modelled by a random relative error of 2^-21.
 """
 import math
 
@@ -36,20 +39,47 @@ def trunc_i(x):
 
 
 class Scene:
-    def __init__(self, n, boxes, mode):
-        self.n, self.nb, self.boxes, self.mode = n, (n + 7) // 8, boxes, mode  # boxes: [(lo3, hi3)] in bricks, hi exclusive
+    def __init__(self, n, boxes, mode, B=8):
+        self.n, self.B, self.nb, self.boxes, self.mode = n, B, (n + B - 1) // B, boxes, mode  # boxes: [(lo3, hi3)] in bricks, hi exclusive
+        self.cap = max(4, 128 // B)
 
-    def dist(self, b):
-        """volume.cu distance field: 0 = occupied, else min(CAP, Chebyshev distance to the nearest occupied brick);
+    def occupied(self, b):
+        if self.mode == 1 and not all(0 <= b[k] < self.nb for k in range(3)):
+            return True
+        return any(all(lo[k] <= b[k] < hi[k] for k in range(3)) for lo, hi in self.boxes)
+
+    def dist(self, b, sg=None):
+        """sg = None: the isotropic field of the sort-last windows (volume.cu distance_step_kernel): 0 = occupied, else
+        min(CAP, Chebyshev distance to the nearest occupied brick). sg = (+-1, +-1, +-1): the raycast's directional field
+        (octant_step_kernel): the largest d <= cap such that the cube of d^3 bricks [b, b + sg d) holds no occupied brick.
         M1: bricks outside the grid are occupied."""
-        best = CAP
+        if sg is None:
+            best = CAP
+            for lo, hi in self.boxes:
+                d = max(max(lo[k] - b[k], 0, b[k] - (hi[k] - 1)) for k in range(3))
+                best = min(best, d)
+            if self.mode == 1:
+                for k in range(3):
+                    best = min(best, b[k] + 1, self.nb - b[k])
+            return best
+        if self.occupied(b):
+            return 0
+        d = self.cap
+        # the cube's extent per axis is [b, b + d - 1] or [b - d + 1, b]; shrink d until it clears every box (and the grid, M1)
         for lo, hi in self.boxes:
-            d = max(max(lo[k] - b[k], 0, b[k] - (hi[k] - 1)) for k in range(3))
-            best = min(best, d)
+            # largest d for which the cube misses this box: the box is missed iff on SOME axis the cube ends before it
+            best_axis = 0
+            for k in range(3):
+                if sg[k] > 0:
+                    room = lo[k] - b[k] if b[k] < lo[k] else (self.cap if b[k] >= hi[k] else 0)
+                else:
+                    room = b[k] - (hi[k] - 1) if b[k] >= hi[k] else (self.cap if b[k] < lo[k] else 0)
+                best_axis = max(best_axis, room)
+            d = min(d, best_axis)
         if self.mode == 1:
             for k in range(3):
-                best = min(best, b[k] + 1, self.nb - b[k])
-        return best
+                d = min(d, self.nb - b[k] if sg[k] > 0 else b[k] + 1)
+        return d
 
     def occ_bounds(self):
         lo = [min(bx[0][k] for bx in self.boxes) for k in range(3)]
@@ -83,7 +113,11 @@ def intersect(eye, d):
 
 def step_dt(d, n, dt_scale, dt_floor):
     v = [f32(F(1) / f32(F(n) * abs(d[k]))) for k in range(3)]
-    return f32(F(dt_scale) * max(min(v[0], min(v[1], v[2])), F(dt_floor)))
+    ref = f32(F(dt_scale) * max(min(v[0], min(v[1], v[2])), F(dt_floor)))  # raycast_compute.wgsl:65-68, three divisions
+    a = max(f32(F(n) * abs(d[0])), max(f32(F(n) * abs(d[1])), f32(F(n) * abs(d[2]))))
+    one = f32(F(dt_scale) * max(f32(F(1) / a), F(dt_floor)))  # vkrt_device.cuh step_dt: ONE division by the largest divisor
+    assert one == ref  # correctly rounded division is monotone: the same float
+    return one
 
 
 def position(eye, d, t, h):
@@ -92,19 +126,25 @@ def position(eye, d, t, h):
     return q, [trunc_i(x) for x in q]
 
 
-def leap_count(sc, d_brick, idx, q, rq, drift, eps):
-    """raycast.cu leap_count, operation by operation: R = 8d - (4 + eps); per axis h = sg*R + (4 - q) (one FMA),
-    w = 8*b + h (one FMA), s = w * rq; the grid clip only where a partial last brick sticks out (M1);
+def brick_of(sc, q):
+    """floor(q / B) on the float, as the kernel's FFMA.RM(q, 1 / B, 1.5 * 2^23) computes it (1 / B is a power of two)"""
+    return [int(math.floor(float(q[k]) / sc.B)) for k in range(3)]
+
+
+def leap_count(sc, d_brick, brick, q, rq, drift, eps):
+    """raycast.cu leap_count, operation by operation: R = B d - (B/2 + eps); per axis h = sg*R + (B/2 - q) (one FMA),
+    w = B*b + h (one FMA), s = w * rq; the grid clip only where a partial last brick sticks out (M1);
     n = max(trunc(fma(min(s), 1 - drift, 0.98)), 1) with min(s) capped at 4094."""
-    R = fma(F(8), F(d_brick), f32(-(F(4) + eps)))
+    B = sc.B
+    R = fma(F(B), F(d_brick), f32(-(F(B / 2) + eps)))
     keep = f32(F(1) - drift)
     s = []
     for k in range(3):
         sg = F(1) if rq[k] >= 0 else F(-1)
-        h = fma(sg, R, f32(F(4) - q[k]))
-        w = fma(F(8), F(idx[k] >> 3), h)
+        h = fma(sg, R, f32(F(B / 2) - q[k]))
+        w = fma(F(B), F(brick[k]), h)
         sk = f32(w * rq[k])
-        if sc.mode == 1 and (sc.n & 7) != 0 and sg > 0:
+        if sc.mode == 1 and (sc.n & (B - 1)) != 0 and sg > 0:
             sk = min(sk, f32(f32(f32(F(sc.n) - eps) - q[k]) * rq[k]))
         s.append(sk)
     sm = min(min(s[0], s[1]), min(s[2], F(4094)))
@@ -126,10 +166,11 @@ def walk(sc, eye, d, dt_scale, dt_floor, max_steps=40000):
     return t0, t1, inv, dt, h, ts
 
 
-def sample_info(sc, eye, d, t, h):
+def sample_info(sc, eye, d, t, h, sg=None):
+    """dist: the field's value at the sample's brick (directional for the ray's signs `sg`, else the isotropic one)"""
     q, idx = position(eye, d, t, h)
     inb = all(0 <= idx[k] < sc.n for k in range(3))
-    dist = sc.dist([i >> 3 for i in idx]) if inb else None
+    dist = sc.dist([i // sc.B for i in idx], sg) if inb else None
     return q, idx, inb, dist
 
 
@@ -166,15 +207,18 @@ CASES = [(256, 1.0, 0.01), (1024, 1.0, 0.0), (2048, 2.0, 0.0), (4096, 1.0, 0.0),
 
 @pytest.mark.parametrize("n,dt_scale,dt_floor", CASES)
 @pytest.mark.parametrize("mode", [0, 1])
-def test_leaps_only_pass_over_empty_bricks(n, dt_scale, dt_floor, mode):
-    rng = np.random.default_rng(n * 7 + mode)
-    nb = n // 8
+@pytest.mark.parametrize("B", [2, 8, 32])
+def test_leaps_only_pass_over_empty_bricks(n, dt_scale, dt_floor, mode, B):
+    if B == 2 and n > 1024:
+        pytest.skip("the library picks coarser bricks for grids this large (api.cu occupancy_brick_shift)")
+    rng = np.random.default_rng(n * 7 + mode + 31 * B)
+    nb = n // B
     boxes = []
     for _ in range(3):
         lo = rng.integers(nb // 8, nb * 3 // 4, 3)
         sz = rng.integers(1, max(nb // 6, 2), 3)
         boxes.append((list(lo), list(np.minimum(lo + sz, nb - (1 if mode == 1 else 0)))))
-    sc = Scene(n, boxes, mode)
+    sc = Scene(n, boxes, mode, B)
     eps = f32(F(16.0) * F(1.1920929e-07) * F(n))
     rays = 5 if n >= 2048 else 10
     leaps = skipped = 0
@@ -182,15 +226,20 @@ def test_leaps_only_pass_over_empty_bricks(n, dt_scale, dt_floor, mode):
         eye, d = make_ray(rng, inside=(r % 4 == 3))
         t0, t1, inv, dt, h, ts = walk(sc, eye, d, dt_scale, dt_floor)
         dq = [f32(f32(d[k] * h) * dt) for k in range(3)]
-        rq = [f32(F(1) / dq[k]) if abs(dq[k]) > 1e-12 else F(1e30) for k in range(3)]
-        drift = f32(f32(f32(t1 * F(5.9604645e-08)) / dt) * F(2))
+        # MUFU.RCP + FMUL: a relative error of up to 2^-21 either way
+        rq = [f32(f32(F(1) / dq[k]) * F(1 + rng.uniform(-1, 1) * 2.0 ** -21)) if abs(dq[k]) > 1e-12 else F(1e30) for k in range(3)]
+        sg = [1 if rq[k] > 0 else -1 for k in range(3)]
+        drift = f32(f32(f32(t1 * F(5.9604645e-08)) / dt) * F(2 * (1 + 2.0 ** -21)))
         j = 0
         while j < len(ts):
-            q, idx, inb, dist = sample_info(sc, eye, d, ts[j], h)
-            if not inb:
-                nskip = 1 if mode == 0 else 0
+            q, idx, inb, _ = sample_info(sc, eye, d, ts[j], h)
+            brick = brick_of(sc, q)
+            # M1 consults the padded tables without a bounds test (q == n lands on the pad = occupied); M0 tests the index first
+            dist = sc.dist(brick, sg) if (mode == 1 or inb) else None
+            if mode == 0 and not inb:
+                nskip = 1
             elif dist != 0:
-                nskip = leap_count(sc, dist, idx, q, rq, drift, eps)
+                nskip = leap_count(sc, dist, brick, q, rq, drift, eps)
             else:
                 nskip = 0
             if nskip == 0:
@@ -198,11 +247,27 @@ def test_leaps_only_pass_over_empty_bricks(n, dt_scale, dt_floor, mode):
                 continue
             leaps += 1
             for jj in range(j, min(j + nskip, len(ts))):  # every sample passed over must be a no-op
-                _, idx2, inb2, dist2 = sample_info(sc, eye, d, ts[jj], h)
-                assert (inb2 and dist2 >= 1) or (not inb2 and mode == 0), (n, mode, r, j, jj, nskip, idx2, dist2)
+                _, idx2, inb2, _ = sample_info(sc, eye, d, ts[jj], h)
+                empty = inb2 and not sc.occupied([i // B for i in idx2])
+                assert empty or (not inb2 and mode == 0), (n, mode, B, r, j, jj, nskip, idx2)
                 skipped += 1
             j += nskip
     assert leaps > 0 and skipped > leaps
+
+
+def test_directional_distance_matches_brute_force():
+    """Scene.dist(b, sg) — the analytic stand-in for octant_step_kernel's relaxation — against the definition."""
+    rng = np.random.default_rng(3)
+    for mode in (0, 1):
+        sc = Scene(64, [([2, 3, 1], [4, 5, 3]), ([9, 9, 9], [12, 10, 14])], mode, 4)
+        for _ in range(300):
+            b = [int(v) for v in rng.integers(0, sc.nb, 3)]
+            sg = [int(v) for v in rng.choice([-1, 1], 3)]
+            d = 0
+            while d < sc.cap and not any(sc.occupied([b[0] + sg[0] * i, b[1] + sg[1] * j, b[2] + sg[2] * k])
+                                         for i in range(d + 1) for j in range(d + 1) for k in range(d + 1)):
+                d += 1
+            assert sc.dist(b, sg) == d, (mode, b, sg, d, sc.dist(b, sg))
 
 
 @pytest.mark.parametrize("n,dt_scale,dt_floor", CASES)
