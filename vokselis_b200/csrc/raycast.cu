@@ -241,12 +241,15 @@ template <int MODE, int LAYOUT, int DTYPE, bool SKIP, bool DBG>
 #endif
 __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VKRT_LAYOUT_LINEAR ? VKRT_M1_BLOCKS : 8)) raycast_kernel(const __grid_constant__ RenderArgs A) {
     // ---- which pixel -------------------------------------------------------------------------
-    const uint32_t gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y * blockDim.y + threadIdx.y;
+    // `single`: grid = (block columns, frames of the batch, block rows) — the frame index varies FASTER than the block row, so
+    // the launch works through all its frames top to bottom together and the last blocks it schedules are the (culled, cheap)
+    // bottom rows of every frame; with the frame slowest the launch ended on the last frame's longest rays (launch_raycast).
+    // `tile`: grid = (block columns, block rows, frame * n_tiles + tile).
+    const uint32_t gx = blockIdx.x * blockDim.x + threadIdx.x, gy = (A.n_tiles > 0 ? blockIdx.y : blockIdx.z) * blockDim.y + threadIdx.y;
     float offx = 0.0f, offy = 0.0f;
     uint32_t px = gx, py = gy;
     bool valid = true;
-    // `single`: grid.z = frame of the batch; `tile`: grid.z = frame * n_tiles + tile (the tile shares of several frames in one launch)
-    const uint32_t fr = A.n_tiles > 0 ? blockIdx.z / (uint32_t)A.n_tiles : blockIdx.z;
+    const uint32_t fr = A.n_tiles > 0 ? blockIdx.z / (uint32_t)A.n_tiles : blockIdx.y;
     if (A.n_tiles > 0) {  // `tile` entry: coord = gid + offset; store at gid + u32(offset)
         const VkrtOffset o = A.offsets[blockIdx.z - fr * (uint32_t)A.n_tiles];
         offx = o.x;
@@ -484,7 +487,7 @@ cudaError_t launch_raycast(const RenderArgs& A, int mode, int layout, int dtype,
         grid = dim3((unsigned)((A.tile_size + bw - 1) / bw), (unsigned)((A.tile_size + bh - 1) / bh),
                     (unsigned)A.n_tiles * (unsigned)(A.n_frames > 0 ? A.n_frames : 1));
     } else {
-        grid = dim3((unsigned)((A.W + bw - 1) / bw), (unsigned)((A.H + bh - 1) / bh), (unsigned)(A.n_frames > 0 ? A.n_frames : 1));
+        grid = dim3((unsigned)((A.W + bw - 1) / bw), (unsigned)(A.n_frames > 0 ? A.n_frames : 1), (unsigned)((A.H + bh - 1) / bh));
     }
     if (mode == VKRT_MODE_M0) {
         switch (layout) {
