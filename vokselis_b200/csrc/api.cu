@@ -702,6 +702,11 @@ int do_render(VkrtContext* c, const VkrtCameraUniform* cam, const VkrtUniform* u
     A.leap_lim[0] = A.fx - A.leap_eps; A.leap_lim[1] = A.fy - A.leap_eps; A.leap_lim[2] = A.fz - A.leap_eps;
     A.dt_scale = P.dt_scale; A.dt_floor = P.dt_floor; A.alpha_threshold = P.alpha_threshold; A.initial_alpha = P.initial_alpha;
     memcpy(A.clear, P.clear_color, sizeof A.clear);
+    {
+        const __half2 lo = __floats2half2_rn(A.clear[0], A.clear[1]), hi = __floats2half2_rn(A.clear[2], 1.0f);
+        memcpy(&A.clear_texel.x, &lo, 4);
+        memcpy(&A.clear_texel.y, &hi, 4);
+    }
     A.m1_srgb = P.m1_srgb;
     A.frame = frames_out ? frames_out : c->frame;
     A.rgba8 = rgba8_out;

@@ -260,6 +260,21 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
     }
     valid = valid && px < (uint32_t)A.W && py < (uint32_t)A.H;  // out-of-range textureStore is dropped
 
+    // Four fifths of a frame's blocks lie entirely outside the cull rectangle: they store the clear colour (packed on the
+    // host, A.clear_texel) and leave — no per-pixel cull test, no colour bookkeeping (`single` entry; block-uniform branch).
+    if (!DBG && A.n_tiles == 0) {
+        const float* cull = A.cull[fr];
+        const float bx0 = (float)(blockIdx.x * blockDim.x), by0 = (float)(blockIdx.z * blockDim.y);
+        if (bx0 > cull[2] || bx0 + (float)(blockDim.x - 1) < cull[0] || by0 > cull[3] || by0 + (float)(blockDim.y - 1) < cull[1]) {
+            if (valid) {
+                const size_t o = ((size_t)fr * A.H + py) * A.W + px;
+                A.frame[o] = A.clear_texel;
+                if (A.rgba8) A.rgba8[o] = present_pixel(A.clear_texel);
+            }
+            return;
+        }
+    }
+
     // ---- ray ---------------------------------------------------------------------------------
     // Pixels outside A.cull (the screen rectangle around the projected box, computed on the host with a
     // margin of pixels; the whole plane when the projection is not trustworthy) cannot hit: no ray is built.

@@ -65,6 +65,7 @@ struct RenderArgs {
     float bb_lo[3], bb_hi[3];
     // parameters (VkrtParams)
     float clear[4];
+    uint2 clear_texel;  // what a miss stores: pack_rgba16f(clear.rgb, 1), packed on the host (same RN conversions)
     int m1_srgb;
     // outputs
     uint2* frame;                  // n_frames * W*H rgba16f
