@@ -36,6 +36,8 @@ extern "C" {
     // page-lock memory the caller owns (e.g. a shared-memory segment mapped by one process per GPU)
     fn vkrt_host_register(ptr: *mut c_void, bytes: usize) -> c_int;
     fn vkrt_host_unregister(ptr: *mut c_void) -> c_int;
+    // tuning knob without a reference counterpart: brick edge of the occupancy grid (0 = automatic); frames do not depend on it
+    fn vkrt_set_occupancy_brick(ctx: *mut VkrtContext, edge: c_int) -> c_int;
 }
 
 pub struct CudaRaycast { ctx: *mut VkrtContext, pub width: u32, pub height: u32 }
@@ -51,6 +53,10 @@ impl CudaRaycast {
         let mut ctx = std::ptr::null_mut();
         check(unsafe { vkrt_create(device, width as _, height as _, &mut ctx) })?;
         Ok(Self { ctx, width, height })
+    }
+    /// Brick edge (voxels) of the occupancy grid for volumes created after this call; 0 = the library's choice.
+    pub fn set_occupancy_brick(&self, edge: i32) -> color_eyre::eyre::Result<()> {
+        check(unsafe { vkrt_set_occupancy_brick(self.ctx, edge as c_int) })
     }
     pub fn generate_xor(&self, un: &Uniform) -> color_eyre::eyre::Result<()> {
         check(unsafe { vkrt_generate_xor(self.ctx, un, 256, 0) })

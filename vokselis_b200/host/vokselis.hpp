@@ -133,6 +133,9 @@ class Context {
     }
     // src/context.rs:251-297 `render`: the present pass (tonemap into the Rgba8 capture target)
     void render() { check(vkrt_present(ctx_)); }
+    // No reference counterpart: brick edge (voxels) of the occupancy grid behind exact empty-space skipping, for volumes
+    // created after the call; 0 = the library's choice. Frames do not depend on it.
+    void set_occupancy_brick(int edge) { check(vkrt_set_occupancy_brick(ctx_, edge)); }
     // src/context.rs:299-306 `capture_frame`
     std::vector<uint8_t> capture_frame() {
         std::vector<uint8_t> px((size_t)width_ * height_ * 4);
