@@ -198,9 +198,11 @@ __device__ __forceinline__ float m1_sample(const RenderArgs& A, float2 qxy, floa
 }
 
 // Per-ray constants of the leap length model: reciprocal of the voxel-space advance per step on each axis (sign =
-// direction of travel; 1e30 for an axis the ray does not move along), that sign as +-1, and 1 - the drift allowance.
+// direction of travel; 1e30 for an axis the ray does not move along) and 1 - the drift allowance. (The direction as +-1
+// used to sit in three more registers; leap_count now takes the sign bit of rq: the kernel runs at its 40-register cap,
+// and the three registers ended the spills: +1 %.)
 struct LeapRay {
-    float rqx, rqy, rqz, sgx, sgy, sgz, keep;
+    float rqx, rqy, rqz, keep;
 };
 
 // How many consecutive samples, this one included, provably stay inside the empty region around the sample's
@@ -219,16 +221,20 @@ struct LeapRay {
 template <int MODE>
 __device__ __forceinline__ int leap_count(const RenderArgs& A, const LeapRay& L, uint32_t d, float2 bxy, float bz, float2 qxy, float qz) {
     const float R = fmaf(A.brick, (float)d, A.leap_r0);  // B d - (B / 2 + eps)
-    const float2 hxy = fma2(make_float2(L.sgx, L.sgy), dup2(R), add2(make_float2(-qxy.x, -qxy.y), dup2(A.half_brick)));
-    const float hz = fmaf(L.sgz, R, __fsub_rn(A.half_brick, qz));
+    // sg * R = R with the sign of rq (R > 0): one LOP3 per axis instead of a register per axis for sg; RN(sg*R + c) = RN(+-R + c)
+    const uint32_t Rb = __float_as_uint(R);
+    const float Rx = __uint_as_float(Rb | (__float_as_uint(L.rqx) & 0x80000000u)), Ry = __uint_as_float(Rb | (__float_as_uint(L.rqy) & 0x80000000u));
+    const float Rz = __uint_as_float(Rb | (__float_as_uint(L.rqz) & 0x80000000u));
+    const float2 hxy = add2(make_float2(Rx, Ry), add2(make_float2(-qxy.x, -qxy.y), dup2(A.half_brick)));
+    const float hz = __fadd_rn(Rz, __fsub_rn(A.half_brick, qz));
     const float2 wxy = fma2(dup2(A.brick), bxy, hxy);
     const float wz = fmaf(A.brick, bz, hz);
     const float2 sxy = mul2(wxy, make_float2(L.rqx, L.rqy));
     float sx = sxy.x, sy = sxy.y, sz = __fmul_rn(wz, L.rqz);
     if (MODE == VKRT_MODE_M1 && A.leap_clip) {  // uniform; only grids whose dims are not multiples of 8
-        if (L.sgx > 0.0f) sx = fminf(sx, (A.leap_lim[0] - qxy.x) * L.rqx);
-        if (L.sgy > 0.0f) sy = fminf(sy, (A.leap_lim[1] - qxy.y) * L.rqy);
-        if (L.sgz > 0.0f) sz = fminf(sz, (A.leap_lim[2] - qz) * L.rqz);
+        if (L.rqx > 0.0f) sx = fminf(sx, (A.leap_lim[0] - qxy.x) * L.rqx);
+        if (L.rqy > 0.0f) sy = fminf(sy, (A.leap_lim[1] - qxy.y) * L.rqy);
+        if (L.rqz > 0.0f) sz = fminf(sz, (A.leap_lim[2] - qz) * L.rqz);
     }
     const float sm = fminf(fminf(sx, sy), fminf(sz, (float)(kLeapFastMax - 1)));
     // samples j = 0 .. floor(s - margin) (this one is j = 0) lie inside the region: floor(s - (s*drift + 0.02)) + 1
@@ -319,14 +325,13 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
             L.rqx = fabsf(dqx) > 1e-12f ? __fdividef(1.0f, dqx) : 1e30f;
             L.rqy = fabsf(dqy) > 1e-12f ? __fdividef(1.0f, dqy) : 1e30f;
             L.rqz = fabsf(dqz) > 1e-12f ? __fdividef(1.0f, dqz) : 1e30f;
-            L.sgx = copysignf(1.0f, L.rqx); L.sgy = copysignf(1.0f, L.rqy); L.sgz = copysignf(1.0f, L.rqz);
             // one replayed addition moves t off the exact line by <= ulp(t)/2 <= t1 * 2^-24; in units of a step:
             drift_per_step = __fdividef(t1 * 5.9604645e-08f, dt) * 2.0f;  // x2 safety
             L.keep = 1.0f - drift_per_step;
         }
         // The ray's octant selects its directional distance field (RenderArgs::dist); the signs are the ones the leap
         // length model uses. M1 folds the table into the z brick coordinate (kMagic + octant * slabs per table + bz).
-        const uint32_t oct = SKIP ? ((L.sgx > 0.0f ? 1u : 0u) | (L.sgy > 0.0f ? 2u : 0u) | (L.sgz > 0.0f ? 4u : 0u)) : 0u;
+        const uint32_t oct = SKIP ? ((L.rqx > 0.0f ? 1u : 0u) | (L.rqy > 0.0f ? 2u : 0u) | (L.rqz > 0.0f ? 4u : 0u)) : 0u;
         const float magic_z = fmaf((float)oct, A.dsz_f, kMagic);
         const uint32_t oct_off = oct * A.dist_tab;
         // (Two traversal restructurings were measured and rejected on B200. While-while — every lane first
