@@ -681,8 +681,8 @@ def run_gpu(args):
                     "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["hbm_source"],
                     "compulsory_bytes_per_launch": hbm_bytes, "note": "quad texture (64 MiB, read at most once per launch) + frames (W*H*8 B each); far below HBM peak by construction"},
             "frames_per_launch": frames_per_launch,
-            "binding_resource": "instruction issue: ncu on the 16-frame launch reports issue active 83 %, sm__throughput 82 % of peak over the launch, l1tex 54 %, "
-                                "DRAM 2.6 %, 24.4 of 32 lanes active per instruction, 64.5 M warp instructions per frame (profiles/r02_v5_prof_batch16_m1_quad_skip_final.md); the quad "
+            "binding_resource": "instruction issue: ncu on the 16-frame launch reports issue active 83 %, sm__throughput 82 % of peak over the launch, l1tex 62 %, "
+                                "DRAM 2.6 %, 24.6 of 32 lanes active per instruction, 63.2 M warp instructions per frame (profiles/r02_v6_prof_batch16_m1_quad_skip_final.md); the quad "
                                 "texture is L1/L2-resident, so the texel path is the memory-side bound reported here and HBM (roofline.hbm) is a few % by construction. With skipping "
                                 "off the SAME kernel is bound by the texel path: roofline_dense",
             "note": "achieved = samples actually fetched x 8 B of taps / launch time. Exact empty-space skipping over 2-voxel occupancy bricks with one distance field per ray "

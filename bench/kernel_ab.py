@@ -2,9 +2,11 @@
 
 usage: kernel_ab.py [--vols xor,bonsai] [--layouts 3,4] [--skips 1,0] [--launches 12] [--batch 8] [--modes 1]
 Prints one JSON line per variant: ms per frame (CUDA events, 8 frames per launch, L2 flushed between launches),
-and whether its frames are bit-identical to the first variant's of the same volume.
+whether its frames are bit-identical to the first variant's of the same volume, and a hash of the last frame
+(to compare builds across processes: bench/ab_pick.sh).
 """
 import argparse
+import hashlib
 import json
 import math
 import sys
@@ -56,4 +58,5 @@ with rt.Context(0, W, H) as ctx:
                     same = bool(np.array_equal(ref, f0))
                 print(json.dumps({"vol": vname, "brick": brick, "layout": layout, "skip": skip, "ms_per_frame": float(ms.mean()) / B,
                                   "fps": 1e3 * B / float(ms.mean()), "p10_p90_ms_per_launch": [float(np.percentile(ms, 10)), float(np.percentile(ms, 90))],
-                                  "same_bits_as_first_layout": same}), flush=True)
+                                  "same_bits_as_first_layout": same,
+                                  "sha256_last_frame": hashlib.sha256(f0.tobytes()).hexdigest()[:16]}), flush=True)

@@ -117,8 +117,10 @@ def sample_volume(vol, q):
     return ((c00 * (1 - fy) + c10 * fy) * (1 - fz) + (c01 * (1 - fy) + c11 * fy) * fz) / 255.0
 
 
-def march(vol, occ, dist_of_ray, eye, d, bb_lo, bb_hi):
-    """returns per-ray (leaps, samples). dist_of_ray(bz, by, bx, idx) -> distance for the rays `idx`"""
+def march(vol, occ, dist_of_ray, eye, d, bb_lo, bb_hi, blind=0):
+    """returns per-ray (leaps, samples). dist_of_ray(bz, by, bx, idx) -> distance for the rays `idx`.
+    blind = K: a lane that has just evaluated a sample evaluates up to K more without consulting the distance field, inside the
+    same lock-step iteration (evaluating a sample is always exact; only skipping needs the field)."""
     n = len(eye)
     with np.errstate(divide="ignore"):
         inv = 1.0 / d
@@ -146,7 +148,7 @@ def march(vol, occ, dist_of_ray, eye, d, bb_lo, bb_hi):
     live = hit & (t < t_end)
     idx = np.nonzero(live)[0]
     nbk = N // BR
-    ev = np.zeros(3, np.int64)  # lock-step warp events: iterations, iterations with a leap, iterations with a sample
+    ev = np.zeros(4, np.int64)  # lock-step warp events: iterations, iterations with a leap, iterations with a sample, blind sample passes
     nwarps = n // 32
     while len(idx):
         p = eye[idx] + t[idx, None] * d[idx]
@@ -177,6 +179,18 @@ def march(vol, occ, dist_of_ray, eye, d, bb_lo, bb_hi):
             alpha[si] += (1 - alpha[si]) * v
             samples[si] += 1
             t[si] += dt[si]
+            for _ in range(blind):
+                si = si[(t[si] < t_end[si]) & (alpha[si] < 0.95)]
+                if not len(si):
+                    break
+                ev[3] += len(np.unique(si // 32))
+                pb = eye[si] + t[si, None] * d[si]
+                sv = sample_volume(vol, (pb + 1) * (N / 2))
+                x = np.clip((np.minimum(0.9, sv) - 0.10) / (1.2 - 0.10), 0, 1)
+                v = x * x * (3 - 2 * x)
+                alpha[si] += (1 - alpha[si]) * v
+                samples[si] += 1
+                t[si] += dt[si]
         live_now = (t[idx] < t_end[idx]) & (alpha[idx] < 0.95)
         idx = idx[live_now]
     return leaps, samples, hit, ev

@@ -50,9 +50,11 @@ template <> struct Scalar<VKRT_F32> {
 template <int LAYOUT>
 __device__ __forceinline__ void m0_fetch(const RenderArgs& A, int ix, int iy, int iz, bool inb, float4& c, float4& n) {
     if (LAYOUT == VKRT_LAYOUT_TEXTURE) {
-        // border addressing returns 0 outside: the out-of-range textureLoad definition
-        c = tex3D<float4>(A.tex_a, (float)ix + 0.5f, (float)iy + 0.5f, (float)iz + 0.5f);
-        n = tex3D<float4>(A.tex_b, (float)ix + 0.5f, (float)iy + 0.5f, (float)iz + 0.5f);
+        // border addressing returns 0 outside: the out-of-range textureLoad definition.
+        // (tex3DLod with level 0, here and below: TEX.LZ, no level-of-detail register to set up per fetch — tex3D compiles
+        // to TEX.LL with a register holding the level; the arrays have one level, the texels are the same)
+        c = tex3DLod<float4>(A.tex_a, (float)ix + 0.5f, (float)iy + 0.5f, (float)iz + 0.5f, 0.0f);
+        n = tex3DLod<float4>(A.tex_b, (float)ix + 0.5f, (float)iy + 0.5f, (float)iz + 0.5f, 0.0f);
         return;
     }
     if (!inb) {
@@ -144,7 +146,7 @@ __device__ __forceinline__ float lerp3_quads(float4 g0, float4 g1, float fx, flo
 template <int LAYOUT, int DTYPE>
 __device__ __forceinline__ float m1_sample(const RenderArgs& A, float2 qxy, float qz) {
     if (LAYOUT == VKRT_LAYOUT_TEXTURE) {
-        return tex3D<float>(A.tex_a, qxy.x, qxy.y, qz);  // hardware trilinear, 8-bit weights
+        return tex3DLod<float>(A.tex_a, qxy.x, qxy.y, qz, 0.0f);  // hardware trilinear, 8-bit weights
     }
     // q - 0.5 as RN(q * 1 + -0.5): qxy comes out of a packed multiplication, and ptxas would contract a plain packed
     // addition with it (see RenderArgs::one), rounding u once instead of twice
@@ -175,11 +177,17 @@ __device__ __forceinline__ float m1_sample(const RenderArgs& A, float2 qxy, floa
         // Texel (x0+1, y0+1, z) holds the pre-gathered 2x2 xy footprint v(x0..x0+1, y0..y0+1, z) with clamp-to-edge baked
         // in (volume.cu pregather_quads_kernel); z clamps through the texture's address mode. Two POINT fetches of a 3-D
         // texture return the 8 taps; no gather footprint, 3-D tiled locality across layers.
-        // (the second fetch addresses the same x, y texel through its own coordinate pair, fl + 1.25: one FADD2 instead of
-        // two register copies into the second TEX's operand registers)
-        const float2 cxy = add2(flxy, dup2(1.5f)), cxy1 = add2(flxy, dup2(1.25f));
-        const float4 g0 = tex3D<float4>(A.tex_a, cxy.x, cxy.y, flz + 0.5f);
-        const float4 g1 = tex3D<float4>(A.tex_a, cxy1.x, cxy1.y, flz + 1.5f);
+        // Both fetches read ONE coordinate triple; the second adds the texel offset (0, 0, 1) inside the texture unit
+        // (TEX.LZ.AOFFI; the offset is applied before the address mode, so z + 1 clamps to the edge like a coordinate would):
+        // one packed constant instead of a second coordinate triple (FADD2 + FADD), and level 0 without a level register
+        // (TEX.LZ). CUDA C++ has no texel-offset fetch for 3-D textures, hence the PTX. Same texels, same bits.
+        const float2 cxy = add2(flxy, dup2(1.5f));
+        const float cz = flz + 0.5f;
+        float4 g0, g1;
+        asm("tex.level.3d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}], 0f00000000;"
+            : "=f"(g0.x), "=f"(g0.y), "=f"(g0.z), "=f"(g0.w) : "l"(A.tex_a), "f"(cxy.x), "f"(cxy.y), "f"(cz));
+        asm("tex.level.3d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}], 0f00000000, {0, 0, 1, 0};"
+            : "=f"(g1.x), "=f"(g1.y), "=f"(g1.z), "=f"(g1.w) : "l"(A.tex_a), "f"(cxy.x), "f"(cxy.y), "f"(cz));
         return lerp3_quads(g0, g1, fx, fy, fz);
     }
     const int x0 = (int)flx, y0 = (int)fly, z0 = (int)flz;
@@ -218,7 +226,7 @@ struct LeapRay {
 // through the packed FADD2 / FFMA2 / FMUL2: 11 floating-point instructions for the three axes. In M1 the region is
 // also clipped to the grid when a partial last brick sticks out of it (A.leap_clip; clamp-to-edge sampling: outside is
 // NOT empty; the distance field's border is "occupied", so whole bricks never stick out).
-template <int MODE>
+template <int MODE, bool CLIP>
 __device__ __forceinline__ int leap_count(const RenderArgs& A, const LeapRay& L, uint32_t d, float2 bxy, float bz, float2 qxy, float qz) {
     const float R = fmaf(A.brick, (float)d, A.leap_r0);  // B d - (B / 2 + eps)
     // sg * R = R with the sign of rq (R > 0): one LOP3 per axis instead of a register per axis for sg; RN(sg*R + c) = RN(+-R + c)
@@ -231,7 +239,7 @@ __device__ __forceinline__ int leap_count(const RenderArgs& A, const LeapRay& L,
     const float wz = fmaf(A.brick, bz, hz);
     const float2 sxy = mul2(wxy, make_float2(L.rqx, L.rqy));
     float sx = sxy.x, sy = sxy.y, sz = __fmul_rn(wz, L.rqz);
-    if (MODE == VKRT_MODE_M1 && A.leap_clip) {  // uniform; only grids whose dims are not multiples of 8
+    if (MODE == VKRT_MODE_M1 && CLIP && A.leap_clip) {  // uniform; only grids whose dims are not multiples of the brick edge
         if (L.rqx > 0.0f) sx = fminf(sx, (A.leap_lim[0] - qxy.x) * L.rqx);
         if (L.rqy > 0.0f) sy = fminf(sy, (A.leap_lim[1] - qxy.y) * L.rqy);
         if (L.rqz > 0.0f) sz = fminf(sz, (A.leap_lim[2] - qz) * L.rqz);
@@ -241,7 +249,9 @@ __device__ __forceinline__ int leap_count(const RenderArgs& A, const LeapRay& L,
     return max(__float2int_rz(fmaf(sm, L.keep, 0.98f)), 1);
 }
 
-template <int MODE, int LAYOUT, int DTYPE, bool SKIP, bool DBG>
+// CLIP = false: the host vouches for A.leap_clip == 0 (launch3), and the leap drops the uniform test of it (three issue
+// slots per leap: LDCU + UISETP + BRA.U)
+template <int MODE, int LAYOUT, int DTYPE, bool SKIP, bool DBG, bool CLIP>
 #ifndef VKRT_M1_BLOCKS
 #define VKRT_M1_BLOCKS 12
 #endif
@@ -340,7 +350,7 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
         // space, all by the warp minimum: 13 % slower, the 20 % extra samples taken by lanes that could have
         // leapt outweigh the leaps saved, profiles/r01_uniform_ab.md.)
         float t = t0, t_end = t1;
-        bool terminated = false;  // (DBG bookkeeping only)
+        bool terminated = false;  // early ray termination: alpha reached the threshold
         if (SKIP) {
             // Clip the march to the bounding box of the occupied bricks (grown by one voxel, A.bb_*): every
             // sample outside it lies in an empty brick, i.e. is a bit-exact no-op, so the loop may stop at the
@@ -380,7 +390,10 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
             }
         }
         const float2 exy = make_float2(eye.x, eye.y), dxy = make_float2(dir.x, dir.y), hxy = make_float2(A.hx, A.hy), one2 = dup2(A.one);
-        while (t < t_end) {
+        // Early ray termination is part of the loop condition, not a `break` out of the divergent sample branch: a `break`
+        // costs a reliable-reconvergence pair (BSSY.RELIABLE / BSYNC) in EVERY iteration plus BREAK + BRA in the sample path;
+        // the flag lives in a predicate and rides on the loop's own branch (`@P0 BRA P2`).
+        while (!terminated && t < t_end) {
             // p = eye + t*dir ; q = (p + 1) * (N/2) — exact (IEEE round-to-nearest per component, the oracle's operation
             // order), decides the texel; x and y go through the packed FMUL2 / FADD2
             const float2 pxy = fma2(mul2(dup2(t), dxy), one2, exy);  // RN(m * 1 + e) = RN(m + e), see A.one
@@ -406,14 +419,14 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
                     uint32_t cell = (__float_as_uint(bzm) * A.dsy + __float_as_uint(bxy.y)) * A.dsx + __float_as_uint(bxy.x) - A.dist_bias;
                     cell = min(cell, A.dist_last);
                     const uint32_t d = __ldg(A.dist + cell);
-                    if (d != 0u) n = leap_count<MODE>(A, L, d, add2(bxy, dup2(-kMagic)), __fsub_rn(bzm, magic_z), qxy, qz);
+                    if (d != 0u) n = leap_count<MODE, CLIP>(A, L, d, add2(bxy, dup2(-kMagic)), __fsub_rn(bzm, magic_z), qxy, qz);
                 } else if (!inb) {
                     n = 1;
                 } else {
                     const int bx = ix >> A.obs, by = iy >> A.obs, bz = iz >> A.obs;
                     const uint32_t cell = ((uint32_t)bz * A.dsy + (uint32_t)by) * A.dsx + (uint32_t)bx + oct_off;
                     const uint32_t d = __ldg(A.dist + cell);
-                    if (d != 0u) n = leap_count<MODE>(A, L, d, make_float2((float)bx, (float)by), (float)bz, qxy, qz);
+                    if (d != 0u) n = leap_count<MODE, CLIP>(A, L, d, make_float2((float)bx, (float)by), (float)bz, qxy, qz);
                 }
                 if (n > 0) {
                     if (DBG) {
@@ -437,13 +450,18 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
                 const f3 p = {pxy.x, pxy.y, pz};
                 m0_shade(col, c, n, p, A.clear);
             } else {
-                m1_shade(col, m1_sample<LAYOUT, DTYPE>(A, qxy, qz));
+                m1_shade_acc(col, m1_sample<LAYOUT, DTYPE>(A, qxy, qz));  // the palette's constant half is added after the loop
             }
-            if (col.a >= A.alpha_threshold) {
-                terminated = true;
-                break;
+            if (DBG) {  // the counting kernel keeps t at the terminating sample (the tail below counts from it)
+                if (col.a >= A.alpha_threshold) {
+                    terminated = true;
+                    break;
+                }
+                t = xadd(t, dt);
+            } else {
+                t = xadd(t, dt);
+                terminated = col.a >= A.alpha_threshold;
             }
-            t = xadd(t, dt);
         }
         if (DBG && SKIP && !terminated) {  // the reference's loop runs on to the far face: count those iterations
             while (t < t1) {
@@ -453,6 +471,7 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
         }
     }
     if (hit) {
+        if (MODE == VKRT_MODE_M1) m1_finish(col, A.initial_alpha);
         if (MODE == VKRT_MODE_M1 && A.m1_srgb) {
             col.r = linear_to_srgb_naive(col.r);
             col.g = linear_to_srgb_naive(col.g);
@@ -486,11 +505,14 @@ __global__ void __launch_bounds__(128, MODE == VKRT_MODE_M0 ? 10 : (LAYOUT != VK
 template <int MODE, int LAYOUT, int DTYPE>
 cudaError_t launch3(const RenderArgs& A, dim3 grid, dim3 block, cudaStream_t s, bool skip, bool dbg) {
     if (skip) {
-        if (dbg) raycast_kernel<MODE, LAYOUT, DTYPE, true, true><<<grid, block, 0, s>>>(A);
-        else raycast_kernel<MODE, LAYOUT, DTYPE, true, false><<<grid, block, 0, s>>>(A);
+        if (dbg) raycast_kernel<MODE, LAYOUT, DTYPE, true, true, true><<<grid, block, 0, s>>>(A);
+        // M1 on a grid whose dims are multiples of the occupancy brick: the instantiation without the clip test (M0 never
+        // clips: for it this names the same instantiation as the line below)
+        else if (MODE == VKRT_MODE_M1 && !A.leap_clip) raycast_kernel<MODE, LAYOUT, DTYPE, true, false, MODE != VKRT_MODE_M1><<<grid, block, 0, s>>>(A);
+        else raycast_kernel<MODE, LAYOUT, DTYPE, true, false, true><<<grid, block, 0, s>>>(A);
     } else {
-        if (dbg) raycast_kernel<MODE, LAYOUT, DTYPE, false, true><<<grid, block, 0, s>>>(A);
-        else raycast_kernel<MODE, LAYOUT, DTYPE, false, false><<<grid, block, 0, s>>>(A);
+        if (dbg) raycast_kernel<MODE, LAYOUT, DTYPE, false, true, true><<<grid, block, 0, s>>>(A);
+        else raycast_kernel<MODE, LAYOUT, DTYPE, false, false, true><<<grid, block, 0, s>>>(A);
     }
     return cudaGetLastError();
 }
