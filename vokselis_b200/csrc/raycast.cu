@@ -7,10 +7,10 @@
 //
 // B200 mapping: a block is 8x16 pixels = four warps of 8x4 pixels, so the 32 rays of a
 // warp walk through neighbouring voxels and their texel requests fall into a handful of 32-B sectors
-// (L1 hit rate 98 % on the 256^3 u8 volume). All tiles of a frame go out in ONE launch (grid.z = tile), or the
-// cameras of up to 8 consecutive frames of a sweep (grid.z = frame): one 1080p frame cannot fill 148 SMs.
+// (L1 hit rate 94-98 % on the 256^3 u8 volume). All tiles of a frame go out in ONE launch (grid.z = tile), or the
+// cameras of up to VKRT_MAX_BATCH consecutive frames of a sweep (grid.y = frame): one 1080p frame cannot fill 148 SMs.
 // Not a contraction: no tensor cores. Measured limiters (profiles/): instruction issue when skipping is on
-// (SM throughput 86 % of peak with 8 frames per launch), the texture data pipe in the dense case (l1tex 97 %).
+// (issue active 83 %, SM throughput 82 % of peak at 16-30 frames per launch), the texel path in the dense case (l1tex 98 %).
 #include <cstdio>
 #include <cstdlib>
 
