@@ -117,10 +117,12 @@ def sample_volume(vol, q):
     return ((c00 * (1 - fy) + c10 * fy) * (1 - fz) + (c01 * (1 - fy) + c11 * fy) * fz) / 255.0
 
 
-def march(vol, occ, dist_of_ray, eye, d, bb_lo, bb_hi, blind=0):
+def march(vol, occ, dist_of_ray, eye, d, bb_lo, bb_hi, blind=0, join=0):
     """returns per-ray (leaps, samples). dist_of_ray(bz, by, bx, idx) -> distance for the rays `idx`.
     blind = K: a lane that has just evaluated a sample evaluates up to K more without consulting the distance field, inside the
-    same lock-step iteration (evaluating a sample is always exact; only skipping needs the field)."""
+    same lock-step iteration (evaluating a sample is always exact; only skipping needs the field).
+    join = D: in an iteration where some lane of the warp samples anyway, lanes whose distance is <= D sample too instead of
+    leaping (a short leap costs the warp a whole pass through the leap path)."""
     n = len(eye)
     with np.errstate(divide="ignore"):
         inv = 1.0 / d
@@ -158,6 +160,10 @@ def march(vol, occ, dist_of_ray, eye, d, bb_lo, bb_hi, blind=0):
         dd = dist_of_ray(bi[:, 2], bi[:, 1], bi[:, 0], idx)
         dd = np.where(inside, dd, 0)
         lp = dd > 0
+        if join:
+            wid0 = idx // 32
+            samp_warps = np.unique(wid0[~lp])
+            lp &= ~((dd <= join) & np.isin(wid0, samp_warps))
         # leap
         R = BR * dd - BR / 2 - 1e-3
         w = BR * bi + (sg[idx] * R[:, None] + (BR / 2 - q))
