@@ -242,7 +242,7 @@ def main():
             res[name] = (leaps.sum(), samples.sum(), warp_iters.sum(), leaps.reshape(-1, 32).max(axis=1).sum(),
                          samples.reshape(-1, 32).max(axis=1).sum())
             # instruction model of the kernel's loop: head + tail per iteration, leap path, sample path
-            cost = ev[0] * 32 + ev[1] * 26 + ev[2] * 56
+            cost = ev[0] * 29 + ev[1] * 30 + ev[2] * 48  # issue slots of the final build: profiles/loop_sass_r02.md (head + tail, leap + rejoin, sample)
             print(f"frame {fr:3d} {name:7s}: lock-step warp iterations {ev[0]} with-leap {ev[1]} with-sample {ev[2]}  model cost {cost / 1e6:.2f} M warp-inst (x9 per frame)")
             print(f"frame {fr:3d} {name:7s}: lane leaps {leaps.sum():9d}  lane samples {samples.sum():9d}  "
                   f"sum over warps of max-lane iterations {warp_iters.sum():8d}  (max-lane leaps {res[name][3]}, max-lane samples {res[name][4]})")
